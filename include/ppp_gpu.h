@@ -1,0 +1,155 @@
+/* ppp_gpu.h — C ABI of libppp_gpu.so, the B200 (sm_100a) drop-in for the data-parallel geometric
+ * core of tsai0507/PolishPathPlanning.
+ *
+ * The reference has no plugin / FFI boundary: its hot path is a set of C++ member functions that
+ * call PCL/FLANN on class-owned clouds.  Each entry point below replaces the
+ * body of the reference function(s) cited next to it (paths relative to /root/reference); the
+ * adapter classes in polishpathplanning_b200/host/ keep the reference's own signatures and call
+ * these.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the boundary; every function returns PPP_OK (0) or a negative
+ *    ppp_status; ppp_last_error() gives a message (thread-local).
+ *  - "host API": all pointers are HOST memory, calls are synchronous.  "device API" (ppp_dev_*):
+ *    data pointers are DEVICE memory on the context's GPU, work is enqueued on ppp_stream()
+ *    and the call returns without waiting unless stated.
+ *  - points: records of `stride_bytes` (>= 12, multiple of 4) whose first three floats are x,y,z
+ *    (pcl::PointXYZRGB: stride 32, include/Path_Generate.h:32-33).  Non-finite points are kept in
+ *    the index numbering but never returned as neighbours / band members, as PCL does.
+ *  - neighbour order and all ties: ascending (squared distance, point index)  (SURVEY.md App. A.3/A.4).
+ *  - one context per GPU per process; query calls on one cloud are serialised internally, so the
+ *    reference's two sweep threads (src/Path_Alg/path_dynamic_alg.cpp:308-334) may share a handle.
+ *  - there is NO CPU fallback: without a CUDA device ppp_create fails with PPP_ERR_CUDA.
+ */
+#ifndef PPP_GPU_H
+#define PPP_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPP_ABI_VERSION 1
+
+typedef enum ppp_status {
+  PPP_OK = 0,
+  PPP_ERR_INVALID = -1,   /* bad argument */
+  PPP_ERR_CUDA = -2,      /* CUDA runtime error / no device */
+  PPP_ERR_NOMEM = -3,     /* allocation failed */
+  PPP_ERR_CAPACITY = -4,  /* caller-provided output too small; required size reported */
+  PPP_ERR_UNSUPPORTED = -5
+} ppp_status;
+
+typedef struct ppp_ctx ppp_ctx;
+typedef struct ppp_cloud ppp_cloud;
+
+/* flags for the normal estimators */
+#define PPP_COV_PCL110 0u   /* PCL 1.10.0 single-pass E[xx]-E[x]E[x] covariance (default) */
+#define PPP_COV_SHIFTED 1u  /* later PCL: first neighbour subtracted before accumulation */
+
+/* pairing modes of ppp_slice_contours */
+#define PPP_PAIR_GEN2 0 /* variant A: path_generater::insert_point, src/Path_Generation.cpp:107-206 */
+#define PPP_PAIR_SECT 1 /* variant B: SectPath::insert_point,      src/contour_alg.cpp:165-237   */
+
+/* ------------------------------------------------------------------------------------------ */
+/* context                                                                                      */
+int ppp_abi_version(void);
+int ppp_create(int device, ppp_ctx** out);
+void ppp_destroy(ppp_ctx* ctx);
+const char* ppp_last_error(void);
+void* ppp_stream(ppp_ctx* ctx); /* cudaStream_t all work of this context is enqueued on */
+int ppp_sync(ppp_ctx* ctx);
+/* pinned host staging buffers (optional; any host memory is accepted by the host API) */
+void* ppp_host_alloc(size_t bytes);
+void ppp_host_free(void* p);
+/* Number of kernels this library has launched on the context since creation (bench gpu_launches). */
+int64_t ppp_launch_count(ppp_ctx* ctx);
+/* CUDA-event timing on the context's stream: tag 0..15; begin/end bracket a region, read returns
+ * the accumulated milliseconds and number of regions since the last reset (synchronises). */
+int ppp_timer_begin(ppp_ctx* ctx, int tag);
+int ppp_timer_end(ppp_ctx* ctx, int tag);
+int ppp_timer_read(ppp_ctx* ctx, int tag, double* total_ms, int64_t* regions, int reset);
+/* Per-kernel device time of the library's own kernels (CUDA events around each launch while
+ * enabled). names: ';'-separated "name=ms_total:launches" written into buf. */
+int ppp_kernel_profile(ppp_ctx* ctx, int enable);
+int ppp_kernel_profile_read(ppp_ctx* ctx, char* buf, size_t cap, int reset);
+
+/* ------------------------------------------------------------------------------------------ */
+/* cloud = device-resident copy + spatial index.
+ * Replaces: pcl::KdTreeFLANN::setInputCloud (Set_kdtree, src/Path_Generation.cpp:335-338,695;
+ * src/contour_alg.cpp:292), the private search::KdTree inside NormalEstimation
+ * (src/Path_Generation.cpp:326-327) and pcl::getMinMax3D (src/Path_Generation.cpp:293,709). */
+int ppp_cloud_upload(ppp_ctx* ctx, const void* pts_host, size_t n, size_t stride_bytes, ppp_cloud** out);
+int ppp_dev_cloud_attach(ppp_ctx* ctx, const void* pts_dev, size_t n, size_t stride_bytes, ppp_cloud** out);
+int ppp_cloud_free(ppp_cloud* cloud);
+int64_t ppp_cloud_size(const ppp_cloud* cloud);
+int ppp_cloud_bbox(const ppp_cloud* cloud, float min_xyz[3], float max_xyz[3]); /* getMinMax3D */
+/* Optional tuning: cell size (same unit as the points) used by the next index build for
+ * k-searches; 0 = automatic from the cloud's surface density. */
+int ppp_cloud_set_cell_hint(ppp_cloud* cloud, float cell_size);
+
+/* ------------------------------------------------------------------------------------------ */
+/* neighbour searches.  q == NULL: the cloud's own points are the queries (nq ignored).
+ * Replaces pcl::KdTreeFLANN::nearestKSearch / radiusSearch call sites.       */
+int ppp_knn(ppp_cloud* cloud, const float* q, size_t nq, size_t q_stride_bytes, int k,
+            int32_t* idx_out /* nq*k, -1 padded */, float* d2_out /* nullable */);
+/* two-call sizing: idx_out == NULL writes counts only; otherwise offsets (nq+1) must be the
+ * exclusive scan of counts and lists are written sorted by (d2, idx). Membership d2 < (float)(r*r). */
+int ppp_radius(ppp_cloud* cloud, const float* q, size_t nq, size_t q_stride_bytes, double radius,
+               int32_t* counts, const int64_t* offsets, int32_t* idx_out, float* d2_out);
+
+/* ------------------------------------------------------------------------------------------ */
+/* estimate_normal(): pcl::NormalEstimation::compute (src/Path_Generation.cpp:323-333,
+ * src/contour_alg.cpp:142-151, src/slicing_method.cpp:204-214).  normals_out: n records of
+ * normal_stride_bytes; stride 32 = pcl::Normal {nx,ny,nz,0, curvature,0,0,0}; stride 16 = {nx,ny,nz,curvature}.
+ * < 3 neighbours or a non-finite point => all four values NaN.  knn_idx_out (n*k) nullable.    */
+int ppp_normals_knn(ppp_cloud* cloud, int k, const float viewpoint[3], unsigned flags, void* normals_out,
+                    size_t normal_stride_bytes, int32_t* knn_idx_out);
+int ppp_normals_radius(ppp_cloud* cloud, double radius, const float viewpoint[3], unsigned flags,
+                       void* normals_out, size_t normal_stride_bytes);
+
+/* ------------------------------------------------------------------------------------------ */
+/* rangedX_index() for ALL planes in one pass: pcl::PassThrough on "x"
+ * (src/Path_Generation.cpp:94-104, src/contour_alg.cpp:153-163).  truncate_center != 0 reproduces
+ * the reference's int-truncated band centre: limits (float)(-hw + (int)x), (float)(hw + (int)x).
+ * offsets: S+1.  idx_out == NULL: sizing call (offsets only).  idx_cap = capacity of idx_out.  */
+int ppp_slice_bands(ppp_cloud* cloud, const float* plane_x, int S, float half_width, int truncate_center,
+                    int64_t* offsets, int32_t* idx_out, int64_t idx_cap);
+
+/* rangedX_index + insert_point + the map->array flattening of path_track / OnePath
+ * (src/Path_Generation.cpp:107-206,659-676; src/contour_alg.cpp:165-264) for all planes.
+ * Output per slice: nodes in ascending y (std::map order, last insertion wins on equal y), as the
+ * three double arrays the reference hands to Spline(n, y, x, z) (include/Spline.h:10-20).
+ * node_offsets: S+1.  y/x/z capacity node_cap (total); on PPP_ERR_CAPACITY node_offsets[S] holds the
+ * required total.  y == NULL: sizing call.                                                     */
+int ppp_slice_contours(ppp_cloud* cloud, const float* plane_x, int S, float half_width, int truncate_center,
+                       int pairing_mode, int64_t* node_offsets, double* y, double* x, double* z,
+                       int64_t node_cap);
+
+/* ------------------------------------------------------------------------------------------ */
+/* device API (results stay in HBM; used by bench.py's device-resident leg and the multi-GPU
+ * sharding in polishpathplanning_b200/parallel.py).  Query sub-ranges are given in SORTED
+ * (cell-major) order so that a rank's share is spatially compact: [first, first+count).        */
+int ppp_dev_index(ppp_cloud* cloud, int k_hint, double radius_hint); /* (re)build the grid now */
+int ppp_dev_normals_knn(ppp_cloud* cloud, int k, const float viewpoint[3], unsigned flags, int64_t first,
+                        int64_t count, float* normals_dev, size_t normal_stride_bytes,
+                        int32_t* knn_idx_dev /* n*k rows by ORIGINAL index, nullable */,
+                        float* knn_d2_dev /* nullable */);
+int ppp_dev_normals_radius(ppp_cloud* cloud, double radius, const float viewpoint[3], unsigned flags,
+                           int64_t first, int64_t count, float* normals_dev, size_t normal_stride_bytes);
+/* contours for the planes [0,S) given on the HOST (small); results in device buffers owned by
+ * the cloud until the next call; pointers returned through the out arguments. Synchronises once
+ * to learn the node total.  */
+int ppp_dev_slice_contours(ppp_cloud* cloud, const float* plane_x_host, int S, float half_width,
+                           int truncate_center, int pairing_mode, const int64_t** node_offsets_dev,
+                           const double** y_dev, const double** x_dev, const double** z_dev,
+                           int64_t* total_nodes, int64_t* total_band_members);
+/* original index of the point at sorted position p (device array of n int32) */
+const int32_t* ppp_dev_sorted_order(ppp_cloud* cloud);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPP_GPU_H */

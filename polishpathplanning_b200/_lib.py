@@ -1,0 +1,92 @@
+"""ctypes binding of libppp_gpu.so (include/ppp_gpu.h).  Fails loudly when the library is missing:
+there is no CPU or PyTorch fallback for the hot path."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libppp_gpu.so")
+
+PPP_OK = 0
+PPP_ERR_INVALID = -1
+PPP_ERR_CUDA = -2
+PPP_ERR_NOMEM = -3
+PPP_ERR_CAPACITY = -4
+PPP_ERR_UNSUPPORTED = -5
+
+PPP_COV_PCL110 = 0
+PPP_COV_SHIFTED = 1
+PPP_PAIR_GEN2 = 0
+PPP_PAIR_SECT = 1
+
+_vp = C.c_void_p
+_f32p = C.POINTER(C.c_float)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+_f64p = C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); every symbol include/ppp_gpu.h declares
+SIGNATURES = {
+    "ppp_abi_version": (C.c_int, []),
+    "ppp_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "ppp_destroy": (None, [_vp]),
+    "ppp_last_error": (C.c_char_p, []),
+    "ppp_stream": (_vp, [_vp]),
+    "ppp_sync": (C.c_int, [_vp]),
+    "ppp_host_alloc": (_vp, [C.c_size_t]),
+    "ppp_host_free": (None, [_vp]),
+    "ppp_launch_count": (C.c_int64, [_vp]),
+    "ppp_timer_begin": (C.c_int, [_vp, C.c_int]),
+    "ppp_timer_end": (C.c_int, [_vp, C.c_int]),
+    "ppp_timer_read": (C.c_int, [_vp, C.c_int, _f64p, _i64p, C.c_int]),
+    "ppp_kernel_profile": (C.c_int, [_vp, C.c_int]),
+    "ppp_kernel_profile_read": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.c_int]),
+    "ppp_cloud_upload": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.POINTER(_vp)]),
+    "ppp_dev_cloud_attach": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.POINTER(_vp)]),
+    "ppp_cloud_free": (C.c_int, [_vp]),
+    "ppp_cloud_size": (C.c_int64, [_vp]),
+    "ppp_cloud_bbox": (C.c_int, [_vp, _f32p, _f32p]),
+    "ppp_cloud_set_cell_hint": (C.c_int, [_vp, C.c_float]),
+    "ppp_knn": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp, _vp]),
+    "ppp_radius": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.c_double, _vp, _vp, _vp, _vp]),
+    "ppp_normals_knn": (C.c_int, [_vp, C.c_int, _f32p, C.c_uint, _vp, C.c_size_t, _vp]),
+    "ppp_normals_radius": (C.c_int, [_vp, C.c_double, _f32p, C.c_uint, _vp, C.c_size_t]),
+    "ppp_slice_bands": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, _vp, _vp, C.c_int64]),
+    "ppp_slice_contours": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, C.c_int, _vp, _vp, _vp, _vp, C.c_int64]),
+    "ppp_dev_index": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "ppp_dev_normals_knn": (C.c_int, [_vp, C.c_int, _f32p, C.c_uint, C.c_int64, C.c_int64, _vp, C.c_size_t, _vp, _vp]),
+    "ppp_dev_normals_radius": (C.c_int, [_vp, C.c_double, _f32p, C.c_uint, C.c_int64, C.c_int64, _vp, C.c_size_t]),
+    "ppp_dev_slice_contours": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp),
+                                         C.POINTER(_vp), C.POINTER(_vp), _i64p, _i64p]),
+    "ppp_dev_sorted_order": (_vp, [_vp]),
+}
+
+_lib = None
+
+
+class PPPError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__("libppp_gpu status %d: %s" % (status, msg))
+        self.status = status
+
+
+def load():
+    """Load libppp_gpu.so; raises if it has not been built (python -m polishpathplanning_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "libppp_gpu.so is missing at %s. Build it with `python -m polishpathplanning_b200.build` "
+                "(nvcc, sm_100a). The hot path has no CPU / PyTorch fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status):
+    if status != PPP_OK:
+        raise PPPError(status, load().ppp_last_error().decode("utf-8", "replace"))
+    return status

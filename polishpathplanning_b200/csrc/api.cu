@@ -1,0 +1,480 @@
+// extern "C" surface of libppp_gpu.so (include/ppp_gpu.h): context, cloud handles, host-pointer
+// wrappers around the device pipeline.  No CPU fallback anywhere: without a usable CUDA device
+// ppp_create fails and nothing else can be called.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "ppp_internal.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void ppp_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define LOCK(ctx) std::lock_guard<std::recursive_mutex> _lk((ctx)->mu)
+
+#define REQUIRE(cond, msg)            \
+  do {                                \
+    if (!(cond)) {                    \
+      ppp_set_error("%s: %s", __func__, msg); \
+      return PPP_ERR_INVALID;         \
+    }                                 \
+  } while (0)
+
+extern "C" {
+
+int ppp_abi_version(void) { return PPP_ABI_VERSION; }
+const char* ppp_last_error(void) { return g_err; }
+
+int ppp_create(int device, ppp_ctx** out) {
+  if (!out) { ppp_set_error("ppp_create: out is NULL"); return PPP_ERR_INVALID; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    ppp_set_error("ppp_create: no CUDA device (%s); libppp_gpu has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    cudaGetLastError();
+    return PPP_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { ppp_set_error("ppp_create: device %d out of range [0,%d)", device, ndev); return PPP_ERR_INVALID; }
+  PPP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PPP_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    ppp_set_error("ppp_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return PPP_ERR_UNSUPPORTED;
+  }
+  ppp_ctx* ctx = new ppp_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  PPP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  cudaMemPool_t pool;
+  PPP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;  // keep freed blocks cached: temporaries are re-used every call
+  PPP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  *out = ctx;
+  return PPP_OK;
+}
+
+void ppp_destroy(ppp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->kstats)
+    for (auto& p : kv.second.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  for (int t = 0; t < 16; t++)
+    for (auto& p : ctx->t_pending[t]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+void* ppp_stream(ppp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int ppp_sync(ppp_ctx* ctx) {
+  REQUIRE(ctx, "ctx is NULL");
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PPP_OK;
+}
+
+void* ppp_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+void ppp_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int64_t ppp_launch_count(ppp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ppp_timer_begin(ppp_ctx* ctx, int tag) {
+  REQUIRE(ctx && tag >= 0 && tag < 16, "bad ctx/tag");
+  LOCK(ctx);
+  cudaEvent_t a, b;
+  PPP_CUDA(cudaEventCreate(&a));
+  PPP_CUDA(cudaEventCreate(&b));
+  PPP_CUDA(cudaEventRecord(a, ctx->stream));
+  ctx->t_pending[tag].emplace_back(a, b);
+  return PPP_OK;
+}
+int ppp_timer_end(ppp_ctx* ctx, int tag) {
+  REQUIRE(ctx && tag >= 0 && tag < 16, "bad ctx/tag");
+  LOCK(ctx);
+  REQUIRE(!ctx->t_pending[tag].empty(), "timer_end without timer_begin");
+  PPP_CUDA(cudaEventRecord(ctx->t_pending[tag].back().second, ctx->stream));
+  return PPP_OK;
+}
+int ppp_timer_read(ppp_ctx* ctx, int tag, double* total_ms, int64_t* regions, int reset) {
+  REQUIRE(ctx && tag >= 0 && tag < 16, "bad ctx/tag");
+  LOCK(ctx);
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->t_pending[tag]) {
+    float ms = 0;
+    PPP_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
+    ctx->t_ms[tag] += ms;
+    ctx->t_regions[tag]++;
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  ctx->t_pending[tag].clear();
+  if (total_ms) *total_ms = ctx->t_ms[tag];
+  if (regions) *regions = ctx->t_regions[tag];
+  if (reset) { ctx->t_ms[tag] = 0; ctx->t_regions[tag] = 0; }
+  return PPP_OK;
+}
+
+int ppp_kernel_profile(ppp_ctx* ctx, int enable) {
+  REQUIRE(ctx, "ctx is NULL");
+  LOCK(ctx);
+  ctx->profile = enable != 0;
+  return PPP_OK;
+}
+int ppp_kernel_profile_read(ppp_ctx* ctx, char* buf, size_t cap, int reset) {
+  REQUIRE(ctx && buf && cap > 0, "bad arguments");
+  LOCK(ctx);
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::string s;
+  for (auto& kv : ctx->kstats) {
+    KernelStat& st = kv.second;
+    for (auto& p : st.pending) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) { st.ms += ms; st.launches++; }
+      cudaEventDestroy(p.first);
+      cudaEventDestroy(p.second);
+    }
+    st.pending.clear();
+    char line[256];
+    snprintf(line, sizeof(line), "%s=%.6f:%lld;", kv.first.c_str(), st.ms, (long long)st.launches);
+    s += line;
+  }
+  if (reset) ctx->kstats.clear();
+  snprintf(buf, cap, "%s", s.c_str());
+  return PPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cloud
+// ---------------------------------------------------------------------------------------------
+static int cloud_new(ppp_ctx* ctx, size_t n, ppp_cloud** out) {
+  ppp_cloud* c = new ppp_cloud();
+  c->ctx = ctx;
+  c->n = (int64_t)n;
+  c->grids.reserve(8);
+  *out = c;
+  return PPP_OK;
+}
+
+int ppp_dev_cloud_attach(ppp_ctx* ctx, const void* pts_dev, size_t n, size_t stride_bytes, ppp_cloud** out) {
+  REQUIRE(ctx && out, "ctx/out is NULL");
+  REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride_bytes must be >= 12 and a multiple of 4");
+  REQUIRE(n == 0 || pts_dev, "pts is NULL");
+  REQUIRE(n < 2147483647ull, "at most 2^31-2 points (int32 indices, as PCL)");
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  ppp_cloud* c = nullptr;
+  PPP_TRY(cloud_new(ctx, n, &c));
+  int st = cloud_ingest(c, pts_dev, stride_bytes);
+  if (st != PPP_OK) { ppp_cloud_free(c); return st; }
+  *out = c;
+  return PPP_OK;
+}
+
+int ppp_cloud_upload(ppp_ctx* ctx, const void* pts_host, size_t n, size_t stride_bytes, ppp_cloud** out) {
+  REQUIRE(ctx && out, "ctx/out is NULL");
+  REQUIRE(stride_bytes >= 12 && stride_bytes % 4 == 0, "stride_bytes must be >= 12 and a multiple of 4");
+  REQUIRE(n == 0 || pts_host, "pts is NULL");
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  void* raw = nullptr;
+  PPP_TRY(dev_alloc(ctx, (char**)&raw, std::max<size_t>(n * stride_bytes, 16)));
+  if (n) PPP_CUDA(cudaMemcpyAsync(raw, pts_host, n * stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int st = ppp_dev_cloud_attach(ctx, raw, n, stride_bytes, out);
+  dev_free(ctx, (char*)raw);
+  return st;
+}
+
+int ppp_cloud_free(ppp_cloud* c) {
+  if (!c) return PPP_OK;
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  cudaSetDevice(ctx->device);
+  dev_free(ctx, c->xyz4);
+  for (auto& g : c->grids) { dev_free(ctx, g.sorted); dev_free(ctx, g.cell_start); dev_free(ctx, g.order); }
+  dev_free(ctx, c->c_node_off); dev_free(ctx, c->c_y); dev_free(ctx, c->c_x); dev_free(ctx, c->c_z);
+  delete c;
+  return PPP_OK;
+}
+
+int64_t ppp_cloud_size(const ppp_cloud* c) { return c ? c->n : -1; }
+
+int ppp_cloud_bbox(const ppp_cloud* c, float mn[3], float mx[3]) {
+  REQUIRE(c && mn && mx, "NULL argument");
+  for (int d = 0; d < 3; d++) { mn[d] = c->bmin[d]; mx[d] = c->bmax[d]; }
+  return PPP_OK;
+}
+
+int ppp_cloud_set_cell_hint(ppp_cloud* c, float cell) {
+  REQUIRE(c, "cloud is NULL");
+  REQUIRE(cell >= 0 && std::isfinite(cell), "cell size must be >= 0");
+  c->cell_hint = cell;
+  return PPP_OK;
+}
+
+const int32_t* ppp_dev_sorted_order(ppp_cloud* c) {
+  if (!c || c->grids.empty()) return nullptr;
+  return c->grids.back().order;
+}
+
+int ppp_dev_index(ppp_cloud* c, int k_hint, double radius_hint) {
+  REQUIRE(c, "cloud is NULL");
+  LOCK(c->ctx);
+  PPP_CUDA(cudaSetDevice(c->ctx->device));
+  GridStore* g;
+  double h = radius_hint > 0 ? cloud_cell_for_radius(c, radius_hint) : cloud_cell_for_k(c, k_hint > 0 ? k_hint : 16);
+  return cloud_get_grid(c, h, &g);
+}
+
+// ---------------------------------------------------------------------------------------------
+// device-level pipeline entries
+// ---------------------------------------------------------------------------------------------
+int ppp_dev_normals_knn(ppp_cloud* c, int k, const float vp[3], unsigned flags, int64_t first, int64_t count,
+                        float* normals_dev, size_t normal_stride_bytes, int32_t* knn_idx_dev, float* knn_d2_dev) {
+  REQUIRE(c, "cloud is NULL");
+  REQUIRE(k >= 1, "k must be >= 1");
+  REQUIRE(normal_stride_bytes >= 16 && normal_stride_bytes % 4 == 0, "normal stride must be >= 16 and a multiple of 4");
+  REQUIRE(normals_dev || knn_idx_dev, "nothing to compute");
+  LOCK(c->ctx);
+  PPP_CUDA(cudaSetDevice(c->ctx->device));
+  if (count < 0) count = c->n_finite - first;
+  REQUIRE(first >= 0 && first + count <= c->n_finite, "query range outside the indexed points");
+  GridStore* g;
+  PPP_TRY(cloud_get_grid(c, cloud_cell_for_k(c, k), &g));
+  return knn_launch(c, *g, nullptr, count, 0, first, k, knn_idx_dev, knn_d2_dev, normals_dev != nullptr, vp, flags,
+                    normals_dev, (int)(normal_stride_bytes / 4));
+}
+
+int ppp_dev_normals_radius(ppp_cloud* c, double radius, const float vp[3], unsigned flags, int64_t first, int64_t count,
+                           float* normals_dev, size_t normal_stride_bytes) {
+  REQUIRE(c && normals_dev, "NULL argument");
+  REQUIRE(radius > 0 && std::isfinite(radius), "radius must be > 0");
+  REQUIRE(normal_stride_bytes >= 16 && normal_stride_bytes % 4 == 0, "normal stride must be >= 16 and a multiple of 4");
+  LOCK(c->ctx);
+  PPP_CUDA(cudaSetDevice(c->ctx->device));
+  if (count < 0) count = c->n_finite - first;
+  REQUIRE(first >= 0 && first + count <= c->n_finite, "query range outside the indexed points");
+  GridStore* g;
+  PPP_TRY(cloud_get_grid(c, cloud_cell_for_radius(c, radius), &g));
+  float r2 = (float)(radius * radius);  // [upstream] pcl::KdTreeFLANN::radiusSearch
+  return normals_radius_launch(c, *g, first, count, r2, vp, flags, normals_dev, (int)(normal_stride_bytes / 4));
+}
+
+static int pick_any_grid(ppp_cloud* c, GridStore** g) {
+  if (!c->grids.empty()) { *g = &c->grids.back(); return PPP_OK; }
+  return cloud_get_grid(c, cloud_cell_for_k(c, 16), g);
+}
+
+int ppp_dev_slice_contours(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center,
+                           int pairing_mode, const int64_t** node_offsets_dev, const double** y_dev,
+                           const double** x_dev, const double** z_dev, int64_t* total_nodes, int64_t* total_members) {
+  REQUIRE(c, "cloud is NULL");
+  REQUIRE(S >= 0 && (S == 0 || plane_x_host), "bad planes");
+  REQUIRE(pairing_mode == PPP_PAIR_GEN2 || pairing_mode == PPP_PAIR_SECT, "unknown pairing mode");
+  REQUIRE(half_width >= 0 && std::isfinite(half_width), "half_width must be >= 0");
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  int64_t* boff = nullptr; int32_t* bidx = nullptr; float* planes = nullptr; int64_t M = 0;
+  PPP_TRY(bands_launch(c, plane_x_host, S, half_width, truncate_center, &boff, &bidx, &M, &planes));
+  GridStore* g;
+  int st = pick_any_grid(c, &g);
+  int64_t total = 0;
+  if (st == PPP_OK) st = contours_launch(c, *g, planes, S, half_width, truncate_center, boff, bidx, M, nullptr, pairing_mode, &total);
+  dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, planes);
+  if (st != PPP_OK) return st;
+  if (node_offsets_dev) *node_offsets_dev = c->c_node_off;
+  if (y_dev) *y_dev = c->c_y;
+  if (x_dev) *x_dev = c->c_x;
+  if (z_dev) *z_dev = c->c_z;
+  if (total_nodes) *total_nodes = total;
+  if (total_members) *total_members = M;
+  return PPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-pointer API
+// ---------------------------------------------------------------------------------------------
+int ppp_knn(ppp_cloud* c, const float* q, size_t nq, size_t q_stride_bytes, int k, int32_t* idx_out, float* d2_out) {
+  REQUIRE(c && idx_out, "NULL argument");
+  REQUIRE(k >= 1, "k must be >= 1");
+  REQUIRE(!q || (q_stride_bytes >= 12 && q_stride_bytes % 4 == 0), "query stride must be >= 12 and a multiple of 4");
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  GridStore* g;
+  PPP_TRY(cloud_get_grid(c, cloud_cell_for_k(c, k), &g));
+  int64_t rows = q ? (int64_t)nq : c->n;
+  int32_t* idx_d = nullptr; float* d2_d = nullptr; float* q_d = nullptr;
+  PPP_TRY(dev_alloc(ctx, &idx_d, (size_t)rows * k));
+  if (d2_out) PPP_TRY(dev_alloc(ctx, &d2_d, (size_t)rows * k));
+  int st;
+  if (q) {
+    PPP_TRY(dev_alloc(ctx, (char**)&q_d, nq * q_stride_bytes + 16));
+    if (nq) PPP_CUDA(cudaMemcpyAsync(q_d, q, nq * q_stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    st = knn_launch(c, *g, q_d, (int64_t)nq, (int)(q_stride_bytes / 4), 0, k, idx_d, d2_d, false, nullptr, 0, nullptr, 0);
+  } else {
+    st = knn_launch(c, *g, nullptr, c->n_finite, 0, 0, k, idx_d, d2_d, false, nullptr, 0, nullptr, 0);
+  }
+  if (st == PPP_OK && rows) {
+    PPP_CUDA(cudaMemcpyAsync(idx_out, idx_d, (size_t)rows * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d2_out) PPP_CUDA(cudaMemcpyAsync(d2_out, d2_d, (size_t)rows * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, idx_d); dev_free(ctx, d2_d); dev_free(ctx, (char*)q_d);
+  if (st != PPP_OK) return st;
+  PPP_CUDA(e);
+  return PPP_OK;
+}
+
+int ppp_radius(ppp_cloud* c, const float* q, size_t nq, size_t q_stride_bytes, double radius, int32_t* counts,
+               const int64_t* offsets, int32_t* idx_out, float* d2_out) {
+  REQUIRE(c && counts, "NULL argument");
+  REQUIRE(radius > 0 && std::isfinite(radius), "radius must be > 0");
+  REQUIRE(!q || (q_stride_bytes >= 12 && q_stride_bytes % 4 == 0), "query stride must be >= 12 and a multiple of 4");
+  REQUIRE(!idx_out || offsets, "offsets required with idx_out");
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  GridStore* g;
+  PPP_TRY(cloud_get_grid(c, cloud_cell_for_radius(c, radius), &g));
+  float r2 = (float)(radius * radius);
+  int64_t rows = q ? (int64_t)nq : c->n;
+  int64_t nquery = q ? (int64_t)nq : c->n_finite;
+  float* q_d = nullptr;
+  if (q) {
+    PPP_TRY(dev_alloc(ctx, (char**)&q_d, nq * q_stride_bytes + 16));
+    if (nq) PPP_CUDA(cudaMemcpyAsync(q_d, q, nq * q_stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int qsf = (int)(q_stride_bytes / 4);
+  int32_t* cnt_d = nullptr;
+  PPP_TRY(dev_alloc(ctx, &cnt_d, (size_t)rows));
+  int st = PPP_OK;
+  if (!idx_out) {
+    int mx = radius_count_launch(c, *g, q_d, nquery, qsf, 0, r2, cnt_d);
+    if (mx < 0) st = mx;
+    if (st == PPP_OK && rows) PPP_CUDA(cudaMemcpyAsync(counts, cnt_d, (size_t)rows * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    int64_t total = offsets[rows];
+    int64_t* off_d = nullptr; int32_t* idx_d = nullptr; float* d2_d = nullptr;
+    PPP_TRY(dev_alloc(ctx, &off_d, (size_t)rows + 1));
+    PPP_TRY(dev_alloc(ctx, &idx_d, (size_t)std::max<int64_t>(total, 1)));
+    if (d2_out) PPP_TRY(dev_alloc(ctx, &d2_d, (size_t)std::max<int64_t>(total, 1)));
+    PPP_CUDA(cudaMemcpyAsync(off_d, offsets, ((size_t)rows + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    st = radius_fill_launch(c, *g, q_d, nquery, qsf, 0, r2, off_d, idx_d, d2_d);
+    if (st == PPP_OK && total) {
+      PPP_CUDA(cudaMemcpyAsync(idx_out, idx_d, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      if (d2_out) PPP_CUDA(cudaMemcpyAsync(d2_out, d2_d, (size_t)total * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, off_d); dev_free(ctx, idx_d); dev_free(ctx, d2_d);
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, cnt_d); dev_free(ctx, (char*)q_d);
+  if (st != PPP_OK) return st;
+  PPP_CUDA(e);
+  return PPP_OK;
+}
+
+static int normals_host(ppp_cloud* c, int k, double radius, const float vp[3], unsigned flags, void* normals_out,
+                        size_t stride, int32_t* knn_idx_out) {
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  float* n_d = nullptr; int32_t* idx_d = nullptr;
+  size_t nbytes = (size_t)c->n * stride;
+  PPP_TRY(dev_alloc(ctx, (char**)&n_d, std::max<size_t>(nbytes, 16)));
+  if (stride > 32) PPP_CUDA(cudaMemsetAsync(n_d, 0, nbytes, ctx->stream));
+  if (knn_idx_out) PPP_TRY(dev_alloc(ctx, &idx_d, (size_t)c->n * k));
+  int st = k > 0 ? ppp_dev_normals_knn(c, k, vp, flags, 0, -1, n_d, stride, idx_d, nullptr)
+                 : ppp_dev_normals_radius(c, radius, vp, flags, 0, -1, n_d, stride);
+  if (st == PPP_OK && c->n) {
+    PPP_CUDA(cudaMemcpyAsync(normals_out, n_d, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (knn_idx_out) PPP_CUDA(cudaMemcpyAsync(knn_idx_out, idx_d, (size_t)c->n * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, (char*)n_d); dev_free(ctx, idx_d);
+  if (st != PPP_OK) return st;
+  PPP_CUDA(e);
+  return PPP_OK;
+}
+
+int ppp_normals_knn(ppp_cloud* c, int k, const float vp[3], unsigned flags, void* normals_out, size_t stride,
+                    int32_t* knn_idx_out) {
+  REQUIRE(c && normals_out, "NULL argument");
+  REQUIRE(k >= 1, "k must be >= 1");
+  REQUIRE(stride >= 16 && stride % 4 == 0, "normal stride must be >= 16 and a multiple of 4");
+  return normals_host(c, k, 0.0, vp, flags, normals_out, stride, knn_idx_out);
+}
+
+int ppp_normals_radius(ppp_cloud* c, double radius, const float vp[3], unsigned flags, void* normals_out, size_t stride) {
+  REQUIRE(c && normals_out, "NULL argument");
+  REQUIRE(radius > 0 && std::isfinite(radius), "radius must be > 0");
+  REQUIRE(stride >= 16 && stride % 4 == 0, "normal stride must be >= 16 and a multiple of 4");
+  return normals_host(c, 0, radius, vp, flags, normals_out, stride, nullptr);
+}
+
+int ppp_slice_bands(ppp_cloud* c, const float* plane_x, int S, float half_width, int truncate_center, int64_t* offsets,
+                    int32_t* idx_out, int64_t idx_cap) {
+  REQUIRE(c && offsets, "NULL argument");
+  REQUIRE(S >= 0 && (S == 0 || plane_x), "bad planes");
+  REQUIRE(half_width >= 0 && std::isfinite(half_width), "half_width must be >= 0");
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  int64_t* boff = nullptr; int32_t* bidx = nullptr; float* planes = nullptr; int64_t M = 0;
+  PPP_TRY(bands_launch(c, plane_x, S, half_width, truncate_center, &boff, &bidx, &M, &planes));
+  int st = PPP_OK;
+  PPP_CUDA(cudaMemcpyAsync(offsets, boff, ((size_t)S + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (idx_out) {
+    if (idx_cap < M) { ppp_set_error("ppp_slice_bands: idx_cap %lld < required %lld", (long long)idx_cap, (long long)M); st = PPP_ERR_CAPACITY; }
+    else if (M) PPP_CUDA(cudaMemcpyAsync(idx_out, bidx, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, planes);
+  PPP_CUDA(e);
+  return st;
+}
+
+int ppp_slice_contours(ppp_cloud* c, const float* plane_x, int S, float half_width, int truncate_center, int pairing_mode,
+                       int64_t* node_offsets, double* y, double* x, double* z, int64_t node_cap) {
+  REQUIRE(c && node_offsets, "NULL argument");
+  REQUIRE(!y || (x && z), "y, x, z must be given together");
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  const int64_t* off_d; const double *y_d, *x_d, *z_d; int64_t total = 0, M = 0;
+  PPP_TRY(ppp_dev_slice_contours(c, plane_x, S, half_width, truncate_center, pairing_mode, &off_d, &y_d, &x_d, &z_d, &total, &M));
+  PPP_CUDA(cudaMemcpyAsync(node_offsets, off_d, ((size_t)S + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  int st = PPP_OK;
+  if (y) {
+    if (node_cap < total) {
+      ppp_set_error("ppp_slice_contours: node_cap %lld < required %lld", (long long)node_cap, (long long)total);
+      st = PPP_ERR_CAPACITY;
+    } else if (total) {
+      PPP_CUDA(cudaMemcpyAsync(y, y_d, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      PPP_CUDA(cudaMemcpyAsync(x, x_d, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      PPP_CUDA(cudaMemcpyAsync(z, z_d, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return st;
+}
+
+}  // extern "C"

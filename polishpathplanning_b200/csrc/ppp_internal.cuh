@@ -1,0 +1,172 @@
+// Internal declarations shared by the translation units of libppp_gpu.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ppp_gpu.h"
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void ppp_set_error(const char* fmt, ...);
+
+#define PPP_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ppp_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));      \
+      return PPP_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define PPP_TRY(call)              \
+  do {                             \
+    int _s = (call);               \
+    if (_s != PPP_OK) return _s;   \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// context / cloud
+// ---------------------------------------------------------------------------------------------
+struct KernelStat {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  double ms = 0;
+  int64_t launches = 0;
+};
+
+struct ppp_ctx {
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  std::recursive_mutex mu;
+  int64_t launches = 0;
+  bool profile = false;
+  std::map<std::string, KernelStat> kstats;
+  cudaEvent_t t_begin[16] = {}, t_end[16] = {};
+  double t_ms[16] = {};
+  int64_t t_regions[16] = {};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> t_pending[16];
+};
+
+// Device-side view of the column grid (passed by value to kernels).
+// Cells tile the two largest-extent axes (u, v) of the cloud; a cell row (fixed v) is contiguous
+// in `sorted`, so the candidates of a query are (2R+1) contiguous ranges.
+struct GridView {
+  const float4* sorted;       // n_sorted records: x, y, z, __int_as_float(original index)
+  const int32_t* cell_start;  // nu*nv + 1
+  int nu, nv;                 // cells along u (fastest) and v
+  int au, av;                 // which of x(0) y(1) z(2) are u and v
+  float min_u, min_v;
+  float inv_h, h;
+  float slack;                // rounding slack (same unit as h) subtracted from ring bounds
+  int n_sorted;
+};
+
+struct GridStore {
+  GridView v{};
+  float4* sorted = nullptr;
+  int32_t* cell_start = nullptr;
+  int32_t* order = nullptr;  // original index per sorted position
+  double h = 0;
+};
+
+struct ppp_cloud {
+  ppp_ctx* ctx = nullptr;
+  int64_t n = 0;
+  int64_t n_finite = 0;
+  float4* xyz4 = nullptr;  // original order, w = 0 (finite) / NaN (non-finite point)
+  float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
+  double density = 0;  // finite points per unit area of the (u, v) bounding rectangle
+  int au = 0, av = 1;
+  float cell_hint = 0;
+  std::vector<GridStore> grids;
+  // results of the last ppp_dev_slice_contours (owned by the cloud)
+  int64_t* c_node_off = nullptr;
+  double *c_y = nullptr, *c_x = nullptr, *c_z = nullptr;
+  int64_t c_cap = 0;
+  int c_S_cap = 0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// launch wrapper: counts launches, optional per-kernel CUDA-event timing
+// ---------------------------------------------------------------------------------------------
+struct LaunchScope {
+  ppp_ctx* ctx;
+  const char* name;
+  cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(ppp_ctx* c, const char* n) : ctx(c), name(n) {
+    ctx->launches++;
+    if (ctx->profile) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, ctx->stream);
+    }
+  }
+  ~LaunchScope() {
+    if (a) {
+      cudaEventRecord(b, ctx->stream);
+      ctx->kstats[name].pending.emplace_back(a, b);
+    }
+  }
+};
+
+// `kernel` must be a plain identifier (bind template instantiations to a local `auto kern = ...`).
+#define PPP_LAUNCH(ctx, name, kernel, grid, block, smem, ...)                             \
+  do {                                                                                    \
+    LaunchScope _ls((ctx), (name));                                                       \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                       \
+  } while (0)
+
+#define PPP_CHECK_LAUNCH() PPP_CUDA(cudaGetLastError())
+
+template <typename T>
+int dev_alloc(ppp_ctx* ctx, T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream);
+  if (e != cudaSuccess) {
+    ppp_set_error("cudaMallocAsync(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e));
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? PPP_ERR_NOMEM : PPP_ERR_CUDA;
+  }
+  return PPP_OK;
+}
+template <typename T>
+void dev_free(ppp_ctx* ctx, T* p) {
+  if (p) cudaFreeAsync((void*)p, ctx->stream);
+}
+
+// scan.cu
+int scan_exclusive_i32(ppp_ctx* ctx, const int32_t* in, int32_t* out, int64_t n);       // out[n] = total too (n+1 outputs)
+int scan_exclusive_i32_to_i64(ppp_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);  // n+1 outputs
+
+// grid.cu
+int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes);
+int cloud_get_grid(ppp_cloud* c, double h, GridStore** out);
+double cloud_cell_for_k(const ppp_cloud* c, int k);
+double cloud_cell_for_radius(const ppp_cloud* c, double r);
+
+// knn.cu
+int knn_launch(ppp_cloud* c, const GridStore& g, const float* q_dev, int64_t nq, int q_stride_f, int64_t first,
+               int k, int32_t* idx_dev, float* d2_dev, bool with_normals, const float vp[3], unsigned flags,
+               float* normals_dev, int normal_stride_f);
+int radius_count_launch(ppp_cloud* c, const GridStore& g, const float* q_dev, int64_t nq, int q_stride_f,
+                        int64_t first, float r2, int32_t* counts_dev);
+int radius_fill_launch(ppp_cloud* c, const GridStore& g, const float* q_dev, int64_t nq, int q_stride_f,
+                       int64_t first, float r2, const int64_t* offsets_dev, int32_t* idx_dev, float* d2_dev);
+int normals_radius_launch(ppp_cloud* c, const GridStore& g, int64_t first, int64_t count, float r2,
+                          const float vp[3], unsigned flags, float* normals_dev, int normal_stride_f);
+
+// slices.cu
+int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center,
+                 int64_t** offsets_dev_out, int32_t** idx_dev_out, int64_t* total_out, float** planes_dev_out);
+int contours_launch(ppp_cloud* c, const GridStore& g, const float* planes_dev, int S, float half_width,
+                    int truncate_center, const int64_t* band_off_dev, const int32_t* band_idx_dev,
+                    int64_t band_total, const int64_t* band_off_host, int mode, int64_t* total_nodes_out);

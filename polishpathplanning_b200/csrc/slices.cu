@@ -1,0 +1,505 @@
+// Plane-slice band extraction for ALL planes in one pass over the cloud, and the per-slice
+// contour: left/right classification, pairing (gen-2 variant A / SectPath variant B),
+// interpolation onto the plane and the std::map ascending-y ordering.
+// Replaces rangedX_index (src/Path_Generation.cpp:94-104; src/contour_alg.cpp:153-163),
+// insert_point (src/Path_Generation.cpp:107-206; src/contour_alg.cpp:165-237) and the map ->
+// array flattening in path_track / OnePath (src/Path_Generation.cpp:659-676; src/contour_alg.cpp:240-257).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "ppp_device.cuh"
+
+namespace {
+
+constexpr int CT_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------
+// bands
+// ---------------------------------------------------------------------------------------------
+struct BandSet {
+  const float* lo;      // sorted ascending (NaN planes last, never matched)
+  const float* hi;      // same order
+  const int32_t* slice; // original slice number of sorted entry
+  int S;
+};
+
+// slices containing x form the contiguous sorted range [first hi >= x, first lo > x)
+__device__ __forceinline__ void band_range(const BandSet& b, float x, int& first, int& last) {
+  int l = 0, r = b.S;
+  while (l < r) { int m = (l + r) >> 1; if (__ldg(b.lo + m) <= x) l = m + 1; else r = m; }
+  last = l;  // exclusive
+  l = 0; r = b.S;
+  while (l < r) { int m = (l + r) >> 1; if (__ldg(b.hi + m) < x) l = m + 1; else r = m; }
+  first = l;
+}
+
+// PassThrough: finite point, !(x < lo || x > hi).  Pass 1 counts, pass 2 fills (unordered),
+// then each band is sorted by point index (PassThrough returns ascending indices).
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_band_scan(BandSet b, const float4* __restrict__ xyz4, int64_t n,
+                                                   int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
+                                                   int32_t* __restrict__ idx_out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = __ldg(xyz4 + i);
+  if (p.w != p.w) return;
+  int f, l;
+  band_range(b, p.x, f, l);
+  for (int t = f; t < l; t++) {
+    // lo/hi sorted together only when all bands have one width; re-test to stay exact otherwise
+    if (p.x < __ldg(b.lo + t) || p.x > __ldg(b.hi + t)) continue;
+    int s = __ldg(b.slice + t);
+    int pos = atomicAdd(counts + s, 1);
+    if (FILL) idx_out[offsets[s] + pos] = (int32_t)i;
+  }
+}
+
+// Sorting network on a (possibly non power-of-two) array with virtual +inf padding: every
+// compare-exchange puts the minimum at the lower index, partners beyond n are skipped.
+template <typename T>
+__device__ void cta_sort(T* a, int n) {
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      int l = i ^ (k - 1);
+      if (l > i && l < n) { T x = a[i], y = a[l]; if (y < x) { a[i] = y; a[l] = x; } }
+    }
+    __syncthreads();
+    for (int j = k >> 2; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int l = i ^ j;
+        if (l > i && l < n) { T x = a[i], y = a[l]; if (y < x) { a[i] = y; a[l] = x; } }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CT_THREADS) k_band_sort(const int64_t* __restrict__ offsets, int32_t* __restrict__ idx, int smem_cap) {
+  extern __shared__ int32_t s_idx[];
+  int s = blockIdx.x;
+  int64_t o = offsets[s];
+  int n = (int)(offsets[s + 1] - o);
+  if (n <= 1) return;
+  if (n <= smem_cap) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_idx[i] = idx[o + i];
+    __syncthreads();
+    cta_sort(s_idx, n);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) idx[o + i] = s_idx[i];
+  } else {
+    cta_sort(idx + o, n);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// contours
+// ---------------------------------------------------------------------------------------------
+struct ContourParams {
+  GridView g;
+  const float4* xyz4;
+  const float* planes;   // S, original order
+  const float* lo;       // S, original order
+  const float* hi;
+  const int64_t* band_off;
+  const int32_t* band_idx;
+  int mode;              // PPP_PAIR_GEN2 / PPP_PAIR_SECT
+  // scratch, all indexed by band offset
+  int32_t *El, *Er;      // left / right members (ascending index)
+  u64* keys;
+  float *ys, *zs;
+  int32_t *posR, *posL, *lp, *rp;
+  unsigned char *fl, *fr;
+  double *ty, *tz;       // un-compacted nodes per slice
+  int32_t* n_nodes;      // S
+};
+
+__device__ __forceinline__ uint32_t f2ord_dev(float f) {
+  uint32_t b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// CTA-wide exclusive prefix count of a per-thread flag over the current tile; `running` is
+// advanced by the tile total (kept identical in every thread).
+__device__ __forceinline__ int cta_flag_rank(bool flag, int* s_warp, int& running) {
+  unsigned m = __ballot_sync(0xffffffffu, flag);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) s_warp[w] = __popc(m);
+  __syncthreads();
+  int base = 0, tot = 0;
+  for (int i = 0; i < CT_THREADS / 32; i++) {
+    int c = s_warp[i];
+    if (i < w) base += c;
+    tot += c;
+  }
+  int r = running + base + __popc(m & ((1u << lane) - 1u));
+  running += tot;
+  __syncthreads();
+  return r;
+}
+
+// Nearest member of one side of the slice (x in [lo,hi]; left: x > plane, right: x < plane).
+// metric 0: flann d2, ties -> lowest index.   (variant B; contract (d2, idx))
+// metric 1: Eigen norm sqrtf(dx^2 + (dy^2 + dz^2)), ties -> highest index (std::map<float,int>
+//           overwrite in src/Path_Generation.cpp:143-150: equal keys keep the last j).
+// Searches the grid ring by ring; gives up after RMAX rings and scans the side's member list.
+__device__ int nn_side(const GridView& g, const float4* __restrict__ xyz4, float qx, float qy, float qz, float lo,
+                       float hi, float plane, bool want_left, int metric, const int32_t* list, int nlist) {
+  if (nlist <= 0) return -1;
+  const int RMAX = 6;
+  u64 best = PPP_KEY_INF;
+  auto consider = [&](float cx, float cy, float cz, int idx) {
+    if (cx < lo || cx > hi) return;
+    if (want_left ? !(cx > plane) : !(cx < plane)) return;
+    u64 key;
+    if (metric == 0) {
+      key = make_key(d2_flann(qx, qy, qz, cx, cy, cz), idx);
+    } else {
+      float dx = __fsub_rn(qx, cx), dy = __fsub_rn(qy, cy), dz = __fsub_rn(qz, cz);
+      float nn = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz))));
+      key = ((u64)__float_as_uint(nn) << 32) | (u64)(~(uint32_t)idx);
+    }
+    if (key < best) best = key;
+  };
+  int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
+  int cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
+  int R = 1, R_prev = -1;
+  bool done = false;
+  while (true) {
+    visit_annulus(g, cu, cv, R_prev, R, [&](float4 c) { consider(c.x, c.y, c.z, __float_as_int(c.w)); });
+    if (best != PPP_KEY_INF) {
+      float b2 = ring_bound2(g, R, cu, cv);
+      float v = __uint_as_float((uint32_t)(best >> 32));
+      if (metric == 0 ? (v < b2) : (v < __fsqrt_rd(b2))) { done = true; break; }
+    }
+    if (block_covers_grid(g, cu, cv, R)) { done = true; break; }
+    if (R >= RMAX) break;
+    R_prev = R;
+    R++;
+  }
+  if (!done) {
+    best = PPP_KEY_INF;
+    for (int t = 0; t < nlist; t++) {
+      int idx = list[t];
+      float4 c = __ldg(xyz4 + idx);
+      consider(c.x, c.y, c.z, idx);
+    }
+  }
+  if (best == PPP_KEY_INF) return -1;
+  uint32_t low = (uint32_t)(best & 0xFFFFFFFFull);
+  return metric == 0 ? (int)low : (int)(~low);
+}
+
+// kdtree.nearestKSearch(p, 1): global nearest under (d2, idx): for a cloud point, the lowest index
+// among the points at float distance 0 from it (itself unless the cloud has duplicates).
+__device__ int nn_full(const GridView& g, float qx, float qy, float qz) {
+  u64 best = PPP_KEY_INF;
+  int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
+  int cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
+  int R = 1, R_prev = -1;
+  while (true) {
+    visit_annulus(g, cu, cv, R_prev, R, [&](float4 c) {
+      u64 key = make_key(d2_flann(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+      if (key < best) best = key;
+    });
+    if (best != PPP_KEY_INF && key_d2(best) < ring_bound2(g, R, cu, cv)) break;
+    if (block_covers_grid(g, cu, cv, R)) break;
+    R_prev = R;
+    R++;
+  }
+  return best == PPP_KEY_INF ? -1 : key_idx(best);
+}
+
+__device__ __forceinline__ int lower_pos(const int32_t* a, int n, int v) {
+  int l = 0, r = n;
+  while (l < r) { int m = (l + r) >> 1; if (a[m] < v) l = m + 1; else r = m; }
+  return l;
+}
+
+__global__ void __launch_bounds__(CT_THREADS) k_contour(ContourParams P) {
+  __shared__ int s_warp[CT_THREADS / 32];
+  __shared__ int s_npairs;
+  const int s = blockIdx.x;
+  const int64_t o = P.band_off[s];
+  const int B = (int)(P.band_off[s + 1] - o);
+  const float plane = P.planes[s], lo = P.lo[s], hi = P.hi[s];
+  const int32_t* band = P.band_idx + o;
+  int32_t* El = P.El + o;
+  int32_t* Er = P.Er + o;
+  // ---- classify: El (x > plane), Er (x < plane), order preserved; x == plane dropped ----
+  int nL = 0, nR = 0;
+  for (int base = 0; base < B; base += CT_THREADS) {
+    int i = base + threadIdx.x;
+    int idx = -1;
+    bool isL = false, isR = false;
+    if (i < B) {
+      idx = band[i];
+      float x = __ldg(&P.xyz4[idx].x);
+      // (point - PlanePoint).dot((1,0,0)): sign of (x - plane) for finite points
+      float d = __fsub_rn(x, plane);
+      isL = d > 0.0f;
+      isR = d < 0.0f;
+    }
+    int rl = cta_flag_rank(isL, s_warp, nL);
+    int rr = cta_flag_rank(isR, s_warp, nR);
+    if (isL) El[rl] = idx;
+    if (isR) Er[rr] = idx;
+  }
+  __syncthreads();
+  int npairs = 0;
+  float* ys = P.ys + o;
+  float* zs = P.zs + o;
+  u64* keys = P.keys + o;
+  if (nL > 0 && nR > 0) {
+    if (P.mode == PPP_PAIR_SECT) {
+      // one pair per left point, no flags (src/contour_alg.cpp:185-211)
+      for (int i = threadIdx.x; i < nL; i += CT_THREADS) {
+        float4 pl = __ldg(P.xyz4 + El[i]);
+        int r = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, Er, nR);
+        float4 pr = __ldg(P.xyz4 + r);
+        int rc = nn_full(P.g, pr.x, pr.y, pr.z);
+        int l2 = nn_side(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, El, nL);
+        float4 pl2 = __ldg(P.xyz4 + l2);
+        int lc = nn_full(P.g, pl2.x, pl2.y, pl2.z);
+        P.lp[o + i] = lc;
+        P.rp[o + i] = rc;
+      }
+      npairs = nL;
+      __syncthreads();
+    } else {
+      // gen-2: nearest right of every left, nearest left of every right (flag-independent),
+      // then the order-dependent greedy flag pass replayed by one thread.
+      for (int i = threadIdx.x; i < nL; i += CT_THREADS) {
+        float4 pl = __ldg(P.xyz4 + El[i]);
+        int r = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 1, Er, nR);
+        P.posR[o + i] = lower_pos(Er, nR, r);
+        P.fl[o + i] = 0;
+      }
+      for (int j = threadIdx.x; j < nR; j += CT_THREADS) {
+        float4 pr = __ldg(P.xyz4 + Er[j]);
+        int l = nn_side(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 1, El, nL);
+        P.posL[o + j] = lower_pos(El, nL, l);
+        P.fr[o + j] = 0;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int nl = 0, nr = 0;
+        for (int i = 0; i < nL; i++) {
+          if (P.fl[o + i]) continue;
+          int j = P.posR[o + i];
+          if (P.fr[o + j]) continue;
+          P.rp[o + nr++] = Er[j];
+          P.fr[o + j] = 1;
+          int i2 = P.posL[o + j];
+          if (!P.fl[o + i2]) { P.lp[o + nl++] = El[i2]; P.fl[o + i2] = 1; }
+        }
+        s_npairs = nl;  // interpolation runs over left_pair.size() (src/Path_Generation.cpp:189)
+      }
+      __syncthreads();
+      npairs = s_npairs;
+    }
+    // ---- interpolate onto the plane (float32, no FMA) ----
+    for (int i = threadIdx.x; i < npairs; i += CT_THREADS) {
+      float4 r = __ldg(P.xyz4 + P.rp[o + i]);
+      float4 l = __ldg(P.xyz4 + P.lp[o + i]);
+      float t = __fdiv_rn(__fsub_rn(plane, r.x), __fsub_rn(l.x, r.x));
+      float y = __fadd_rn(r.y, __fmul_rn(t, __fsub_rn(l.y, r.y)));
+      float z = __fadd_rn(r.z, __fmul_rn(t, __fsub_rn(l.z, r.z)));
+      ys[i] = y;
+      zs[i] = z;
+      // std::map<double,...> key order; -0.0 and +0.0 are one key
+      keys[i] = ((u64)f2ord_dev(__fadd_rn(y, 0.0f)) << 32) | (u64)(uint32_t)i;
+    }
+    __syncthreads();
+    cta_sort(keys, npairs);
+  }
+  // ---- unique keys: key of the first insertion, value of the last ----
+  int nodes = 0;
+  double* ty = P.ty + o;
+  double* tz = P.tz + o;
+  for (int base = 0; base < npairs; base += CT_THREADS) {
+    int i = base + threadIdx.x;
+    bool first = false, last = false;
+    u64 k = 0;
+    if (i < npairs) {
+      k = keys[i];
+      first = (i == 0) || ((keys[i - 1] >> 32) != (k >> 32));
+      last = (i == npairs - 1) || ((keys[i + 1] >> 32) != (k >> 32));
+    }
+    // r = number of run starts strictly before i; run index of i = r (if it starts a run) else r - 1
+    int r = cta_flag_rank(first, s_warp, nodes);
+    if (i < npairs) {
+      uint32_t pi = (uint32_t)(k & 0xFFFFFFFFull);
+      int run = first ? r : r - 1;
+      if (first) ty[run] = (double)ys[pi];
+      if (last) tz[run] = (double)zs[pi];
+    }
+  }
+  if (threadIdx.x == 0) P.n_nodes[s] = nodes;
+}
+
+__global__ void __launch_bounds__(256) k_compact_nodes(const int64_t* __restrict__ band_off, const int64_t* __restrict__ node_off,
+                                                      const float* __restrict__ planes, const double* __restrict__ ty,
+                                                      const double* __restrict__ tz, double* __restrict__ y,
+                                                      double* __restrict__ x, double* __restrict__ z) {
+  int s = blockIdx.x;
+  int64_t so = band_off[s], d = node_off[s];
+  int n = (int)(node_off[s + 1] - d);
+  double px = (double)planes[s];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    y[d + i] = ty[so + i];
+    x[d + i] = px;
+    z[d + i] = tz[so + i];
+  }
+}
+
+}  // namespace
+
+static void band_limits_host(float plane_x, float half_width, int truncate_center, float* lo, float* hi) {
+  if (truncate_center) {
+    int position = (int)plane_x;  // rangedX_index(int position) receives the float plane x
+    int hw = (int)half_width;
+    *lo = (float)(-hw + position);
+    *hi = (float)(hw + position);
+  } else {
+    *lo = plane_x - half_width;
+    *hi = plane_x + half_width;
+  }
+}
+
+// Device arrays produced: offsets (S+1, int64), idx (total), planes/lo/hi (3*S floats, original order).
+int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center,
+                 int64_t** offsets_dev_out, int32_t** idx_dev_out, int64_t* total_out, float** planes_dev_out) {
+  ppp_ctx* ctx = c->ctx;
+  *offsets_dev_out = nullptr; *idx_dev_out = nullptr; *planes_dev_out = nullptr; *total_out = 0;
+  std::vector<float> lo(S), hi(S);
+  std::vector<int32_t> perm(S);
+  for (int s = 0; s < S; s++) {
+    if (std::isfinite(plane_x_host[s]) && std::fabs(plane_x_host[s]) < 2.0e9f) band_limits_host(plane_x_host[s], half_width, truncate_center, &lo[s], &hi[s]);
+    else lo[s] = hi[s] = NAN;
+    perm[s] = s;
+  }
+  std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) {
+    bool na = std::isnan(lo[a]), nb = std::isnan(lo[b]);
+    if (na != nb) return nb;
+    if (na) return false;
+    return lo[a] < lo[b];
+  });
+  // host staging: [planes S][lo S][hi S][lo_sorted S][hi_sorted S] + perm
+  std::vector<float> stage(5 * (size_t)S);
+  int Sv = 0;  // sorted entries with valid limits
+  for (int s = 0; s < S; s++) {
+    stage[s] = plane_x_host[s];
+    stage[S + s] = lo[s];
+    stage[2 * S + s] = hi[s];
+  }
+  for (int t = 0; t < S; t++) {
+    int s = perm[t];
+    if (!std::isnan(lo[s])) Sv = t + 1;
+    stage[3 * S + t] = lo[s];
+    stage[4 * S + t] = hi[s];
+  }
+  // hi must be non-decreasing in lo-sorted order for the range lookup; true for a single width
+  // (float rounding of x +/- hw is monotone). Otherwise widen the lookup: use running max/min.
+  float* fdev = nullptr;
+  int32_t* pdev = nullptr;
+  PPP_TRY(dev_alloc(ctx, &fdev, 5 * (size_t)std::max(S, 1)));
+  PPP_TRY(dev_alloc(ctx, &pdev, (size_t)std::max(S, 1)));
+  int32_t* counts = nullptr;
+  int64_t* offsets = nullptr;
+  PPP_TRY(dev_alloc(ctx, &counts, (size_t)std::max(S, 1)));
+  PPP_TRY(dev_alloc(ctx, &offsets, (size_t)S + 1));
+  if (S > 0) {
+    PPP_CUDA(cudaMemcpyAsync(fdev, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PPP_CUDA(cudaMemcpyAsync(pdev, perm.data(), (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    // the pageable staging vectors must stay alive until the copies have been consumed
+    PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  PPP_CUDA(cudaMemsetAsync(counts, 0, (size_t)std::max(S, 1) * sizeof(int32_t), ctx->stream));
+  BandSet b{fdev + 3 * (size_t)S, fdev + 4 * (size_t)S, pdev, Sv};
+  unsigned blocks = (unsigned)((c->n + 255) / 256);
+  if (c->n > 0 && Sv > 0) {
+    auto kc = k_band_scan<false>;
+    PPP_LAUNCH(ctx, "band_count", kc, blocks, 256, 0, b, (const float4*)c->xyz4, c->n, counts, (const int64_t*)nullptr,
+               (int32_t*)nullptr);
+    PPP_CHECK_LAUNCH();
+  }
+  PPP_TRY(scan_exclusive_i32_to_i64(ctx, counts, offsets, S));
+  int64_t total = 0;
+  PPP_CUDA(cudaMemcpyAsync(&total, offsets + S, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  int32_t* idx = nullptr;
+  PPP_TRY(dev_alloc(ctx, &idx, (size_t)std::max<int64_t>(total, 1)));
+  if (total > 0) {
+    PPP_CUDA(cudaMemsetAsync(counts, 0, (size_t)S * sizeof(int32_t), ctx->stream));
+    auto kf = k_band_scan<true>;
+    PPP_LAUNCH(ctx, "band_fill", kf, blocks, 256, 0, b, (const float4*)c->xyz4, c->n, counts, (const int64_t*)offsets, idx);
+    PPP_CHECK_LAUNCH();
+    int smem_cap = 24576;  // 96 KB of int32
+    PPP_CUDA(cudaFuncSetAttribute(k_band_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 4));
+    PPP_LAUNCH(ctx, "band_sort", k_band_sort, (unsigned)S, CT_THREADS, (size_t)smem_cap * 4, (const int64_t*)offsets, idx,
+               smem_cap);
+    PPP_CHECK_LAUNCH();
+  }
+  dev_free(ctx, counts);
+  dev_free(ctx, pdev);
+  *offsets_dev_out = offsets;
+  *idx_dev_out = idx;
+  *planes_dev_out = fdev;  // [planes][lo][hi] in original order (+ sorted copies behind)
+  *total_out = total;
+  return PPP_OK;
+}
+
+int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, int S, float half_width,
+                    int truncate_center, const int64_t* band_off_dev, const int32_t* band_idx_dev, int64_t band_total,
+                    const int64_t* band_off_host, int mode, int64_t* total_nodes_out) {
+  (void)half_width; (void)truncate_center; (void)band_off_host;
+  ppp_ctx* ctx = c->ctx;
+  *total_nodes_out = 0;
+  size_t M = (size_t)std::max<int64_t>(band_total, 1);
+  ContourParams P{};
+  P.g = gs.v; P.xyz4 = c->xyz4;
+  P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
+  P.band_off = band_off_dev; P.band_idx = band_idx_dev; P.mode = mode;
+  PPP_TRY(dev_alloc(ctx, &P.El, M)); PPP_TRY(dev_alloc(ctx, &P.Er, M));
+  PPP_TRY(dev_alloc(ctx, &P.keys, M));
+  PPP_TRY(dev_alloc(ctx, &P.ys, M)); PPP_TRY(dev_alloc(ctx, &P.zs, M));
+  PPP_TRY(dev_alloc(ctx, &P.lp, M)); PPP_TRY(dev_alloc(ctx, &P.rp, M));
+  if (mode == PPP_PAIR_GEN2) {
+    PPP_TRY(dev_alloc(ctx, &P.posR, M)); PPP_TRY(dev_alloc(ctx, &P.posL, M));
+    PPP_TRY(dev_alloc(ctx, &P.fl, M)); PPP_TRY(dev_alloc(ctx, &P.fr, M));
+  }
+  PPP_TRY(dev_alloc(ctx, &P.ty, M)); PPP_TRY(dev_alloc(ctx, &P.tz, M));
+  PPP_TRY(dev_alloc(ctx, &P.n_nodes, (size_t)std::max(S, 1)));
+  // (re)allocate the cloud-owned result buffers
+  if (c->c_S_cap < S + 1) {
+    dev_free(ctx, c->c_node_off);
+    PPP_TRY(dev_alloc(ctx, &c->c_node_off, (size_t)S + 1));
+    c->c_S_cap = S + 1;
+  }
+  if (S > 0) {
+    PPP_LAUNCH(ctx, "contour", k_contour, (unsigned)S, CT_THREADS, 0, P);
+    PPP_CHECK_LAUNCH();
+  }
+  PPP_TRY(scan_exclusive_i32_to_i64(ctx, P.n_nodes, c->c_node_off, S));
+  int64_t total = 0;
+  PPP_CUDA(cudaMemcpyAsync(&total, c->c_node_off + S, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (c->c_cap < total || !c->c_y) {
+    dev_free(ctx, c->c_y); dev_free(ctx, c->c_x); dev_free(ctx, c->c_z);
+    size_t cap = (size_t)std::max<int64_t>(total, 1);
+    PPP_TRY(dev_alloc(ctx, &c->c_y, cap)); PPP_TRY(dev_alloc(ctx, &c->c_x, cap)); PPP_TRY(dev_alloc(ctx, &c->c_z, cap));
+    c->c_cap = (int64_t)cap;
+  }
+  if (total > 0) {
+    PPP_LAUNCH(ctx, "compact_nodes", k_compact_nodes, (unsigned)S, 256, 0, band_off_dev, (const int64_t*)c->c_node_off,
+               planes_dev, (const double*)P.ty, (const double*)P.tz, c->c_y, c->c_x, c->c_z);
+    PPP_CHECK_LAUNCH();
+  }
+  dev_free(ctx, P.El); dev_free(ctx, P.Er); dev_free(ctx, P.keys); dev_free(ctx, P.ys); dev_free(ctx, P.zs);
+  dev_free(ctx, P.lp); dev_free(ctx, P.rp); dev_free(ctx, P.posR); dev_free(ctx, P.posL); dev_free(ctx, P.fl);
+  dev_free(ctx, P.fr); dev_free(ctx, P.ty); dev_free(ctx, P.tz); dev_free(ctx, P.n_nodes);
+  *total_nodes_out = total;
+  return PPP_OK;
+}
