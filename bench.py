@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py — points/sec through kNN(k=16) + PCA normals + plane slicing + ordered contours.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): 1M-point synthetic freeform panel, k=16 normals + 200
+slices (5 mm apart, band +-2 mm, SectPath pairing), per GPU.  For N > 1 the panel grows to N x 1M
+points (weak scaling), is cut into N x-slabs with a 12 mm halo (polishpathplanning_b200/parallel.py);
+every rank runs the whole path on its slab and its planes, results are gathered to rank 0 (NCCL).
+
+One "step" = one pass of the hot path over the cloud, starting from the raw pcl::PointXYZRGB
+records: pack + bounding box, grid index build, fused kNN + normals (writes neighbour ids and
+normals), band extraction for all planes, per-slice pairing + interpolation + ordering.
+  value : device-resident (raw records already in HBM, results left in HBM), CUDA-event timed.
+  e2e   : the same step through the host-pointer C ABI (pinned host buffers; H2D of the records,
+          D2H of normals and contour nodes inside the timed region).
+  roofline : dominant kernel's algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference : the CPU oracle (port of the reference's PCL/FLANN path; the
+          reference itself cannot be built here) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "points/sec kNN(k=16)+normals+slicing"
+UNIT = "points/s"
+N_PER_GPU = 1_000_000
+K_NEIGH = 16
+S_PER_MILLION = 200       # 5 mm plane spacing on the 1000 mm panel
+HALF_WIDTH = 2.0
+HALO_MM = 12.0
+PAIRING = "B"             # SectPath::insert_point (src/contour_alg.cpp:165-237)
+CPU_SAMPLE_N = 250_000    # bounded CPU sample: same density, same plane spacing
+CPU_SAMPLE_S = 100
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.samples = []
+        self.proc = None
+        self.thr = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thr = threading.Thread(target=self._read, daemon=True)
+        self.thr.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 8:
+                self.samples.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for p in self.samples:
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_planes(x_min, x_max, S):
+    step = (float(x_max) - float(x_min)) / S
+    return (float(x_min) + step * (np.arange(S) + 0.5)).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference's CPU path)
+# ------------------------------------------------------------------------------------------------
+def cpu_step(po, cloud, planes, threads):
+    oc = po.OracleCloud(cloud)                      # kd-tree build  (Set_kdtree)
+    oc.normals(k=K_NEIGH, threads=threads)          # estimate_normal (k-search variant)
+    oc.slice_contours(planes, PAIRING, HALF_WIDTH, True, threads=threads)  # rangedX_index + insert_point + ordering
+    oc.close()
+
+
+def cpu_baseline(threads_all=True, reps=1):
+    from oracle import ppp_oracle as po
+    from polishpathplanning_b200 import synth
+    cloud = synth.panel(CPU_SAMPLE_N, seed=0)
+    planes = make_planes(cloud[:, 0].min(), cloud[:, 0].max(), CPU_SAMPLE_S)
+    cores = po.num_threads() if threads_all else 1
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_step(po, cloud, planes, cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return CPU_SAMPLE_N / best, cores, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ppp_oracle as po
+    from polishpathplanning_b200 import synth
+    cloud = synth.panel(CPU_SAMPLE_N, seed=0)
+    planes = make_planes(cloud[:, 0].min(), cloud[:, 0].max(), CPU_SAMPLE_S)
+    cores = po.num_threads()
+    for _ in range(args.warmup):
+        cpu_step(po, cloud, planes, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(po, cloud, planes, cores)
+    dt = time.perf_counter() - t0
+    v = CPU_SAMPLE_N * args.steps / dt
+    sample = ("oracle port of the reference CPU path, %d-point panel (same density and plane spacing as the GPU "
+              "workload), k=%d normals + %d slices, pairing %s, OpenMP over points/slices"
+              % (CPU_SAMPLE_N, K_NEIGH, CPU_SAMPLE_S, PAIRING))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(gpus):
+    return {"workload": "cfg2: %d-point synthetic freeform panel per GPU (seed 0, 1 pt/mm^2), k=%d normals + %d slices "
+                        "per million points (5 mm spacing, +-2 mm bands, SectPath pairing)" % (N_PER_GPU, K_NEIGH, S_PER_MILLION),
+            "points_per_gpu": N_PER_GPU, "k": K_NEIGH, "slices_total": int(round(S_PER_MILLION * np.sqrt(gpus))),
+            "pairing": "B(SectPath)", "partition": "x-slabs+%gmm halo" % HALO_MM if gpus > 1 else "single GPU",
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from polishpathplanning_b200 import api, parallel, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks (python -m torch.distributed.run ...)" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    ctx = api.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    # ---- data (host prep is untimed: it stands for loading the PCD) ----
+    n_total = N_PER_GPU * world
+    S_total = int(round(S_PER_MILLION * np.sqrt(world)))
+    cloud_g = synth.panel(n_total, seed=0)
+    planes_g = make_planes(cloud_g[:, 0].min(), cloud_g[:, 0].max(), S_total)
+    if world > 1:
+        cuts = parallel.slab_cuts(cloud_g[:, 0], world)
+        local_idx, owned = parallel.slab_select(cloud_g, cuts, rank, HALO_MM)
+        cloud = np.ascontiguousarray(cloud_g[local_idx])
+        my_planes_pos = parallel.owned_planes(planes_g, cuts, rank)
+        planes = np.ascontiguousarray(planes_g[my_planes_pos])
+        n_owned = int(owned.sum())
+    else:
+        cloud, planes, owned, local_idx = cloud_g, planes_g, None, None
+        n_owned = n_total
+    del cloud_g
+    n_local = cloud.shape[0]
+
+    with torch.cuda.stream(stream):
+        raw_d = torch.from_numpy(cloud).to(dev)
+        normals_d = torch.empty((n_local, 8), dtype=torch.float32, device=dev)
+        idx_d = torch.empty((n_local, K_NEIGH), dtype=torch.int32, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        owned_d = torch.from_numpy(np.nonzero(owned)[0]).to(dev) if owned is not None else None
+    stream.synchronize()
+
+    last = {}
+
+    def dev_step():
+        c = api.Cloud(ctx, device_ptr=raw_d.data_ptr(), n=n_local, stride_bytes=32)
+        c.dev_normals_knn(K_NEIGH, normals_d.data_ptr(), 32, idx_ptr=idx_d.data_ptr())
+        res = c.dev_slice_contours(planes, PAIRING, HALF_WIDTH, True)
+        last["nodes"] = res["total_nodes"]
+        last["members"] = res["total_members"]
+        if world > 1:
+            # results to rank 0: owned normals (compact nx,ny,nz,curv) + contour nodes (y,x,z)
+            with torch.cuda.stream(stream):
+                own = normals_d.index_select(0, owned_d)[:, [0, 1, 2, 4]].contiguous()
+                tn = res["total_nodes"]
+                nodes = torch.empty((3, max(tn, 1)), dtype=torch.float64, device=dev)
+                if tn:
+                    for j, key in enumerate(("y", "x", "z")):
+                        src = _wrap_f64(torch, res[key], tn, dev)
+                        nodes[j, :tn] = src
+                parallel.gather_to_rank0(dist, [own], rank, world, device=dev)
+                parallel.gather_to_rank0(dist, [nodes.t().contiguous()[:tn]], rank, world, device=dev)
+        c.close()
+
+    def sync_all():
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        flush_l2(); dev_step()
+    sync_all()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.timer_read(0, reset=True)
+    l0 = ctx.launch_count()
+    sync_all()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush_l2()
+        stream.synchronize()
+        ctx.timer_begin(0)
+        dev_step()
+        ctx.timer_end(0)
+    sync_all()
+    t_wall = time.perf_counter() - t_wall0
+    total_ms, regions = ctx.timer_read(0, reset=True)
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    assert regions == args.steps
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+        cnt = torch.tensor([n_owned], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt)
+        units = int(cnt.item())
+    else:
+        units = n_owned
+    value = units * args.steps / (total_ms * 1e-3)
+
+    # ---- per-kernel pass (roofline of the dominant kernel), same steps, CUDA events per launch ----
+    ctx.kernel_profile(True)
+    ctx.kernel_profile_read(reset=True)
+    for _ in range(args.steps):
+        flush_l2()
+        dev_step()
+    sync_all()
+    prof = ctx.kernel_profile_read(reset=True)
+    ctx.kernel_profile(False)
+
+    # ---- end to end through the host-pointer C ABI (pinned buffers) ----
+    pin_cloud = ctx.pinned_empty(cloud.shape, np.float32)
+    pin_cloud[...] = cloud
+    pin_normals = ctx.pinned_empty((n_local, 8), np.float32)
+    e2e_bytes = {}
+
+    def host_step():
+        c = api.Cloud(ctx, pin_cloud)
+        c.normals_knn(K_NEIGH, out=pin_normals)
+        off, y, x, z = c.slice_contours(planes, PAIRING, HALF_WIDTH, True, node_cap=max(last.get("nodes", 0), 1024))
+        e2e_bytes["h2d"] = pin_cloud.nbytes + planes.nbytes * 5 + 4 * len(planes)
+        e2e_bytes["d2h"] = pin_normals.nbytes + off.nbytes + 3 * y.nbytes
+        c.close()
+        return off, y, x, z
+
+    for _ in range(min(args.warmup, 3)):
+        host_step()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = units * args.steps / e2e_s
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        dom = max(prof.items(), key=lambda kv: kv[1][0]) if prof else ("none", (0.0, 0))
+        dom_name, (dom_ms, dom_launches) = dom
+        alg_bytes = {
+            "knn_normals": n_local * (32 + 4 * K_NEIGH),   # 16 B point in + 4k B ids + 16 B normal out
+            "knn": n_local * (16 + 4 * K_NEIGH),
+            "contour": 16 * last.get("members", 0) + 24 * last.get("nodes", 0),
+            "band_count": 16 * n_local, "band_fill": 16 * n_local + 4 * last.get("members", 0),
+            "pack_bbox": 12 * n_local + 16 * n_local,
+            "cell_count": 16 * n_local, "cell_scatter": 16 * n_local + 20 * n_local,
+        }.get(dom_name)
+        roof = None
+        if alg_bytes and dom_launches:
+            achieved = alg_bytes / (dom_ms * 1e-3 / dom_launches) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "dram_traffic.json")
+            if os.path.exists(tp):
+                try:
+                    with open(tp) as f:
+                        traffic = json.load(f).get(dom_name)
+                except Exception:
+                    traffic = None
+            roof = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms / dom_launches,
+                    "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+        cpu = None
+        if world == 1:
+            v_all, cores, secs = cpu_baseline(True)
+            v_one, _, secs1 = cpu_baseline(False)
+            cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "oracle port of the reference CPU path on a %d-point panel (same density/plane spacing), "
+                             "k=%d normals + %d slices pairing %s; %.2f s with %d threads, %.2f s single-thread"
+                             % (CPU_SAMPLE_N, K_NEIGH, CPU_SAMPLE_S, PAIRING, secs, cores, secs1),
+                   "single_thread_value": v_one}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_bytes.get("h2d", 0)),
+                    "d2h_bytes_per_step": int(e2e_bytes.get("d2h", 0)), "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof, "cpu_baseline": cpu,
+            "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            "points_local": n_local, "band_members": last.get("members"), "contour_nodes": last.get("nodes"),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def _wrap_f64(torch, ptr, n, dev):
+    """View n doubles at raw device pointer `ptr` as a torch tensor (no copy)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(h, device=dev)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
