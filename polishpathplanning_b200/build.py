@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libppp_gpu.so")
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
 SOURCES = ["api.cu", "scan.cu", "grid.cu", "knn.cu", "slices.cu"]
-HEADERS = ["ppp_internal.cuh", "ppp_device.cuh", os.path.join("..", "..", "include", "ppp_gpu.h")]
+HEADERS = ["ppp_internal.cuh", "ppp_device.cuh", "sortnet.cuh", os.path.join("..", "..", "include", "ppp_gpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -210,6 +210,7 @@ int ppp_cloud_free(ppp_cloud* c) {
   dev_free(ctx, c->xyz4);
   for (auto& g : c->grids) { dev_free(ctx, g.sorted); dev_free(ctx, g.cell_start); dev_free(ctx, g.order); }
   dev_free(ctx, c->c_node_off); dev_free(ctx, c->c_y); dev_free(ctx, c->c_x); dev_free(ctx, c->c_z);
+  dev_free(ctx, c->dup_flag);
   delete c;
   return PPP_OK;
 }
@@ -293,11 +294,13 @@ int ppp_dev_slice_contours(ppp_cloud* c, const float* plane_x_host, int S, float
   LOCK(ctx);
   PPP_CUDA(cudaSetDevice(ctx->device));
   int64_t* boff = nullptr; int32_t* bidx = nullptr; float* planes = nullptr; int64_t M = 0;
-  PPP_TRY(bands_launch(c, plane_x_host, S, half_width, truncate_center, &boff, &bidx, &M, &planes));
+  std::vector<int64_t> off_h;
+  PPP_TRY(bands_launch(c, plane_x_host, S, half_width, truncate_center, pairing_mode == PPP_PAIR_GEN2, &boff, &bidx, &M,
+                       &planes, &off_h));
   GridStore* g;
   int st = pick_any_grid(c, &g);
   int64_t total = 0;
-  if (st == PPP_OK) st = contours_launch(c, *g, planes, S, half_width, truncate_center, boff, bidx, M, nullptr, pairing_mode, &total);
+  if (st == PPP_OK) st = contours_launch(c, *g, planes, S, boff, bidx, M, off_h, pairing_mode, &total);
   dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, planes);
   if (st != PPP_OK) return st;
   if (node_offsets_dev) *node_offsets_dev = c->c_node_off;
@@ -440,7 +443,7 @@ int ppp_slice_bands(ppp_cloud* c, const float* plane_x, int S, float half_width,
   LOCK(ctx);
   PPP_CUDA(cudaSetDevice(ctx->device));
   int64_t* boff = nullptr; int32_t* bidx = nullptr; float* planes = nullptr; int64_t M = 0;
-  PPP_TRY(bands_launch(c, plane_x, S, half_width, truncate_center, &boff, &bidx, &M, &planes));
+  PPP_TRY(bands_launch(c, plane_x, S, half_width, truncate_center, 1, &boff, &bidx, &M, &planes, nullptr));
   int st = PPP_OK;
   PPP_CUDA(cudaMemcpyAsync(offsets, boff, ((size_t)S + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (idx_out) {

@@ -8,10 +8,13 @@
 // [j*blockDim + t], bank = t, conflict-free) as 64-bit keys (d2 bits << 32 | index), so the
 // reference's (d2, index) order is a single unsigned compare and the list is already in the
 // order the PCL covariance must be accumulated in.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cmath>
 
 #include "ppp_device.cuh"
+#include "sortnet.cuh"
 
 namespace {
 
@@ -34,6 +37,11 @@ struct SearchParams {
   int nsf;
   float vpx, vpy, vpz;
   unsigned flags;
+  int32_t* dup_flag;    // self mode: set to 1 if a different point lies at float distance 0
+  // fast path -> generic path hand-over: queries the fixed-radius fast kernel could not finish
+  int32_t* redo_list;   // query numbers t (fast kernel appends; generic kernel consumes)
+  int32_t* redo_count;
+  int use_redo;         // generic kernel: take the query number from redo_list[thread]
 };
 
 __device__ __forceinline__ void list_insert(u64* L, int BD, int& cnt, int cap, u64 key) {
@@ -51,7 +59,12 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
   extern __shared__ u64 s_keys[];
   const int BD = blockDim.x;
   int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
-  if (t >= P.nq) return;
+  if (P.use_redo) {
+    if (t >= *P.redo_count) return;
+    t = P.redo_list[t];
+  } else if (t >= P.nq) {
+    return;
+  }
   const GridView& g = P.g;
   float qx, qy, qz;
   int64_t row;
@@ -66,6 +79,8 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
   }
   u64* L = s_keys + threadIdx.x;
   int cnt = 0;
+  bool dup_seen = false;
+  const bool self = P.q == nullptr;
   const bool fin = finite3(qx, qy, qz);
   if (fin && g.n_sorted > 0) {
     int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
@@ -75,6 +90,7 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
       visit_annulus(g, cu, cv, -1, P.R0, [&](float4 c) {
         u64 key = make_key(d2_flann(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
         if (key < tau) {
+          dup_seen |= (key >> 32) == 0 && self && __float_as_int(c.w) != (int)row;
           list_insert(L, BD, cnt, P.cap, key);
           if (cnt == P.cap) tau = min(tau, L[(P.cap - 1) * BD] + 1);  // full: keep the cap smallest
         }
@@ -88,6 +104,7 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
       while (true) {
         visit_annulus(g, cu, cv, R_prev, R, [&](float4 c) {
           u64 key = make_key(d2_flann(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+          dup_seen |= (key >> 32) == 0 && self && __float_as_int(c.w) != (int)row;
           if (key < tau) {
             list_insert(L, BD, cnt, P.cap, key);
             if (cnt == P.cap) tau = L[(P.cap - 1) * BD];
@@ -100,6 +117,7 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
       }
     }
   }
+  if (dup_seen && P.dup_flag) *P.dup_flag = 1;
   // ---- outputs ----
   if (P.idx_out) {
     if (P.mode == 0) {
@@ -141,6 +159,296 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
     }
     store_normal(P.normals, row, P.nsf, o);
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Fast k-nearest path (k <= 32): fixed (2*R0+1)^2 cell block, warp-uniform candidate loops,
+// accepted candidates buffered per thread in shared memory and merged K at a time into a sorted
+// register list with sorting networks (Batcher odd-even merge sort + bitonic merge).  No
+// data-dependent branches inside the selection: the only divergence left is the row ranges.
+// A candidate is accepted only if d2 < ring_bound2(R0) (beyond that the block is not a superset
+// of the neighbourhood), so a query that does not collect k candidates is handed to the generic
+// ring-expanding kernel through redo_list; everything it does finish is exact.
+// ---------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128, (K <= 16 ? 5 : 2)) k_knn_fast(SearchParams P) {
+  extern __shared__ u64 s_keys[];
+  constexpr int BD = 128;  // launch block size (immediate shared-memory offsets)
+  const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
+  const GridView& g = P.g;
+  const bool valid = t < P.nq;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  int64_t row = 0;
+  if (valid) {
+    if (P.q) {
+      const float* qp = P.q + t * P.q_sf;
+      qx = __ldg(qp); qy = __ldg(qp + 1); qz = __ldg(qp + 2);
+      row = t;
+    } else {
+      float4 p = __ldg(g.sorted + P.first + t);
+      qx = p.x; qy = p.y; qz = p.z;
+      row = __float_as_int(p.w);
+    }
+  }
+  const bool self = P.q == nullptr;
+  const bool fin = valid && finite3(qx, qy, qz);
+  const bool act = fin && g.n_sorted > 0;
+  u64* pend_s = s_keys + threadIdx.x;
+  u64 best[K];
+#pragma unroll
+  for (int i = 0; i < K; i++) best[i] = PPP_KEY_INF;
+  int pc = 0;
+  bool dup_seen = false;
+  const int R = P.R0;
+  int cu = 0, cv = 0;
+  u64 tau = 0;  // inactive lanes accept nothing
+  if (act) {
+    cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
+    cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
+    tau = make_key(ring_bound2(g, R, cu, cv), 0);
+  }
+
+  // Merge the pending buffers into `best` (INF-padded load, sort network, bitonic merge).  One
+  // straight-line copy of the networks only: duplicated copies thrash the instruction cache.
+  auto flush = [&]() {
+    u64 pend[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      u64 v = pend_s[i * BD];  // unconditional load (stale slots are ignored), then pad
+      pend[i] = i < pc ? v : PPP_KEY_INF;
+    }
+    SortNet<K>::sort(pend);
+    SortNet<K>::merge_keep_smallest(best, pend);
+    pc = 0;
+    if (best[K - 1] < tau) tau = best[K - 1];
+  };
+
+  // rows dv = -R..R, plus one pseudo-row (dv = R+1) whose single empty iteration drains the
+  // pending buffers: one flush site keeps the unrolled networks in the instruction cache once.
+  // U candidates per iteration: the loads are issued together, then consumed.
+  constexpr int U = 4;
+  int zero_cnt = 0;
+#pragma unroll 1
+  for (int dv = -R; dv <= R + 1; dv++) {
+    int s = 0, e = 0;
+    int v = cv + dv;
+    const bool drain = dv == R + 1;
+    if (!drain && act && v >= 0 && v < g.nv) {
+      int a = max(cu - R, 0), b = min(cu + R, g.nu - 1);
+      if (a <= b) {
+        const int32_t* rowp = g.cell_start + (int64_t)v * g.nu;
+        s = __ldg(rowp + a);
+        e = __ldg(rowp + b + 1);
+      }
+    }
+    // drain row: one empty iteration with trigger level 0.  Written arithmetically (no select on
+    // `drain`) so the compiler does not clone the loop body, and with it the flush networks.
+    const int n_it = (__reduce_max_sync(0xffffffffu, e - s) + U - 1) / U + (dv - R > 0 ? 1 : 0);
+    const int trig = min(K - U, (R + 1 - dv) * K);  // flush when some lane could overflow next iteration
+#pragma unroll 1
+    for (int it = 0; it < n_it; it++) {
+      float4 c[U];
+      bool in[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        int i = s + it * U + u;
+        in[u] = i < e;
+        c[u] = __ldg(g.sorted + (in[u] ? i : 0));
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        float d2 = d2_flann(qx, qy, qz, c[u].x, c[u].y, c[u].z);
+        u64 key = make_key(d2, __float_as_int(c[u].w));
+        zero_cnt += (in[u] && d2 == 0.0f) ? 1 : 0;
+        if (in[u] && key < tau) {
+          pend_s[pc * BD] = key;
+          pc++;
+        }
+      }
+      if (__any_sync(0xffffffffu, pc > trig)) flush();
+    }
+  }
+  // a self query always sees itself at distance 0; a second zero-distance point is a duplicate
+  dup_seen = self && zero_cnt >= 2;
+  if (dup_seen && P.dup_flag) *P.dup_flag = 1;
+  if (!valid) return;
+
+  // complete iff kk candidates were found inside the bound (then the kk-th is < bound by construction)
+  const int kk = P.kk;
+  bool complete = !act || kk == 0;
+  if (!complete) {
+    u64 kth = PPP_KEY_INF;
+#pragma unroll
+    for (int i = 0; i < K; i++) if (i == kk - 1) kth = best[i];
+    complete = kth != PPP_KEY_INF;
+    // the whole grid inside the block: nothing else exists, whatever was found is final.  (The
+    // bound prefilter may have rejected far candidates, so this only helps when kk exceeds the cloud.)
+  }
+  if (!complete) {
+    int slot = atomicAdd(P.redo_count, 1);
+    P.redo_list[slot] = (int32_t)t;
+    return;
+  }
+  const int k = P.cap;
+  if (P.idx_out) {
+    int32_t* io = P.idx_out + row * (int64_t)k;
+    float* dout = P.d2_out ? P.d2_out + row * (int64_t)k : nullptr;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      if (j < k) {
+        bool has = best[j] != PPP_KEY_INF;
+        io[j] = has ? key_idx(best[j]) : -1;
+        if (dout) dout[j] = has ? key_d2(best[j]) : CUDART_INF_F;
+      }
+    }
+  }
+  if (P.normals) {
+    float o[4];
+    int m = 0;
+#pragma unroll
+    for (int j = 0; j < K; j++) m += (j < k && best[j] != PPP_KEY_INF) ? 1 : 0;
+    if (!fin || m < 3) {
+      o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
+    } else {
+      float4 nb[K];
+#pragma unroll
+      for (int j = 0; j < K; j++)
+        if (j < m) nb[j] = __ldg(P.xyz4 + key_idx(best[j]));
+      float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
+      float kx = shifted ? nb[0].x : 0.f, ky = shifted ? nb[0].y : 0.f, kz = shifted ? nb[0].z : 0.f;
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        if (j < m) {
+          float x = nb[j].x, y = nb[j].y, z = nb[j].z;
+          if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
+          accumulate_point(acc, x, y, z);
+        }
+      }
+      normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
+    }
+    store_normal(P.normals, row, P.nsf, o);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Ring-expanding k-nearest search, one WARP per query: the hand-over path of k_knn_fast (sparse
+// regions, cloud borders; typically well under 1% of the queries).  The 32 lanes stride over the
+// candidates of each ring (coalesced), each lane keeps its own sorted list of at most k keys in
+// shared memory, and after every ring the k smallest of the 32 lists are extracted with warp-wide
+// 64-bit min reductions to test the exactness bound.  A thread-per-query kernel is latency-bound
+// here: few queries, each a long chain of dependent loads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    u64 t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t < v ? t : v;
+  }
+  return v;
+}
+
+constexpr int WARPQ_WARPS = 4;
+
+__global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
+  extern __shared__ u64 s_keys[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const GridView& g = P.g;
+  const int k = P.cap, kk = P.kk;
+  u64* L = s_keys + (size_t)w * 32 * k + lane;  // entry j of this lane at L[j * 32]
+  const int n_redo = *P.redo_count;
+  // persistent warps: the number of hand-over queries is only known on the device
+  for (int64_t slot = (int64_t)blockIdx.x * WARPQ_WARPS + w; slot < n_redo; slot += (int64_t)gridDim.x * WARPQ_WARPS) {
+  const int64_t t = P.redo_list[slot];
+  float qx, qy, qz;
+  int64_t row;
+  if (P.q) {
+    const float* qp = P.q + t * P.q_sf;
+    qx = __ldg(qp); qy = __ldg(qp + 1); qz = __ldg(qp + 2);
+    row = t;
+  } else {
+    float4 p = __ldg(g.sorted + P.first + t);
+    qx = p.x; qy = p.y; qz = p.z;
+    row = __float_as_int(p.w);
+  }
+  const int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
+  const int cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
+  int cnt = 0;
+  u64 tau = PPP_KEY_INF;  // warp-uniform acceptance threshold (k-th best after the last ring)
+  u64 mine = PPP_KEY_INF; // lane j ends up holding the j-th nearest key
+  int du = max(max(-cu, cu - (g.nu - 1)), 0), dv0 = max(max(-cv, cv - (g.nv - 1)), 0);
+  int R = max(P.R0, max(du, dv0));
+  int R_prev = -1;
+  while (true) {
+    // annulus R_prev < max(|du|,|dv|) <= R, lanes striding over each contiguous cell range
+    const int v0 = max(cv - R, 0), v1 = min(cv + R, g.nv - 1);
+    for (int v = v0; v <= v1; v++) {
+      const int32_t* rowp = g.cell_start + (int64_t)v * g.nu;
+      const bool full = abs(v - cv) > R_prev;
+      for (int part = 0; part < (full ? 1 : 2); part++) {
+        int a, b;
+        if (full) { a = max(cu - R, 0); b = min(cu + R, g.nu - 1); }
+        else if (part == 0) { a = max(cu - R, 0); b = min(cu - R_prev - 1, g.nu - 1); }
+        else { a = max(cu + R_prev + 1, 0); b = min(cu + R, g.nu - 1); }
+        if (a > b) continue;
+        const int s = __ldg(rowp + a), e = __ldg(rowp + b + 1);
+        for (int i = s + lane; i < e; i += 32) {
+          float4 c = __ldg(g.sorted + i);
+          u64 key = make_key(d2_flann(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+          if (key < tau) list_insert(L, 32, cnt, k, key);
+        }
+      }
+    }
+    __syncwarp();
+    // k smallest of the 32 sorted lists
+    int head = 0;
+    u64 kth = PPP_KEY_INF;
+    mine = PPP_KEY_INF;
+    for (int j = 0; j < kk; j++) {
+      u64 h = head < cnt ? L[head * 32] : PPP_KEY_INF;
+      u64 m = warp_min_u64(h);
+      if (m == PPP_KEY_INF) break;
+      if (h == m) head++;  // keys are unique (distinct point indices)
+      if (lane == j) mine = m;
+      kth = (j == kk - 1) ? m : kth;
+    }
+    if (kth != PPP_KEY_INF && key_d2(kth) < ring_bound2(g, R, cu, cv)) break;
+    if (block_covers_grid(g, cu, cv, R)) break;
+    if (kth != PPP_KEY_INF) tau = kth;  // nothing at or beyond the current k-th can enter any more
+    R_prev = R;
+    R++;
+  }
+  const int have = __popc(__ballot_sync(0xffffffffu, mine != PPP_KEY_INF));
+  if (P.idx_out && lane < k) {
+    P.idx_out[row * (int64_t)k + lane] = mine != PPP_KEY_INF ? key_idx(mine) : -1;
+    if (P.d2_out) P.d2_out[row * (int64_t)k + lane] = mine != PPP_KEY_INF ? key_d2(mine) : CUDART_INF_F;
+  }
+  if (P.normals) {
+    float o[4];
+    if (have < 3) {
+      o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
+    } else {
+      // sequential accumulation in list order, computed redundantly by every lane
+      float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
+      float kx = 0.f, ky = 0.f, kz = 0.f;
+      const int my_idx = mine != PPP_KEY_INF ? key_idx(mine) : 0;
+      for (int j = 0; j < have; j++) {
+        int idx = __shfl_sync(0xffffffffu, my_idx, j);
+        float4 a = __ldg(P.xyz4 + idx);
+        if (shifted && j == 0) { kx = a.x; ky = a.y; kz = a.z; }
+        float x = a.x, y = a.y, z = a.z;
+        if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
+        accumulate_point(acc, x, y, z);
+      }
+      normal_from_accumulators(acc, have, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
+    }
+    if (lane == 0) store_normal(P.normals, row, P.nsf, o);
+  }
+  __syncwarp();
+  }  // slot loop
 }
 
 __global__ void __launch_bounds__(128) k_radius_count(SearchParams P, int32_t* __restrict__ counts, int32_t* __restrict__ max_count) {
@@ -225,17 +533,85 @@ int radius_rings(const GridView& g, double r) {
 
 static int launch_search(ppp_cloud* c, SearchParams& P) {
   ppp_ctx* ctx = c->ctx;
+  if (!P.q) {
+    if (!c->dup_flag) {
+      PPP_TRY(dev_alloc(ctx, &c->dup_flag, 1));
+      PPP_CUDA(cudaMemsetAsync(c->dup_flag, 0, sizeof(int32_t), ctx->stream));
+    }
+    P.dup_flag = c->dup_flag;
+    // the flag is complete once every indexed point has been a query of a search with >= 1 ring
+    if (P.first == 0 && P.nq == c->n_finite && P.R0 >= 1 && (P.mode == 1 || P.cap >= 2)) c->dup_known = true;
+  }
   int block; size_t smem;
   PPP_TRY(pick_block(ctx, std::max(P.cap, 1), &block, &smem));
+  if (P.use_redo) {  // few, scattered queries: small blocks spread them over all SMs
+    block = 32;
+    smem = (size_t)std::max(P.cap, 1) * 8 * block;
+  }
   if (smem > 48 * 1024)
     PPP_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (P.nq > 0) {
     unsigned blocks = (unsigned)((P.nq + block - 1) / block);
-    PPP_LAUNCH(ctx, P.mode == 0 ? (P.normals ? "knn_normals" : "knn") : (P.normals ? "radius_normals" : "radius_fill"),
+    PPP_LAUNCH(ctx, P.use_redo ? "knn_redo" : P.mode == 0 ? (P.normals ? "knn_normals" : "knn") : (P.normals ? "radius_normals" : "radius_fill"),
                k_search, blocks, block, smem, P);
     PPP_CHECK_LAUNCH();
   }
   return PPP_OK;
+}
+
+template <int K>
+static int launch_knn_fast_k(ppp_cloud* c, SearchParams& P) {
+  ppp_ctx* ctx = c->ctx;
+  auto kern = k_knn_fast<K>;
+  const int block = 128;
+  size_t smem = (size_t)K * 8 * block;
+  if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  unsigned blocks = (unsigned)((P.nq + block - 1) / block);
+  PPP_LAUNCH(ctx, P.normals ? "knn_normals" : "knn", kern, blocks, block, smem, P);
+  PPP_CHECK_LAUNCH();
+  return PPP_OK;
+}
+
+// fast fixed-block kernel, then the generic ring-expanding kernel on whatever it handed over
+static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
+  ppp_ctx* ctx = c->ctx;
+  if (!P.q) {
+    if (!c->dup_flag) {
+      PPP_TRY(dev_alloc(ctx, &c->dup_flag, 1));
+      PPP_CUDA(cudaMemsetAsync(c->dup_flag, 0, sizeof(int32_t), ctx->stream));
+    }
+    P.dup_flag = c->dup_flag;
+    if (P.first == 0 && P.nq == c->n_finite) c->dup_known = true;
+  }
+  int32_t* redo = nullptr;
+  PPP_TRY(dev_alloc(ctx, &redo, (size_t)P.nq + 1));
+  PPP_CUDA(cudaMemsetAsync(redo, 0, sizeof(int32_t), ctx->stream));
+  P.redo_count = redo;
+  P.redo_list = redo + 1;
+  P.use_redo = 0;
+  int st;
+  if (P.cap <= 8) st = launch_knn_fast_k<8>(c, P);
+  else if (P.cap <= 16) st = launch_knn_fast_k<16>(c, P);
+  else st = launch_knn_fast_k<32>(c, P);
+  if (st == PPP_OK) {
+    // hand-over queries: one warp each (grid sized for the worst case; surplus warps exit at once)
+    P.use_redo = 1;
+    size_t smem = (size_t)WARPQ_WARPS * 32 * P.cap * 8;
+    if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(k_knn_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // more than ~1/8 of the queries failing means the cell size is badly matched; still correct, just slower
+    unsigned blocks = (unsigned)std::min<int64_t>((P.nq + WARPQ_WARPS - 1) / WARPQ_WARPS, (int64_t)ctx->sm_count * 8);
+    PPP_LAUNCH(ctx, "knn_redo", k_knn_warp, blocks, WARPQ_WARPS * 32, smem, P);
+    PPP_CHECK_LAUNCH();
+  }
+  if (st == PPP_OK && getenv("PPP_DEBUG")) {
+    int32_t n_redo = 0;
+    cudaMemcpyAsync(&n_redo, redo, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    fprintf(stderr, "[ppp] knn fast path: %lld queries, %d handed to the ring-expanding kernel (h=%g, R0=%d)\n",
+            (long long)P.nq, n_redo, (double)P.g.h, P.R0);
+  }
+  dev_free(ctx, redo);
+  return st;
 }
 
 int knn_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq, int q_stride_f, int64_t first, int k,
@@ -254,6 +630,7 @@ int knn_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq
                P.normals, normal_stride_f);
     PPP_CHECK_LAUNCH();
   }
+  if (k <= 32 && nq > 0 && !getenv("PPP_KNN_GENERIC")) return launch_knn_fast(c, P);
   return launch_search(c, P);
 }
 

@@ -98,8 +98,10 @@ __device__ __forceinline__ void compute_roots(float m00, float m01, float m02, f
     if (q > 0.0f) q = 0.0f;
     float rho = __fsqrt_rn(-a_over_3);
     float theta = __fmul_rn((float)atan2((double)__fsqrt_rn(-q), (double)half_b), s_inv3);
-    float cos_theta = (float)cos((double)theta);
-    float sin_theta = (float)sin((double)theta);
+    double sd, cd;
+    sincos((double)theta, &sd, &cd);
+    float cos_theta = (float)cd;
+    float sin_theta = (float)sd;
     roots[0] = __fadd_rn(c2_over_3, __fmul_rn(__fmul_rn(2.0f, rho), cos_theta));
     roots[1] = __fsub_rn(c2_over_3, __fmul_rn(rho, __fadd_rn(cos_theta, __fmul_rn(s_sqrt3, sin_theta))));
     roots[2] = __fsub_rn(c2_over_3, __fmul_rn(rho, __fsub_rn(cos_theta, __fmul_rn(s_sqrt3, sin_theta))));

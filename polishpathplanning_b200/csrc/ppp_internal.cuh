@@ -92,6 +92,9 @@ struct ppp_cloud {
   double *c_y = nullptr, *c_x = nullptr, *c_z = nullptr;
   int64_t c_cap = 0;
   int c_S_cap = 0;
+  // set by the self-query searches: the cloud holds distinct points at float distance 0
+  int32_t* dup_flag = nullptr;
+  bool dup_known = false;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -165,8 +168,9 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& g, int64_t first, int64
                           const float vp[3], unsigned flags, float* normals_dev, int normal_stride_f);
 
 // slices.cu
-int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center,
-                 int64_t** offsets_dev_out, int32_t** idx_dev_out, int64_t* total_out, float** planes_dev_out);
-int contours_launch(ppp_cloud* c, const GridStore& g, const float* planes_dev, int S, float half_width,
-                    int truncate_center, const int64_t* band_off_dev, const int32_t* band_idx_dev,
-                    int64_t band_total, const int64_t* band_off_host, int mode, int64_t* total_nodes_out);
+int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center, int sort_bands,
+                 int64_t** offsets_dev_out, int32_t** idx_dev_out, int64_t* total_out, float** planes_dev_out,
+                 std::vector<int64_t>* offsets_host_out);
+int contours_launch(ppp_cloud* c, const GridStore& g, const float* planes_dev, int S, const int64_t* band_off_dev,
+                    const int32_t* band_idx_dev, int64_t band_total, const std::vector<int64_t>& band_off_host, int mode,
+                    int64_t* total_nodes_out);

@@ -34,24 +34,82 @@ __device__ __forceinline__ void band_range(const BandSet& b, float x, int& first
   first = l;
 }
 
-// PassThrough: finite point, !(x < lo || x > hi).  Pass 1 counts, pass 2 fills (unordered),
-// then each band is sorted by point index (PassThrough returns ascending indices).
-template <bool FILL>
-__global__ void __launch_bounds__(256) k_band_scan(BandSet b, const float4* __restrict__ xyz4, int64_t n,
-                                                   int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
-                                                   int32_t* __restrict__ idx_out) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 p = __ldg(xyz4 + i);
-  if (p.w != p.w) return;
-  int f, l;
-  band_range(b, p.x, f, l);
-  for (int t = f; t < l; t++) {
-    // lo/hi sorted together only when all bands have one width; re-test to stay exact otherwise
-    if (p.x < __ldg(b.lo + t) || p.x > __ldg(b.hi + t)) continue;
-    int s = __ldg(b.slice + t);
-    int pos = atomicAdd(counts + s, 1);
-    if (FILL) idx_out[offsets[s] + pos] = (int32_t)i;
+// PassThrough: finite point, !(x < lo || x > hi).
+// Each block owns a contiguous chunk of the cloud and histograms its members per slice in shared
+// memory (global atomics on S counters serialise at ~50 ns per update; shared-memory atomics do
+// not), then touches each global counter once.  The fill pass reserves one contiguous range per
+// (block, slice) the same way and places members with shared-memory ranks.  Order inside a band
+// is arbitrary here; k_band_sort restores PassThrough's ascending-index order where a caller
+// needs it (ppp_slice_bands output, the order-dependent gen-2 pairing).
+constexpr int BAND_SMEM_BINS = 12288;  // 48 KB of int32
+
+template <typename F>
+__device__ __forceinline__ void for_memberships(const BandSet& b, float x, F&& f) {
+  int first, last;
+  band_range(b, x, first, last);
+  for (int t = first; t < last; t++) {
+    // lo/hi are sorted together only when all bands have one width; re-test to stay exact otherwise
+    if (x < __ldg(b.lo + t) || x > __ldg(b.hi + t)) continue;
+    f(t);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_band_count(BandSet b, const float4* __restrict__ xyz4, int64_t n, int64_t chunk,
+                                                    int use_smem, int32_t* __restrict__ counts) {
+  extern __shared__ int32_t s_cnt[];
+  if (use_smem) {
+    for (int t = threadIdx.x; t < b.S; t += blockDim.x) s_cnt[t] = 0;
+    __syncthreads();
+  }
+  int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, n);
+  for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    float4 p = __ldg(xyz4 + i);
+    if (p.w != p.w) continue;
+    for_memberships(b, p.x, [&](int t) {
+      if (use_smem) atomicAdd(s_cnt + t, 1);
+      else atomicAdd(counts + __ldg(b.slice + t), 1);
+    });
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < b.S; t += blockDim.x) {
+      int c = s_cnt[t];
+      if (c) atomicAdd(counts + __ldg(b.slice + t), c);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_band_fill(BandSet b, const float4* __restrict__ xyz4, int64_t n, int64_t chunk,
+                                                   int use_smem, int32_t* __restrict__ cursor,
+                                                   const int64_t* __restrict__ offsets, int32_t* __restrict__ idx_out) {
+  extern __shared__ int32_t s_mem[];
+  int32_t* s_cnt = s_mem;
+  int32_t* s_base = s_mem + b.S;
+  int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, n);
+  if (use_smem) {
+    for (int t = threadIdx.x; t < b.S; t += blockDim.x) s_cnt[t] = 0;
+    __syncthreads();
+    for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+      float4 p = __ldg(xyz4 + i);
+      if (p.w != p.w) continue;
+      for_memberships(b, p.x, [&](int t) { atomicAdd(s_cnt + t, 1); });
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < b.S; t += blockDim.x) {
+      int c = s_cnt[t];
+      s_base[t] = c ? atomicAdd(cursor + __ldg(b.slice + t), c) : 0;
+      s_cnt[t] = 0;
+    }
+    __syncthreads();
+  }
+  for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
+    float4 p = __ldg(xyz4 + i);
+    if (p.w != p.w) continue;
+    for_memberships(b, p.x, [&](int t) {
+      int s = __ldg(b.slice + t);
+      int pos = use_smem ? s_base[t] + atomicAdd(s_cnt + t, 1) : atomicAdd(cursor + s, 1);
+      idx_out[offsets[s] + pos] = (int32_t)i;
+    });
   }
 }
 
@@ -339,6 +397,120 @@ __global__ void __launch_bounds__(CT_THREADS) k_contour(ContourParams P) {
   if (threadIdx.x == 0) P.n_nodes[s] = nodes;
 }
 
+// ---- SectPath pairing (variant B), fully parallel over band members ---------------------------
+// One thread per band member m (any order inside a band).  A member with x > plane is a
+// "left" query i of src/contour_alg.cpp:185-211: pr = NN_Er(pl); right_pair = NN_full(pr);
+// pl' = NN_El(pr); left_pair = NN_full(pl'); node = interpolation of the pair onto the plane.
+// The map insertion order of the reference is the ascending-index order of El, so the original
+// index of the left query decides between equal-y nodes (k_slice_order).
+struct PairParams {
+  GridView g;
+  const float4* xyz4;
+  const float* planes;
+  const float* lo;
+  const float* hi;
+  const int64_t* band_off;
+  const int32_t* band_idx;
+  int S;
+  int64_t M;
+  const int32_t* dup_flag;  // device flag: cloud has distinct points at float distance 0 (nullptr: assume yes)
+  u64* keys;
+  float* ys;
+  float* zs;
+};
+
+__global__ void __launch_bounds__(128) k_pair_nodes(PairParams P) {
+  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= P.M) return;
+  // slice of member m: last s with band_off[s] <= m
+  int l = 0, r = P.S;
+  while (l < r) { int mid = (l + r) >> 1; if (__ldg(P.band_off + mid + 1) <= m) l = mid + 1; else r = mid; }
+  const int s = l;
+  const float plane = __ldg(P.planes + s), lo = __ldg(P.lo + s), hi = __ldg(P.hi + s);
+  const int idx = __ldg(P.band_idx + m);
+  float4 pl = __ldg(P.xyz4 + idx);
+  u64 key = PPP_KEY_INF;
+  float y = 0.f, z = 0.f;
+  if (__fsub_rn(pl.x, plane) > 0.0f) {
+    const int32_t* band = P.band_idx + __ldg(P.band_off + s);
+    const int B = (int)(__ldg(P.band_off + s + 1) - __ldg(P.band_off + s));
+    const bool dups = P.dup_flag ? (*P.dup_flag != 0) : true;
+    int ri = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, band, B);
+    if (ri >= 0) {
+      float4 pr = __ldg(P.xyz4 + ri);
+      int rc = dups ? nn_full(P.g, pr.x, pr.y, pr.z) : ri;
+      int li = nn_side(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, band, B);
+      float4 pl2 = __ldg(P.xyz4 + li);
+      int lc = dups ? nn_full(P.g, pl2.x, pl2.y, pl2.z) : li;
+      float4 a = __ldg(P.xyz4 + rc);  // index_right
+      float4 b = __ldg(P.xyz4 + lc);  // index_left
+      float t = __fdiv_rn(__fsub_rn(plane, a.x), __fsub_rn(b.x, a.x));
+      y = __fadd_rn(a.y, __fmul_rn(t, __fsub_rn(b.y, a.y)));
+      z = __fadd_rn(a.z, __fmul_rn(t, __fsub_rn(b.z, a.z)));
+      // low word = slot inside the band (the payload address); equal-y ties are resolved by
+      // original index in k_slice_order
+      key = ((u64)f2ord_dev(__fadd_rn(y, 0.0f)) << 32) | (u64)(uint32_t)(m - __ldg(P.band_off + s));
+    }
+  }
+  P.keys[m] = key;
+  P.ys[m] = y;
+  P.zs[m] = z;
+}
+
+// CTA per slice: sort the slice's node keys (INF = not a node) by (y, slot), then keep one node
+// per distinct y with std::map semantics: the key of the FIRST insertion (lowest left index; only
+// matters for -0.0 / +0.0) and the value of the LAST insertion (highest left index).
+__global__ void __launch_bounds__(CT_THREADS) k_slice_order(const int64_t* __restrict__ band_off, const int32_t* __restrict__ band_idx,
+                                                            const u64* __restrict__ keys_g, const float* __restrict__ ys,
+                                                            const float* __restrict__ zs, u64* __restrict__ scratch,
+                                                            int smem_cap, double* __restrict__ ty, double* __restrict__ tz,
+                                                            int32_t* __restrict__ n_nodes) {
+  extern __shared__ u64 s_keys64[];
+  __shared__ int s_warp[CT_THREADS / 32];
+  __shared__ int s_valid;
+  const int s = blockIdx.x;
+  const int64_t o = band_off[s];
+  const int B = (int)(band_off[s + 1] - o);
+  u64* k = (B <= smem_cap) ? s_keys64 : (scratch + o);
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  int local_valid = 0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    u64 key = keys_g[o + i];
+    k[i] = key;
+    local_valid += key != PPP_KEY_INF;
+  }
+  if (local_valid) atomicAdd(&s_valid, local_valid);
+  __syncthreads();
+  const int nv = s_valid;
+  cta_sort(k, B);
+  int nodes = 0;
+  for (int base = 0; base < nv; base += CT_THREADS) {
+    int i = base + threadIdx.x;
+    bool first = false;
+    u64 key = 0;
+    if (i < nv) {
+      key = k[i];
+      first = (i == 0) || ((k[i - 1] >> 32) != (key >> 32));
+    }
+    int r = cta_flag_rank(first, s_warp, nodes);
+    if (first) {
+      int slot = (int)(uint32_t)(key & 0xFFFFFFFFull);
+      int idx = __ldg(band_idx + o + slot);
+      int lo_idx = idx, hi_idx = idx, lo_slot = slot, hi_slot = slot;
+      for (int j = i + 1; j < nv && (k[j] >> 32) == (key >> 32); j++) {
+        int sl = (int)(uint32_t)(k[j] & 0xFFFFFFFFull);
+        int id = __ldg(band_idx + o + sl);
+        if (id < lo_idx) { lo_idx = id; lo_slot = sl; }
+        if (id > hi_idx) { hi_idx = id; hi_slot = sl; }
+      }
+      ty[o + r] = (double)ys[o + lo_slot];
+      tz[o + r] = (double)zs[o + hi_slot];
+    }
+  }
+  if (threadIdx.x == 0) n_nodes[s] = nodes;
+}
+
 __global__ void __launch_bounds__(256) k_compact_nodes(const int64_t* __restrict__ band_off, const int64_t* __restrict__ node_off,
                                                       const float* __restrict__ planes, const double* __restrict__ ty,
                                                       const double* __restrict__ tz, double* __restrict__ y,
@@ -368,9 +540,11 @@ static void band_limits_host(float plane_x, float half_width, int truncate_cente
   }
 }
 
-// Device arrays produced: offsets (S+1, int64), idx (total), planes/lo/hi (3*S floats, original order).
-int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center,
-                 int64_t** offsets_dev_out, int32_t** idx_dev_out, int64_t* total_out, float** planes_dev_out) {
+// Device arrays produced: offsets (S+1, int64), idx (total), planes/lo/hi (3*S floats, original
+// order).  sort_bands != 0: every band in ascending point index (PassThrough order).
+int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center, int sort_bands,
+                 int64_t** offsets_dev_out, int32_t** idx_dev_out, int64_t* total_out, float** planes_dev_out,
+                 std::vector<int64_t>* offsets_host_out) {
   ppp_ctx* ctx = c->ctx;
   *offsets_dev_out = nullptr; *idx_dev_out = nullptr; *planes_dev_out = nullptr; *total_out = 0;
   std::vector<float> lo(S), hi(S);
@@ -400,8 +574,6 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
     stage[3 * S + t] = lo[s];
     stage[4 * S + t] = hi[s];
   }
-  // hi must be non-decreasing in lo-sorted order for the range lookup; true for a single width
-  // (float rounding of x +/- hw is monotone). Otherwise widen the lookup: use running max/min.
   float* fdev = nullptr;
   int32_t* pdev = nullptr;
   PPP_TRY(dev_alloc(ctx, &fdev, 5 * (size_t)std::max(S, 1)));
@@ -410,37 +582,43 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
   int64_t* offsets = nullptr;
   PPP_TRY(dev_alloc(ctx, &counts, (size_t)std::max(S, 1)));
   PPP_TRY(dev_alloc(ctx, &offsets, (size_t)S + 1));
+  PPP_CUDA(cudaMemsetAsync(counts, 0, (size_t)std::max(S, 1) * sizeof(int32_t), ctx->stream));
   if (S > 0) {
     PPP_CUDA(cudaMemcpyAsync(fdev, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     PPP_CUDA(cudaMemcpyAsync(pdev, perm.data(), (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    // the pageable staging vectors must stay alive until the copies have been consumed
-    PPP_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  PPP_CUDA(cudaMemsetAsync(counts, 0, (size_t)std::max(S, 1) * sizeof(int32_t), ctx->stream));
   BandSet b{fdev + 3 * (size_t)S, fdev + 4 * (size_t)S, pdev, Sv};
-  unsigned blocks = (unsigned)((c->n + 255) / 256);
+  const int use_smem = Sv <= BAND_SMEM_BINS / 2;  // fill needs two arrays
+  unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((c->n + 1023) / 1024, (int64_t)ctx->sm_count * 8));
+  int64_t chunk = (c->n + blocks - 1) / blocks;
   if (c->n > 0 && Sv > 0) {
-    auto kc = k_band_scan<false>;
-    PPP_LAUNCH(ctx, "band_count", kc, blocks, 256, 0, b, (const float4*)c->xyz4, c->n, counts, (const int64_t*)nullptr,
-               (int32_t*)nullptr);
+    PPP_LAUNCH(ctx, "band_count", k_band_count, blocks, 256, use_smem ? (size_t)Sv * 4 : 0, b, (const float4*)c->xyz4, c->n,
+               chunk, use_smem, counts);
     PPP_CHECK_LAUNCH();
   }
   PPP_TRY(scan_exclusive_i32_to_i64(ctx, counts, offsets, S));
-  int64_t total = 0;
-  PPP_CUDA(cudaMemcpyAsync(&total, offsets + S, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<int64_t> off_h((size_t)S + 1, 0);
+  PPP_CUDA(cudaMemcpyAsync(off_h.data(), offsets, ((size_t)S + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));  // also covers the pageable staging vectors above
+  int64_t total = off_h[S];
   int32_t* idx = nullptr;
   PPP_TRY(dev_alloc(ctx, &idx, (size_t)std::max<int64_t>(total, 1)));
   if (total > 0) {
     PPP_CUDA(cudaMemsetAsync(counts, 0, (size_t)S * sizeof(int32_t), ctx->stream));
-    auto kf = k_band_scan<true>;
-    PPP_LAUNCH(ctx, "band_fill", kf, blocks, 256, 0, b, (const float4*)c->xyz4, c->n, counts, (const int64_t*)offsets, idx);
+    if (use_smem) PPP_CUDA(cudaFuncSetAttribute(k_band_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_SMEM_BINS * 4));
+    PPP_LAUNCH(ctx, "band_fill", k_band_fill, blocks, 256, use_smem ? (size_t)Sv * 8 : 0, b, (const float4*)c->xyz4, c->n, chunk,
+               use_smem, counts, (const int64_t*)offsets, idx);
     PPP_CHECK_LAUNCH();
-    int smem_cap = 24576;  // 96 KB of int32
-    PPP_CUDA(cudaFuncSetAttribute(k_band_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 4));
-    PPP_LAUNCH(ctx, "band_sort", k_band_sort, (unsigned)S, CT_THREADS, (size_t)smem_cap * 4, (const int64_t*)offsets, idx,
-               smem_cap);
-    PPP_CHECK_LAUNCH();
+    if (sort_bands) {
+      int64_t maxB = 0;
+      for (int s = 0; s < S; s++) maxB = std::max(maxB, off_h[s + 1] - off_h[s]);
+      int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(maxB, 1), 49152);  // <= 192 KB of int32
+      if (smem_cap * 4 > 48 * 1024)
+        PPP_CUDA(cudaFuncSetAttribute(k_band_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 4));
+      PPP_LAUNCH(ctx, "band_sort", k_band_sort, (unsigned)S, CT_THREADS, (size_t)smem_cap * 4, (const int64_t*)offsets, idx,
+                 smem_cap);
+      PPP_CHECK_LAUNCH();
+    }
   }
   dev_free(ctx, counts);
   dev_free(ctx, pdev);
@@ -448,41 +626,19 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
   *idx_dev_out = idx;
   *planes_dev_out = fdev;  // [planes][lo][hi] in original order (+ sorted copies behind)
   *total_out = total;
+  if (offsets_host_out) *offsets_host_out = std::move(off_h);
   return PPP_OK;
 }
 
-int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, int S, float half_width,
-                    int truncate_center, const int64_t* band_off_dev, const int32_t* band_idx_dev, int64_t band_total,
-                    const int64_t* band_off_host, int mode, int64_t* total_nodes_out) {
-  (void)half_width; (void)truncate_center; (void)band_off_host;
+static int finish_nodes(ppp_cloud* c, int S, const int64_t* band_off_dev, const float* planes_dev, const int32_t* n_nodes,
+                        const double* ty, const double* tz, int64_t* total_nodes_out) {
   ppp_ctx* ctx = c->ctx;
-  *total_nodes_out = 0;
-  size_t M = (size_t)std::max<int64_t>(band_total, 1);
-  ContourParams P{};
-  P.g = gs.v; P.xyz4 = c->xyz4;
-  P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
-  P.band_off = band_off_dev; P.band_idx = band_idx_dev; P.mode = mode;
-  PPP_TRY(dev_alloc(ctx, &P.El, M)); PPP_TRY(dev_alloc(ctx, &P.Er, M));
-  PPP_TRY(dev_alloc(ctx, &P.keys, M));
-  PPP_TRY(dev_alloc(ctx, &P.ys, M)); PPP_TRY(dev_alloc(ctx, &P.zs, M));
-  PPP_TRY(dev_alloc(ctx, &P.lp, M)); PPP_TRY(dev_alloc(ctx, &P.rp, M));
-  if (mode == PPP_PAIR_GEN2) {
-    PPP_TRY(dev_alloc(ctx, &P.posR, M)); PPP_TRY(dev_alloc(ctx, &P.posL, M));
-    PPP_TRY(dev_alloc(ctx, &P.fl, M)); PPP_TRY(dev_alloc(ctx, &P.fr, M));
-  }
-  PPP_TRY(dev_alloc(ctx, &P.ty, M)); PPP_TRY(dev_alloc(ctx, &P.tz, M));
-  PPP_TRY(dev_alloc(ctx, &P.n_nodes, (size_t)std::max(S, 1)));
-  // (re)allocate the cloud-owned result buffers
   if (c->c_S_cap < S + 1) {
     dev_free(ctx, c->c_node_off);
     PPP_TRY(dev_alloc(ctx, &c->c_node_off, (size_t)S + 1));
     c->c_S_cap = S + 1;
   }
-  if (S > 0) {
-    PPP_LAUNCH(ctx, "contour", k_contour, (unsigned)S, CT_THREADS, 0, P);
-    PPP_CHECK_LAUNCH();
-  }
-  PPP_TRY(scan_exclusive_i32_to_i64(ctx, P.n_nodes, c->c_node_off, S));
+  PPP_TRY(scan_exclusive_i32_to_i64(ctx, n_nodes, c->c_node_off, S));
   int64_t total = 0;
   PPP_CUDA(cudaMemcpyAsync(&total, c->c_node_off + S, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   PPP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -494,12 +650,71 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
   }
   if (total > 0) {
     PPP_LAUNCH(ctx, "compact_nodes", k_compact_nodes, (unsigned)S, 256, 0, band_off_dev, (const int64_t*)c->c_node_off,
-               planes_dev, (const double*)P.ty, (const double*)P.tz, c->c_y, c->c_x, c->c_z);
+               planes_dev, ty, tz, c->c_y, c->c_x, c->c_z);
     PPP_CHECK_LAUNCH();
   }
-  dev_free(ctx, P.El); dev_free(ctx, P.Er); dev_free(ctx, P.keys); dev_free(ctx, P.ys); dev_free(ctx, P.zs);
-  dev_free(ctx, P.lp); dev_free(ctx, P.rp); dev_free(ctx, P.posR); dev_free(ctx, P.posL); dev_free(ctx, P.fl);
-  dev_free(ctx, P.fr); dev_free(ctx, P.ty); dev_free(ctx, P.tz); dev_free(ctx, P.n_nodes);
   *total_nodes_out = total;
   return PPP_OK;
+}
+
+// band_off_host: S+1 offsets (for sizing shared memory).  Variant A needs index-sorted bands.
+int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, int S, const int64_t* band_off_dev,
+                    const int32_t* band_idx_dev, int64_t band_total, const std::vector<int64_t>& band_off_host, int mode,
+                    int64_t* total_nodes_out) {
+  ppp_ctx* ctx = c->ctx;
+  *total_nodes_out = 0;
+  size_t M = (size_t)std::max<int64_t>(band_total, 1);
+  double *ty = nullptr, *tz = nullptr;
+  int32_t* n_nodes = nullptr;
+  PPP_TRY(dev_alloc(ctx, &ty, M)); PPP_TRY(dev_alloc(ctx, &tz, M));
+  PPP_TRY(dev_alloc(ctx, &n_nodes, (size_t)std::max(S, 1)));
+  int st = PPP_OK;
+  if (mode == PPP_PAIR_SECT) {
+    PairParams P{};
+    P.g = gs.v; P.xyz4 = c->xyz4;
+    P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
+    P.band_off = band_off_dev; P.band_idx = band_idx_dev; P.S = S; P.M = band_total;
+    P.dup_flag = c->dup_known ? c->dup_flag : nullptr;
+    PPP_TRY(dev_alloc(ctx, &P.keys, M)); PPP_TRY(dev_alloc(ctx, &P.ys, M)); PPP_TRY(dev_alloc(ctx, &P.zs, M));
+    if (band_total > 0) {
+      PPP_LAUNCH(ctx, "pair_nodes", k_pair_nodes, (unsigned)((band_total + 127) / 128), 128, 0, P);
+      PPP_CHECK_LAUNCH();
+    }
+    int64_t maxB = 0;
+    for (int s = 0; s < S; s++) maxB = std::max(maxB, band_off_host[s + 1] - band_off_host[s]);
+    int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(maxB, 1), 24576);  // <= 192 KB of u64
+    u64* scratch = nullptr;
+    if (maxB > smem_cap) PPP_TRY(dev_alloc(ctx, &scratch, M));
+    if (S > 0) {
+      if ((size_t)smem_cap * 8 > 48 * 1024)
+        PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
+      PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, CT_THREADS, (size_t)smem_cap * 8, band_off_dev, band_idx_dev,
+                 (const u64*)P.keys, (const float*)P.ys, (const float*)P.zs, scratch, smem_cap, ty, tz, n_nodes);
+      PPP_CHECK_LAUNCH();
+    }
+    st = finish_nodes(c, S, band_off_dev, planes_dev, n_nodes, ty, tz, total_nodes_out);
+    dev_free(ctx, P.keys); dev_free(ctx, P.ys); dev_free(ctx, P.zs); dev_free(ctx, scratch);
+  } else {
+    ContourParams P{};
+    P.g = gs.v; P.xyz4 = c->xyz4;
+    P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
+    P.band_off = band_off_dev; P.band_idx = band_idx_dev; P.mode = mode;
+    P.ty = ty; P.tz = tz; P.n_nodes = n_nodes;
+    PPP_TRY(dev_alloc(ctx, &P.El, M)); PPP_TRY(dev_alloc(ctx, &P.Er, M));
+    PPP_TRY(dev_alloc(ctx, &P.keys, M));
+    PPP_TRY(dev_alloc(ctx, &P.ys, M)); PPP_TRY(dev_alloc(ctx, &P.zs, M));
+    PPP_TRY(dev_alloc(ctx, &P.lp, M)); PPP_TRY(dev_alloc(ctx, &P.rp, M));
+    PPP_TRY(dev_alloc(ctx, &P.posR, M)); PPP_TRY(dev_alloc(ctx, &P.posL, M));
+    PPP_TRY(dev_alloc(ctx, &P.fl, M)); PPP_TRY(dev_alloc(ctx, &P.fr, M));
+    if (S > 0) {
+      PPP_LAUNCH(ctx, "contour_gen2", k_contour, (unsigned)S, CT_THREADS, 0, P);
+      PPP_CHECK_LAUNCH();
+    }
+    st = finish_nodes(c, S, band_off_dev, planes_dev, n_nodes, ty, tz, total_nodes_out);
+    dev_free(ctx, P.El); dev_free(ctx, P.Er); dev_free(ctx, P.keys); dev_free(ctx, P.ys); dev_free(ctx, P.zs);
+    dev_free(ctx, P.lp); dev_free(ctx, P.rp); dev_free(ctx, P.posR); dev_free(ctx, P.posL); dev_free(ctx, P.fl);
+    dev_free(ctx, P.fr);
+  }
+  dev_free(ctx, ty); dev_free(ctx, tz); dev_free(ctx, n_nodes);
+  return st;
 }
