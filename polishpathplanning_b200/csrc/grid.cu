@@ -42,22 +42,35 @@ __global__ void __launch_bounds__(256) k_pack_bbox(const float* __restrict__ raw
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
   float mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
   unsigned cnt = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float x, y, z;
-    if (vec_ok) {
-      float4 p = __ldg(reinterpret_cast<const float4*>(raw + i * sf));
-      x = p.x; y = p.y; z = p.z;
-    } else {
-      const float* p = raw + i * sf;
-      x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+  constexpr int PPT = 4;  // points per thread per sweep: PPT independent loads in flight
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x * PPT; base < n; base += (int64_t)gridDim.x * blockDim.x * PPT) {
+    float x[PPT], y[PPT], z[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+      int64_t i = base + (int64_t)j * blockDim.x + threadIdx.x;
+      x[j] = y[j] = z[j] = 0.f;
+      if (i < n) {
+        if (vec_ok) {
+          float4 p = __ldg(reinterpret_cast<const float4*>(raw + i * sf));
+          x[j] = p.x; y[j] = p.y; z[j] = p.z;
+        } else {
+          const float* p = raw + i * sf;
+          x[j] = __ldg(p); y[j] = __ldg(p + 1); z[j] = __ldg(p + 2);
+        }
+      }
     }
-    bool fin = finite3(x, y, z);
-    xyz4[i] = make_float4(x, y, z, fin ? 0.0f : CUDART_NAN_F);
-    if (fin) {
-      cnt++;
-      mn[0] = fminf(mn[0], x); mx[0] = fmaxf(mx[0], x);
-      mn[1] = fminf(mn[1], y); mx[1] = fmaxf(mx[1], y);
-      mn[2] = fminf(mn[2], z); mx[2] = fmaxf(mx[2], z);
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+      int64_t i = base + (int64_t)j * blockDim.x + threadIdx.x;
+      if (i >= n) continue;
+      bool fin = finite3(x[j], y[j], z[j]);
+      xyz4[i] = make_float4(x[j], y[j], z[j], fin ? 0.0f : CUDART_NAN_F);
+      if (fin) {
+        cnt++;
+        mn[0] = fminf(mn[0], x[j]); mx[0] = fmaxf(mx[0], x[j]);
+        mn[1] = fminf(mn[1], y[j]); mx[1] = fmaxf(mx[1], y[j]);
+        mn[2] = fminf(mn[2], z[j]); mx[2] = fmaxf(mx[2], z[j]);
+      }
     }
   }
 #pragma unroll
@@ -69,13 +82,32 @@ __global__ void __launch_bounds__(256) k_pack_bbox(const float* __restrict__ raw
     }
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
-  if ((threadIdx.x & 31) == 0 && cnt) {
+  // block-level combine, then ONE set of global atomics per block (per-warp atomics on the same
+  // seven addresses serialise in L2 and dominated this kernel)
+  __shared__ float s_mn[8][3], s_mx[8][3];
+  __shared__ unsigned s_cnt[8];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
-      atomicMin(&acc->mn[d], f2ord(mn[d]));
-      atomicMax(&acc->mx[d], f2ord(mx[d]));
+    for (int d = 0; d < 3; d++) { s_mn[w][d] = mn[d]; s_mx[w][d] = mx[d]; }
+    s_cnt[w] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); i++) {
+      tot += s_cnt[i];
+#pragma unroll
+      for (int d = 0; d < 3; d++) { mn[d] = fminf(mn[d], s_mn[i][d]); mx[d] = fmaxf(mx[d], s_mx[i][d]); }
     }
-    atomicAdd(&acc->n_finite, (unsigned long long)cnt);
+    if (tot) {
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        atomicMin(&acc->mn[d], f2ord(mn[d]));
+        atomicMax(&acc->mx[d], f2ord(mx[d]));
+      }
+      atomicAdd(&acc->n_finite, (unsigned long long)tot);
+    }
   }
 }
 
@@ -120,7 +152,7 @@ int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes) {
   PPP_LAUNCH(ctx, "bbox_init", k_bbox_init, 1, 1, 0, acc);
   PPP_CHECK_LAUNCH();
   if (c->n > 0) {
-    int blocks = (int)std::min<int64_t>((c->n + 255) / 256, (int64_t)ctx->sm_count * 8);
+    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((c->n + 1023) / 1024, (int64_t)ctx->sm_count * 16));
     PPP_LAUNCH(ctx, "pack_bbox", k_pack_bbox, blocks, 256, 0, (const float*)pts_dev, c->n, sf, vec_ok, c->xyz4, acc);
     PPP_CHECK_LAUNCH();
   }

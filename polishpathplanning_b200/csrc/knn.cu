@@ -229,11 +229,15 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 5 : 2)) k_knn_fast(SearchParam
   // U candidates per iteration: the loads are issued together, then consumed.
   constexpr int U = 4;
   int zero_cnt = 0;
+  u64* wptr = pend_s;  // next free pending slot of this thread (= pend_s + pc * BD)
 #pragma unroll 1
-  for (int dv = -R; dv <= R + 1; dv++) {
+  for (int j = 0; j <= 2 * R + 1; j++) {
+    // rows nearest first: 0, -1, +1, -2, +2, ... so the first merge already yields a tight k-th
+    // distance and the outer rows add few candidates
+    const int dv = (j & 1) ? -((j + 1) >> 1) : (j >> 1);
     int s = 0, e = 0;
     int v = cv + dv;
-    const bool drain = dv == R + 1;
+    const bool drain = j == 2 * R + 1;
     if (!drain && act && v >= 0 && v < g.nv) {
       int a = max(cu - R, 0), b = min(cu + R, g.nu - 1);
       if (a <= b) {
@@ -244,8 +248,8 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 5 : 2)) k_knn_fast(SearchParam
     }
     // drain row: one empty iteration with trigger level 0.  Written arithmetically (no select on
     // `drain`) so the compiler does not clone the loop body, and with it the flush networks.
-    const int n_it = (__reduce_max_sync(0xffffffffu, e - s) + U - 1) / U + (dv - R > 0 ? 1 : 0);
-    const int trig = min(K - U, (R + 1 - dv) * K);  // flush when some lane could overflow next iteration
+    const int n_it = (__reduce_max_sync(0xffffffffu, e - s) + U - 1) / U + (j - 2 * R > 0 ? 1 : 0);
+    const int trig = min(K - U, (2 * R + 1 - j) * K);  // flush when some lane could overflow next iteration
 #pragma unroll 1
     for (int it = 0; it < n_it; it++) {
       float4 c[U];
@@ -262,11 +266,12 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 5 : 2)) k_knn_fast(SearchParam
         u64 key = make_key(d2, __float_as_int(c[u].w));
         zero_cnt += (in[u] && d2 == 0.0f) ? 1 : 0;
         if (in[u] && key < tau) {
-          pend_s[pc * BD] = key;
-          pc++;
+          *wptr = key;
+          wptr += BD;
         }
       }
-      if (__any_sync(0xffffffffu, pc > trig)) flush();
+      pc = (int)(wptr - pend_s) / BD;
+      if (__any_sync(0xffffffffu, pc > trig)) { flush(); wptr = pend_s; }
     }
   }
   // a self query always sees itself at distance 0; a second zero-distance point is a duplicate

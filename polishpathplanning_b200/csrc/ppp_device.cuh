@@ -200,26 +200,30 @@ __device__ __forceinline__ void store_normal(float* base, int64_t row, int strid
 }
 
 // Visit every indexed point whose cell lies in the square annulus R_prev < max(|du|,|dv|) <= R
-// around (cu, cv)  (R_prev = -1: the whole (2R+1)^2 block).
+// around (cu, cv)  (R_prev = -1: the whole (2R+1)^2 block).  [ulo, uhi] optionally restricts the
+// visited cell columns (callers that only want points of an x-interval).
 template <typename F>
-__device__ __forceinline__ void visit_annulus(const GridView& g, int cu, int cv, int R_prev, int R, F&& f) {
+__device__ __forceinline__ void visit_annulus(const GridView& g, int cu, int cv, int R_prev, int R, F&& f,
+                                              int ulo = -2147483647, int uhi = 2147483647) {
   int v0 = max(cv - R, 0), v1 = min(cv + R, g.nv - 1);
+  ulo = max(ulo, 0);
+  uhi = min(uhi, g.nu - 1);
   for (int v = v0; v <= v1; v++) {
     int adv = abs(v - cv);
     const int32_t* row = g.cell_start + (int64_t)v * g.nu;
     if (adv > R_prev) {
-      int a = max(cu - R, 0), b = min(cu + R, g.nu - 1);
+      int a = max(cu - R, ulo), b = min(cu + R, uhi);
       if (a <= b) {
         int s = __ldg(row + a), e = __ldg(row + b + 1);
         for (int i = s; i < e; i++) f(__ldg(g.sorted + i));
       }
     } else {
-      int a = max(cu - R, 0), b = min(cu - R_prev - 1, g.nu - 1);
+      int a = max(cu - R, ulo), b = min(cu - R_prev - 1, uhi);
       if (a <= b) {
         int s = __ldg(row + a), e = __ldg(row + b + 1);
         for (int i = s; i < e; i++) f(__ldg(g.sorted + i));
       }
-      a = max(cu + R_prev + 1, 0); b = min(cu + R, g.nu - 1);
+      a = max(cu + R_prev + 1, ulo); b = min(cu + R, uhi);
       if (a <= b) {
         int s = __ldg(row + a), e = __ldg(row + b + 1);
         for (int i = s; i < e; i++) f(__ldg(g.sorted + i));

@@ -186,7 +186,8 @@ __device__ __forceinline__ int cta_flag_rank(bool flag, int* s_warp, int& runnin
   if (lane == 0) s_warp[w] = __popc(m);
   __syncthreads();
   int base = 0, tot = 0;
-  for (int i = 0; i < CT_THREADS / 32; i++) {
+  const int nw = (blockDim.x + 31) >> 5;
+  for (int i = 0; i < nw; i++) {
     int c = s_warp[i];
     if (i < w) base += c;
     tot += c;
@@ -222,10 +223,17 @@ __device__ int nn_side(const GridView& g, const float4* __restrict__ xyz4, float
   };
   int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
   int cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
+  // when x is the fast grid axis only the cell columns that overlap the wanted x-interval can
+  // hold members (cell coordinates are monotone in x)
+  int ulo = -2147483647, uhi = 2147483647;
+  if (g.au == 0) {
+    ulo = cell_coord_raw(want_left ? plane : lo, g.min_u, g.inv_h);
+    uhi = cell_coord_raw(want_left ? hi : plane, g.min_u, g.inv_h);
+  }
   int R = 1, R_prev = -1;
   bool done = false;
   while (true) {
-    visit_annulus(g, cu, cv, R_prev, R, [&](float4 c) { consider(c.x, c.y, c.z, __float_as_int(c.w)); });
+    visit_annulus(g, cu, cv, R_prev, R, [&](float4 c) { consider(c.x, c.y, c.z, __float_as_int(c.w)); }, ulo, uhi);
     if (best != PPP_KEY_INF) {
       float b2 = ring_bound2(g, R, cu, cv);
       float v = __uint_as_float((uint32_t)(best >> 32));
@@ -276,7 +284,7 @@ __device__ __forceinline__ int lower_pos(const int32_t* a, int n, int v) {
 }
 
 __global__ void __launch_bounds__(CT_THREADS) k_contour(ContourParams P) {
-  __shared__ int s_warp[CT_THREADS / 32];
+  __shared__ int s_warp[32];
   __shared__ int s_npairs;
   const int s = blockIdx.x;
   const int64_t o = P.band_off[s];
@@ -460,13 +468,15 @@ __global__ void __launch_bounds__(128) k_pair_nodes(PairParams P) {
 // CTA per slice: sort the slice's node keys (INF = not a node) by (y, slot), then keep one node
 // per distinct y with std::map semantics: the key of the FIRST insertion (lowest left index; only
 // matters for -0.0 / +0.0) and the value of the LAST insertion (highest left index).
-__global__ void __launch_bounds__(CT_THREADS) k_slice_order(const int64_t* __restrict__ band_off, const int32_t* __restrict__ band_idx,
-                                                            const u64* __restrict__ keys_g, const float* __restrict__ ys,
-                                                            const float* __restrict__ zs, u64* __restrict__ scratch,
-                                                            int smem_cap, double* __restrict__ ty, double* __restrict__ tz,
-                                                            int32_t* __restrict__ n_nodes) {
+constexpr int SO_THREADS = 1024;
+
+__global__ void __launch_bounds__(SO_THREADS) k_slice_order(const int64_t* __restrict__ band_off, const int32_t* __restrict__ band_idx,
+                                                           const u64* __restrict__ keys_g, const float* __restrict__ ys,
+                                                           const float* __restrict__ zs, u64* __restrict__ scratch,
+                                                           int smem_cap, double* __restrict__ ty, double* __restrict__ tz,
+                                                           int32_t* __restrict__ n_nodes) {
   extern __shared__ u64 s_keys64[];
-  __shared__ int s_warp[CT_THREADS / 32];
+  __shared__ int s_warp[32];
   __shared__ int s_valid;
   const int s = blockIdx.x;
   const int64_t o = band_off[s];
@@ -474,18 +484,16 @@ __global__ void __launch_bounds__(CT_THREADS) k_slice_order(const int64_t* __res
   u64* k = (B <= smem_cap) ? s_keys64 : (scratch + o);
   if (threadIdx.x == 0) s_valid = 0;
   __syncthreads();
-  int local_valid = 0;
+  // keep only the node keys (left members that found a pair); their order does not matter yet
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
     u64 key = keys_g[o + i];
-    k[i] = key;
-    local_valid += key != PPP_KEY_INF;
+    if (key != PPP_KEY_INF) k[atomicAdd(&s_valid, 1)] = key;
   }
-  if (local_valid) atomicAdd(&s_valid, local_valid);
   __syncthreads();
   const int nv = s_valid;
-  cta_sort(k, B);
+  cta_sort(k, nv);
   int nodes = 0;
-  for (int base = 0; base < nv; base += CT_THREADS) {
+  for (int base = 0; base < nv; base += blockDim.x) {
     int i = base + threadIdx.x;
     bool first = false;
     u64 key = 0;
@@ -688,7 +696,7 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     if (S > 0) {
       if ((size_t)smem_cap * 8 > 48 * 1024)
         PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
-      PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, CT_THREADS, (size_t)smem_cap * 8, band_off_dev, band_idx_dev,
+      PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, SO_THREADS, (size_t)smem_cap * 8, band_off_dev, band_idx_dev,
                  (const u64*)P.keys, (const float*)P.ys, (const float*)P.zs, scratch, smem_cap, ty, tz, n_nodes);
       PPP_CHECK_LAUNCH();
     }
