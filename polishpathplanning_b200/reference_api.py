@@ -1,0 +1,202 @@
+"""Python mirror of the reference's operator interface for the hot path (same names, argument
+meaning and error behaviour), backed by libppp_gpu.so.  The C++ mirror that a reference
+maintainer links is polishpathplanning_b200/host/ (Path_Generate_gpu.h, contour_alg_gpu.h).
+
+  path_generater  : include/Path_Generate.h:35-76  + src/Path_Generation.cpp   (gen-2, ./main)
+  SectPath        : include/contour_alg.h:50-91    + src/contour_alg.cpp       (config.txt flow)
+
+Only the hot-path members are mirrored (estimate_normal, Set_kdtree, rangedX_index, insert_point,
+slicing_method, path_track / OnePath, the GenPath plane sweep); visualisation, dynamic adjustment,
+way-point export and the GSL spline stay with the reference's own host code.
+Plane positions are generated here exactly as each reference loop does, in float32.
+"""
+import numpy as np
+
+from . import api, synth
+
+_f32 = np.float32
+
+
+# -------------------------------------------------------------------------------------------------
+# plane sweeps (host logic).  All arithmetic in float32 like the reference.
+# -------------------------------------------------------------------------------------------------
+def planes_gen2_contact(min_x, max_x, tool_radius):
+    """Contact_Path_Generation: float locateX = min.x + toolRadius (double add, then float);
+    locateX += int(2R) while locateX < max.x.  src/Path_Generation.cpp:711-723"""
+    step = int(tool_radius * 2)
+    out = []
+    loc = _f32(float(_f32(min_x)) + float(tool_radius))
+    while loc < _f32(max_x) and step > 0:
+        out.append(loc)
+        loc = _f32(loc + _f32(step))
+    return np.asarray(out, _f32)
+
+
+def planes_gen2_slicing(min_x, max_x, tool_radius):
+    """slicing_method: min.x += step/2 (INTEGER division), += step.  src/Path_Generation.cpp:295-303"""
+    step = int(tool_radius * 2)
+    out = []
+    m = _f32(_f32(min_x) + _f32(step // 2))
+    while m < _f32(max_x) and step > 0:
+        out.append(m)
+        m = _f32(m + _f32(step))
+    return np.asarray(out, _f32)
+
+
+def planes_gen1_slicing(min_x, max_x):
+    """free slicing_method: first plane min.x + 40, step 40.  src/slicing_method.cpp:617-626"""
+    out = []
+    m = _f32(_f32(min_x) + _f32(40))
+    while m < _f32(max_x):
+        out.append(m)
+        m = _f32(m + _f32(40))
+    return np.asarray(out, _f32)
+
+
+def planes_sectpath(min_x, max_x, tool_radius):
+    """SectPath::GenPath: backward from centre - step while > min.x (inserted at the front), then
+    forward from the centre while < max.x.  Returned in Path_set order.  src/contour_alg.cpp:305-327"""
+    step = int(tool_radius * 2)
+    centre = _f32(_f32(_f32(min_x) + _f32(max_x)) / _f32(2))
+    front, back = [], []
+    loc = _f32(centre - _f32(step))
+    while loc > _f32(min_x) and step > 0:
+        front.insert(0, loc)
+        loc = _f32(loc - _f32(step))
+    loc = centre
+    while loc < _f32(max_x) and step > 0:
+        back.append(loc)
+        loc = _f32(loc + _f32(step))
+    return np.asarray(front + back, _f32)
+
+
+class _Base:
+    NORMAL_RADIUS = 2.5   # normal_estimation.setRadiusSearch(2.5): src/Path_Generation.cpp:329
+    BAND_HALF_WIDTH = 2.0  # setFilterLimits(-2 + position, 2 + position): src/Path_Generation.cpp:100
+
+    def __init__(self, ctx=None, device=0):
+        self._ctx = ctx or api.Context(device)
+        self._gpu = None
+        self.cloud = None
+        self.Path_set = []
+
+    def _load(self, cloud_name, change_range=True):
+        if isinstance(cloud_name, str):
+            try:
+                cloud = synth.read_pcd(cloud_name)
+            except (OSError, ValueError) as e:
+                # the reference prints PCL_ERROR and carries on with an empty cloud
+                print("Cloudn't read file! (%s)" % e)
+                cloud = np.zeros((0, synth.POINT_STRIDE_FLOATS), np.float32)
+        else:
+            cloud = np.ascontiguousarray(cloud_name, np.float32).copy()
+        if change_range:
+            synth.reference_ctor_scale(cloud)
+        self.cloud = cloud
+        self._invalidate()
+
+    def _invalidate(self):
+        """xyz changed (voxel_down / trans2center / smooth / remove_outlier in the reference):
+        drop the device copy and its index."""
+        if self._gpu is not None:
+            self._gpu.close()
+        self._gpu = None
+
+    def _dev(self):
+        if self._gpu is None:
+            self._gpu = api.Cloud(self._ctx, self.cloud)
+        return self._gpu
+
+    # -- mirrored members ---------------------------------------------------------------------------
+    def Set_kdtree(self):
+        """kdtree.setInputCloud(cloud): builds the device index."""
+        self._dev().dev_index(16, 0.0)
+
+    def estimate_normal(self):
+        """NormalEstimation, radius 2.5, viewpoint (0,0,0) -> (N, 8) pcl::Normal records."""
+        self.cloud_with_normals = self._dev().normals_radius(self.NORMAL_RADIUS)
+        return self.cloud_with_normals
+
+    def rangedX_index(self, position):
+        """std::vector<int> rangedX_index(int position): the argument is truncated to int."""
+        position = int(position)
+        off, idx = self._dev().slice_bands(np.asarray([position], _f32), self.BAND_HALF_WIDTH, True)
+        return idx
+
+    def getMinMax3D(self):
+        return self._dev().bbox()
+
+    def _contours(self, planes, mode):
+        return self._dev().slice_contours(np.asarray(planes, _f32), mode, self.BAND_HALF_WIDTH, True)
+
+
+class path_generater(_Base):
+    """gen-2 planner (what ./main builds): brute-force pairing with greedy flags (variant A)."""
+
+    def __init__(self, cloud_name, Radius, ctx=None, device=0):
+        super().__init__(ctx, device)
+        self.toolRadius = float(Radius)
+        self._load(cloud_name, change_range=True)
+
+    def insert_point(self, indices, PlanePoint):
+        """std::map<double, std::vector<double>> insert_point(indices, PlanePoint): returns the map
+        as (y, x, z) arrays in ascending y.  `indices` must be rangedX_index(PlanePoint[0]), as at
+        every reference call site (src/Path_Generation.cpp:300-301,665)."""
+        plane = _f32(PlanePoint[0])
+        band = self.rangedX_index(plane)
+        if not np.array_equal(np.asarray(indices, np.int32), band):
+            raise ValueError("insert_point: indices differ from rangedX_index(PlanePoint[0])")
+        off, y, x, z = self._contours([plane], api.PPP_PAIR_GEN2)
+        return y, x, z
+
+    def path_track(self, plane_point):
+        y, x, z = self.insert_point(self.rangedX_index(plane_point[0]), plane_point)
+        self.Path_set.append((y, x, z))  # Spline(node_number, point_y, point_x, point_z)
+
+    def slicing_method(self):
+        """All planes of the sweep in one device pass; returns (planes, node_offsets, y, x, z)."""
+        mn, mx = self.getMinMax3D()
+        planes = planes_gen2_slicing(mn[0], mx[0], self.toolRadius)
+        off, y, x, z = self._contours(planes, api.PPP_PAIR_GEN2)
+        print("number of paths: %d" % len(planes))
+        return planes, off, y, x, z
+
+    def Contact_Path_Generation(self, adjust=False):
+        """Plane sweep + path_track of Contact_Path_Generation (dynamic adjustment is out of scope)."""
+        if adjust:
+            raise NotImplementedError("dynamic_adjust_path is sequential host logic outside the hot path")
+        mn, mx = self.getMinMax3D()
+        planes = planes_gen2_contact(mn[0], mx[0], self.toolRadius)
+        off, y, x, z = self._contours(planes, api.PPP_PAIR_GEN2)
+        self.Path_set = [(y[off[s]:off[s + 1]], x[off[s]:off[s + 1]], z[off[s]:off[s + 1]]) for s in range(len(planes))]
+        print("Number of paths: %d" % len(planes))
+        return planes
+
+
+class SectPath(_Base):
+    """SectPath (contour_alg.h): kd-tree pairing without flags (variant B), centre-out sweep."""
+
+    def __init__(self, cloud_name, Tool_Radius, ChangeRange=True, ctx=None, device=0):
+        super().__init__(ctx, device)
+        self.toolRadius = float(Tool_Radius)
+        self._load(cloud_name, change_range=ChangeRange)
+
+    def insert_point(self, indices, PlanePoint):
+        plane = _f32(PlanePoint[0])
+        band = self.rangedX_index(plane)
+        if not np.array_equal(np.asarray(indices, np.int32), band):
+            raise ValueError("insert_point: indices differ from rangedX_index(PlanePoint[0])")
+        off, y, x, z = self._contours([plane], api.PPP_PAIR_SECT)
+        return y, x, z
+
+    def OnePath(self, plane_point):
+        return self.insert_point(self.rangedX_index(plane_point[0]), plane_point)
+
+    def GenPath(self):
+        mn, mx = self.getMinMax3D()
+        planes = planes_sectpath(mn[0], mx[0], self.toolRadius)
+        off, y, x, z = self._contours(planes, api.PPP_PAIR_SECT)
+        self.Path_set = [(y[off[s]:off[s + 1]], x[off[s]:off[s + 1]], z[off[s]:off[s + 1]]) for s in range(len(planes))]
+        print("Number of paths: %d" % len(planes))
+        print("Number of Point Cloud: %d" % self.cloud.shape[0])
+        return planes

@@ -1,0 +1,119 @@
+"""CPU tests of the host-side logic: synthetic clouds, PCD I/O, plane sweeps, and the multi-GPU
+sharding (x-slabs + halo + gather) driven by the oracle on CPU, incl. a world_size-2 gloo run."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ppp_oracle as po
+from polishpathplanning_b200 import parallel, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_panel_deterministic_and_layout():
+    a = synth.panel(5000, 3)
+    b = synth.panel(5000, 3)
+    assert a.dtype == np.float32 and a.shape == (5000, 8) and np.array_equal(a, b)
+    assert not np.array_equal(a, synth.panel(5000, 4))
+    assert np.all(a[:, 3] == 1.0)
+    assert np.all(a[:, 4].view(np.uint32) & 0xFFFFFF == 0xFFFFFF)     # r = g = b = 255
+    m = synth.panel_metres(5000, 3)
+    assert np.array_equal(a[:, :3], m * np.float32(1000.0))              # the reference's *= 1000
+    L = np.sqrt(5000)
+    assert a[:, 0].min() >= 0 and a[:, 0].max() < L * 1.001
+
+
+@pytest.mark.parametrize("binary", [True, False])
+def test_pcd_roundtrip(tmp_path, binary):
+    c = synth.to_pointxyzrgb(synth.panel_metres(300, 2), rgb=0x00102030)
+    p = str(tmp_path / "w.pcd")
+    synth.write_pcd(p, c, binary=binary)
+    r = synth.read_pcd(p)
+    assert r.shape == c.shape
+    assert np.array_equal(r[:, :3], c[:, :3])
+    if binary:
+        assert np.array_equal(r[:, 4].view(np.uint32), c[:, 4].view(np.uint32))
+
+
+def _oracle_rank(cloud_g, planes_g, cuts, rank, halo, k, mode):
+    local_idx, owned = parallel.slab_select(cloud_g, cuts, rank, halo)
+    local = np.ascontiguousarray(cloud_g[local_idx])
+    oc = po.OracleCloud(local)
+    nrm, _ = oc.normals(k=k)
+    idx, d2 = oc.knn(k)
+    bad = parallel.halo_violations(local, owned, d2[:, -1], cuts, rank, halo)
+    pos = parallel.owned_planes(planes_g, cuts, rank)
+    off, y, x, z = oc.slice_contours(planes_g[pos], mode)
+    return local_idx[owned], nrm[owned], bad, (pos, off, y, x, z)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_sharding_equals_single(world):
+    cloud = synth.panel(30000, 9)
+    planes = synth.even_planes(cloud, 12)
+    k, halo = 16, 12.0
+    oc = po.OracleCloud(cloud)
+    ref_n, _ = oc.normals(k=k)
+    ref_c = oc.slice_contours(planes, "B")
+    cuts = parallel.slab_cuts(cloud[:, 0], world)
+    parts = [_oracle_rank(cloud, planes, cuts, r, halo, k, "B") for r in range(world)]
+    owned_total = sum(len(p[0]) for p in parts)
+    assert owned_total == cloud.shape[0]                               # every point owned exactly once
+    assert all(len(p[2]) == 0 for p in parts)                          # halo wide enough
+    full = parallel.assemble_normals(cloud.shape[0], 4, [(p[0], p[1]) for p in parts])
+    assert np.array_equal(full.view(np.uint32), ref_n.view(np.uint32))
+    goff, y, x, z = parallel.assemble_contours(len(planes), [p[3] for p in parts])
+    assert np.array_equal(goff, ref_c[0]) and np.array_equal(y, ref_c[1]) and np.array_equal(z, ref_c[3])
+
+
+def test_halo_violation_detected():
+    cloud = synth.panel(20000, 9)
+    cuts = parallel.slab_cuts(cloud[:, 0], 2)
+    local_idx, owned = parallel.slab_select(cloud, cuts, 0, 0.5)       # far too narrow
+    local = np.ascontiguousarray(cloud[local_idx])
+    _, d2 = po.OracleCloud(local).knn(16)
+    assert len(parallel.halo_violations(local, owned, d2[:, -1], cuts, 0, 0.5)) > 0
+
+
+def _gloo_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cloud = synth.panel(20000, 5)
+    planes = synth.even_planes(cloud, 8)
+    cuts = parallel.slab_cuts(cloud[:, 0], world)
+    gidx, nrm, bad, (pos, off, y, x, z) = _oracle_rank(cloud, planes, cuts, rank, 12.0, 16, "B")
+    assert len(bad) == 0
+    g1 = parallel.gather_to_rank0(dist, [gidx, nrm], rank, world)
+    counts = np.diff(off)
+    node_plane = np.repeat(pos, counts)
+    g2 = parallel.gather_to_rank0(dist, [node_plane, y, x, z], rank, world)
+    if rank == 0:
+        full = parallel.assemble_normals(cloud.shape[0], 4, [(g[0], g[1]) for g in g1])
+        per_rank = []
+        for g in g2:
+            pl, yy, xx, zz = g
+            ppos = np.unique(pl)
+            o = np.concatenate([[0], np.cumsum([(pl == s).sum() for s in ppos])]).astype(np.int64)
+            per_rank.append((ppos.astype(np.int64), o, yy, xx, zz))
+        goff, gy, gx, gz = parallel.assemble_contours(len(planes), per_rank)
+        np.savez(os.path.join(out_dir, "gathered.npz"), normals=full, off=goff, y=gy, z=gz)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gather(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(str(tmp_path / "gathered.npz"))
+    cloud = synth.panel(20000, 5)
+    planes = synth.even_planes(cloud, 8)
+    oc = po.OracleCloud(cloud)
+    ref_n, _ = oc.normals(k=16)
+    ref_c = oc.slice_contours(planes, "B")
+    assert np.array_equal(got["normals"].view(np.uint32), ref_n.view(np.uint32))
+    assert np.array_equal(got["off"], ref_c[0]) and np.array_equal(got["y"], ref_c[1]) and np.array_equal(got["z"], ref_c[3])
