@@ -4,6 +4,7 @@
 pipeline used by bench.py and the multi-GPU sharding.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -24,9 +25,12 @@ class Context:
         check(self.lib.ppp_create(int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
+        self._clouds = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "_h", None):
+            for c in list(self._clouds):  # cloud handles hold device memory of this context
+                c.close()
             self.lib.ppp_destroy(self._h)
             self._h = None
 
@@ -107,6 +111,7 @@ class Cloud:
             check(self.lib.ppp_cloud_upload(ctx._h, _ptr(pts), pts.shape[0], pts.shape[1] * 4, C.byref(h)))
             self.n = pts.shape[0]
         self._h = h
+        ctx._clouds.add(self)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -402,7 +402,8 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
         for (int i = s + lane; i < e; i += 32) {
           float4 c = __ldg(g.sorted + i);
           u64 key = make_key(d2_flann(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
-          if (key < tau) list_insert(L, 32, cnt, k, key);
+          // a full lane list only takes keys below its own last entry (list_insert overwrites it)
+          if (key < tau && (cnt < k || key < L[(k - 1) * 32])) list_insert(L, 32, cnt, k, key);
         }
       }
     }

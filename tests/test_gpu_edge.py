@@ -1,0 +1,284 @@
+"""GPU edge cases the domain has: empty / tiny clouds, k > N, duplicate points, non-finite points,
+points exactly on a plane, empty sides, external query points, strides, error codes; plus the
+committed golden fixtures and the Python mirror of the reference interface."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ppp_oracle as po
+from polishpathplanning_b200 import api, reference_api as ra, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _n4(g):
+    return np.concatenate([g[:, 0:3], g[:, 4:5]], axis=1)
+
+
+def _same_normals(g, o, tol=1e-5):
+    gn = _n4(g) if g.shape[1] == 8 else g
+    assert np.array_equal(np.isnan(gn[:, 0]), np.isnan(o[:, 0]))
+    ok = ~np.isnan(o[:, 0])
+    if ok.any():
+        assert np.abs(gn[ok] - o[ok]).max() <= tol
+
+
+def test_golden_independent_vectors(ctx):
+    """GPU against the cv2.flann / scipy goldens directly (no oracle in the loop)."""
+    g = np.load(os.path.join(GOLD, "independent.npz"))
+    for n, seed, ks in ((4000, 1, (8, 16, 32, 64)), (20000, 4, (16,))):
+        gc = api.Cloud(ctx, synth.panel(n, seed))
+        for k in ks:
+            idx, d2 = gc.knn(k)
+            assert np.array_equal(idx, g["knn_idx_n%d_s%d_k%d" % (n, seed, k)])
+            assert np.array_equal(d2.view(np.uint32), g["knn_d2_n%d_s%d_k%d" % (n, seed, k)].view(np.uint32))
+        gc.close()
+    gc = api.Cloud(ctx, synth.panel(4000, 1))
+    counts, off, idx, d2 = gc.radius(2.5)
+    boundary = set(g["radius_boundary_rows_n4000_s1"].tolist())
+    gcnt = g["radius_counts_n4000_s1"]
+    keep = np.array([i not in boundary for i in range(4000)])
+    assert np.array_equal(counts[keep], gcnt[keep])
+    gc.close()
+
+
+def test_golden_regression_vectors(ctx):
+    r = np.load(os.path.join(GOLD, "oracle_regression.npz"))
+    gc = api.Cloud(ctx, synth.panel(4000, 1))
+    _same_normals(gc.normals_radius(2.5), r["normals_r2p5_n4000_s1"])
+    _same_normals(gc.normals_knn(16), r["normals_k16_n4000_s1"])
+    mn, mx = gc.bbox()
+    assert np.array_equal(np.stack([mn, mx]), r["bbox_n4000_s1"])
+    planes = r["planes_gen2_contact_n4000_s1_R6"]
+    off, idx = gc.slice_bands(planes)
+    assert np.array_equal(off, r["bands_off_n4000_s1"]) and np.array_equal(idx, r["bands_idx_n4000_s1"])
+    for mode in "AB":
+        o, y, x, z = gc.slice_contours(planes, mode)
+        assert np.array_equal(o, r["contour_off_%s_n4000_s1" % mode])
+        assert np.array_equal(y, r["contour_y_%s_n4000_s1" % mode])
+        assert np.array_equal(x, r["contour_x_%s_n4000_s1" % mode])
+        assert np.array_equal(z, r["contour_z_%s_n4000_s1" % mode])
+    gc.close()
+
+
+def test_empty_and_tiny_clouds(ctx):
+    e = np.zeros((0, 8), np.float32)
+    gc = api.Cloud(ctx, e)
+    assert gc.knn(4)[0].shape == (0, 4)
+    assert gc.normals_radius(2.5).shape == (0, 8)
+    off, idx = gc.slice_bands(np.asarray([1.0, 2.0], np.float32))
+    assert off.tolist() == [0, 0, 0] and idx.size == 0
+    off, y, x, z = gc.slice_contours(np.asarray([1.0], np.float32), "B")
+    assert off.tolist() == [0, 0]
+    gc.close()
+    # N < k: k is clamped to N (pcl::KdTreeFLANN::nearestKSearch), rows padded with -1
+    c = synth.panel(5, 1)
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    gi, gd = gc.knn(16)
+    oi, od = oc.knn(16)
+    assert np.array_equal(gi, oi) and np.all(gi[:, 5:] == -1)
+    _same_normals(gc.normals_knn(16), oc.normals(k=16)[0])
+    # two points: fewer than 3 neighbours -> NaN normals
+    c2 = synth.panel(2, 1)
+    g2 = api.Cloud(ctx, c2)
+    assert np.all(np.isnan(_n4(g2.normals_radius(2.5))))
+    g2.close()
+    gc.close()
+
+
+def test_k_sweep_and_large_k(ctx):
+    c = synth.panel(30000, 12)
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    for k in (1, 2, 3, 5, 10, 33, 50, 100):   # 33+ takes the generic ring-expanding kernel
+        gi, gd = gc.knn(k)
+        oi, od = oc.knn(k)
+        assert np.array_equal(gi, oi), k
+        assert np.array_equal(gd.view(np.uint32), od.view(np.uint32)), k
+    gc.close()
+
+
+def test_duplicates_nonfinite_and_sparse(ctx):
+    rng = np.random.default_rng(5)
+    c = synth.panel(20000, 13)
+    c[100:140] = c[60:100]            # exact duplicates: ties on d2 = 0 broken by index
+    c[500, 0] = np.nan
+    c[501, 2] = np.inf
+    c[700:720, 0:3] += 4000.0         # a far-away clump (sparse region, many rings)
+    c[800, 0:3] = (-900.0, -900.0, 50.0)
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    for k in (8, 16):
+        gi, gd = gc.knn(k)
+        oi, od = oc.knn(k)
+        assert np.array_equal(gi, oi)
+        assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    assert np.all(gi[500] == -1) and np.all(gi[501] == -1)
+    gcnt, goff, gidx, gd2 = gc.radius(2.5)
+    ocnt, ooff, oidx, od2 = oc.radius(2.5)
+    assert np.array_equal(gcnt, ocnt) and np.array_equal(gidx, oidx)
+    _same_normals(gc.normals_radius(2.5), oc.normals(radius=2.5)[0])
+    _same_normals(gc.normals_knn(16), oc.normals(k=16)[0])
+    mn, mx = gc.bbox()
+    omn, omx = oc.minmax()
+    assert np.array_equal(mn, omn) and np.array_equal(mx, omx)
+    # slicing with duplicates (variant B canonicalises pairs through the global nearest index)
+    planes = np.asarray([30.2, 47.9, 60.0, 3990.0, -2000.0], np.float32)
+    goff, gidx = gc.slice_bands(planes)
+    ooff, oidx = oc.slice_bands(planes)
+    assert np.array_equal(goff, ooff) and np.array_equal(gidx, oidx)
+    for mode in "AB":
+        g = gc.slice_contours(planes, mode)
+        o = oc.slice_contours(planes, mode)
+        assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[3], o[3])
+    gc.close()
+
+
+def test_point_on_plane_and_empty_side(ctx):
+    c = synth.panel(20000, 14)
+    px = np.float32(55.25)
+    band = po.OracleCloud(c).band(float(px))
+    c[band[:5], 0] = px                       # exactly on the plane: neither left nor right
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    planes = np.asarray([px, c[:, 0].min() - 1.0, c[:, 0].max() + 1.5], np.float32)  # 2nd/3rd: one side empty
+    for mode in "AB":
+        g = gc.slice_contours(planes, mode)
+        o = oc.slice_contours(planes, mode)
+        assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[3], o[3])
+    gc.close()
+
+
+def test_external_queries_and_strides(ctx):
+    c = synth.panel(20000, 15)
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    rng = np.random.default_rng(1)
+    q = np.empty((500, 3), np.float32)
+    q[:, 0:2] = rng.random((500, 2)) * 170 - 15        # some outside the cloud's rectangle
+    q[:, 2] = rng.random(500) * 40 - 10
+    q[7] = (1e4, -1e4, 0)                                # far outside the grid
+    for k in (1, 3, 10):                                 # the reference's own k values
+        gi, gd = gc.knn(k, queries=q)
+        oi, od = oc.knn(k, queries=q)
+        assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    gcnt, goff, gidx, _ = gc.radius(7.5, queries=q)
+    ocnt, ooff, oidx, _ = oc.radius(7.5, queries=q)
+    assert np.array_equal(gcnt, ocnt) and np.array_equal(gidx, oidx)
+    # packed xyz (stride 12) and xyz+pad (stride 16) clouds give the same answers as stride 32
+    for cols in (3, 4):
+        g2 = api.Cloud(ctx, np.ascontiguousarray(c[:, :cols]))
+        assert np.array_equal(g2.knn(8)[0], gc.knn(8)[0])
+        g2.close()
+    # compact normal records (stride 16)
+    n16 = gc.normals_knn(16, stride_floats=4)
+    n32 = gc.normals_knn(16)
+    assert np.array_equal(n16.view(np.uint32), _n4(n32).view(np.uint32))
+    gc.close()
+
+
+def test_grid_axes_follow_extents(ctx):
+    """A cloud that is thin in y instead of z: the grid must pick (x, z)."""
+    c = synth.panel(20000, 16)
+    c2 = c.copy()
+    c2[:, 1], c2[:, 2] = c[:, 2].copy(), c[:, 1].copy()
+    gc = api.Cloud(ctx, c2)
+    oc = po.OracleCloud(c2)
+    assert np.array_equal(gc.knn(16)[0], oc.knn(16)[0])
+    planes = synth.even_planes(c2, 6)
+    g = gc.slice_contours(planes, "B")
+    o = oc.slice_contours(planes, "B")
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[3], o[3])
+    gc.close()
+
+
+def test_error_codes(ctx):
+    gc = api.Cloud(ctx, synth.panel(100, 1))
+    with pytest.raises(api.PPPError) as e:
+        gc.knn(0)
+    assert e.value.status == api._lib.PPP_ERR_INVALID
+    with pytest.raises(api.PPPError):
+        gc.normals_radius(-1.0)
+    with pytest.raises(api.PPPError) as e:
+        gc.knn(100000)
+    assert e.value.status == api._lib.PPP_ERR_UNSUPPORTED
+    with pytest.raises(ValueError):
+        api.Cloud(ctx, np.zeros((4, 2), np.float32))
+    gc.close()
+
+
+def test_reference_interface_mirror(ctx, tmp_path):
+    """./main-shaped flow: PCD in metres -> ctor scaling -> estimate_normal -> plane sweep."""
+    metres = synth.to_pointxyzrgb(synth.panel_metres(30000, 21))
+    pcd = str(tmp_path / "workpiece.pcd")
+    synth.write_pcd(pcd, metres)
+    pg = ra.path_generater(pcd, 15, ctx=ctx)
+    oc = po.OracleCloud(pg.cloud)
+    assert np.array_equal(pg.cloud, synth.panel(30000, 21))
+    _same_normals(pg.estimate_normal(), oc.normals(radius=2.5)[0])
+    band = pg.rangedX_index(40.9)
+    assert np.array_equal(band, oc.band(40.9))
+    y, x, z = pg.insert_point(band, (np.float32(40.9), 0, 0))
+    oy, ox, oz, _, _ = oc.insert_point(band, 40.9, "A")
+    assert np.array_equal(y, oy) and np.array_equal(z, oz)
+    planes = pg.Contact_Path_Generation()
+    mn, mx = oc.minmax()
+    assert np.array_equal(planes, po.planes("gen2_contact", mn[0], mx[0], 15))
+    ooff, oy, ox, oz = oc.slice_contours(planes, "A")
+    for s, (yy, xx, zz) in enumerate(pg.Path_set):
+        assert np.array_equal(yy, oy[ooff[s]:ooff[s + 1]]) and np.array_equal(zz, oz[ooff[s]:ooff[s + 1]])
+    sp = ra.SectPath(pcd, 12, ChangeRange=True, ctx=ctx)
+    planes = sp.GenPath()
+    assert np.array_equal(planes, po.planes("sectpath", mn[0], mx[0], 12))
+    ooff, oy, ox, oz = oc.slice_contours(planes, "B")
+    for s, (yy, xx, zz) in enumerate(sp.Path_set):
+        assert np.array_equal(yy, oy[ooff[s]:ooff[s + 1]]) and np.array_equal(zz, oz[ooff[s]:ooff[s + 1]])
+    # unreadable file: the reference prints an error and carries on with an empty cloud
+    bad = ra.path_generater(str(tmp_path / "missing.pcd"), 15, ctx=ctx)
+    assert bad.cloud.shape[0] == 0
+
+
+def test_full_size_properties(ctx):
+    """BASELINE cfg2 size (1M points, k=16, 200 slices): size-independent checks."""
+    c = synth.panel(1_000_000, 0)
+    gc = api.Cloud(ctx, c)
+    nrm, idx = gc.normals_knn(16, return_idx=True)
+    n4 = _n4(nrm)
+    assert np.all(idx[:, 0] == np.arange(c.shape[0]))                   # nearest neighbour of a point is itself
+    assert idx.min() >= 0 and idx.max() < c.shape[0]
+    assert np.all(np.abs(np.linalg.norm(n4[:, :3], axis=1) - 1) < 1e-5)  # unit normals
+    assert np.all((-(c[:, :3]) * n4[:, :3]).sum(1) >= -1e-2)              # flipped towards (0,0,0)
+    # rows sorted by (d2, idx): recompute d2 exactly as FLANN does
+    sub = np.arange(0, c.shape[0], 997)
+    d = c[sub][:, None, :3] - c[idx[sub]][:, :, :3]
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    di = idx[sub]
+    assert np.all((d2[:, 1:] > d2[:, :-1]) | ((d2[:, 1:] == d2[:, :-1]) & (di[:, 1:] > di[:, :-1])))
+    # oracle on a sample of queries (exact, external-query path)
+    oc = po.OracleCloud(c)
+    oi, _ = oc.knn(16, queries=c[sub][:, :3].copy())
+    assert np.array_equal(idx[sub], oi)
+    planes = synth.even_planes(c, 200)
+    off, bidx = gc.slice_bands(planes)
+    x = c[:, 0]
+    pos = planes.astype(np.int32)
+    for s in (0, 57, 199):
+        m = bidx[off[s]:off[s + 1]]
+        assert np.all(np.diff(m) > 0)
+        assert np.all((x[m] >= np.float32(pos[s] - 2)) & (x[m] <= np.float32(pos[s] + 2)))
+        assert len(m) == int(((x >= np.float32(pos[s] - 2)) & (x <= np.float32(pos[s] + 2))).sum())
+    noff, y, xx, z = gc.slice_contours(planes, "B")
+    for s in range(200):
+        ys = y[noff[s]:noff[s + 1]]
+        assert np.all(np.diff(ys) > 0) and np.all(xx[noff[s]:noff[s + 1]] == np.float64(planes[s]))
+    # idempotence: a second call gives identical bytes
+    noff2, y2, _, z2 = gc.slice_contours(planes, "B")
+    assert np.array_equal(noff, noff2) and np.array_equal(y, y2) and np.array_equal(z, z2)
+    # three slices against the oracle at full size
+    o = oc.slice_contours(planes[[3, 100, 198]], "B")
+    for j, s in enumerate((3, 100, 198)):
+        assert np.array_equal(y[noff[s]:noff[s + 1]], o[1][o[0][j]:o[0][j + 1]])
+    gc.close()
