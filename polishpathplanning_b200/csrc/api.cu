@@ -316,7 +316,7 @@ int ppp_dev_slice_contours(ppp_cloud* c, const float* plane_x_host, int S, float
 // host-pointer API
 // ---------------------------------------------------------------------------------------------
 int ppp_knn(ppp_cloud* c, const float* q, size_t nq, size_t q_stride_bytes, int k, int32_t* idx_out, float* d2_out) {
-  REQUIRE(c && idx_out, "NULL argument");
+  REQUIRE(c && (idx_out || (q ? nq == 0 : c->n == 0)), "NULL argument");
   REQUIRE(k >= 1, "k must be >= 1");
   REQUIRE(!q || (q_stride_bytes >= 12 && q_stride_bytes % 4 == 0), "query stride must be >= 12 and a multiple of 4");
   ppp_ctx* ctx = c->ctx;
@@ -421,16 +421,18 @@ static int normals_host(ppp_cloud* c, int k, double radius, const float vp[3], u
 
 int ppp_normals_knn(ppp_cloud* c, int k, const float vp[3], unsigned flags, void* normals_out, size_t stride,
                     int32_t* knn_idx_out) {
-  REQUIRE(c && normals_out, "NULL argument");
+  REQUIRE(c && (normals_out || c->n == 0), "NULL argument");
   REQUIRE(k >= 1, "k must be >= 1");
   REQUIRE(stride >= 16 && stride % 4 == 0, "normal stride must be >= 16 and a multiple of 4");
+  if (c->n == 0) return PPP_OK;
   return normals_host(c, k, 0.0, vp, flags, normals_out, stride, knn_idx_out);
 }
 
 int ppp_normals_radius(ppp_cloud* c, double radius, const float vp[3], unsigned flags, void* normals_out, size_t stride) {
-  REQUIRE(c && normals_out, "NULL argument");
+  REQUIRE(c && (normals_out || c->n == 0), "NULL argument");
   REQUIRE(radius > 0 && std::isfinite(radius), "radius must be > 0");
   REQUIRE(stride >= 16 && stride % 4 == 0, "normal stride must be >= 16 and a multiple of 4");
+  if (c->n == 0) return PPP_OK;  // the reference carries on with an empty cloud after a failed load
   return normals_host(c, 0, radius, vp, flags, normals_out, stride, nullptr);
 }
 
