@@ -222,7 +222,8 @@ def run_ours(args):
 
     with torch.cuda.stream(stream):
         raw_d = torch.from_numpy(cloud).to(dev)
-        normals_d = torch.empty((n_local, 8), dtype=torch.float32, device=dev)
+        nstride = 8 if world == 1 else 4       # pcl::Normal records; compact {nx,ny,nz,curv} when gathered over NCCL
+        normals_d = torch.empty((n_local, nstride), dtype=torch.float32, device=dev)
         idx_d = torch.empty((n_local, K_NEIGH), dtype=torch.int32, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         flush_rd = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
@@ -230,25 +231,58 @@ def run_ours(args):
     stream.synchronize()
 
     last = {}
+    gat = {}
+    if world > 1:
+        # static gather buffers: equal-sized NCCL gathers, no per-step size exchange
+        # The whole local normal array (owned + halo rows) is gathered: rank 0 keeps the owned rows
+        # through the static local->global index map, so no per-step row selection kernel is needed
+        # (torch.index_select on 1M x 4 floats measured 0.5 ms, ten times the NCCL transfer).
+        t = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gat["own_cap"] = int(t.item())
+        with torch.cuda.stream(stream):
+            gat["own"] = torch.zeros((gat["own_cap"], 4), dtype=torch.float32, device=dev)
+            normals_d = gat["own"][:n_local]
+            # all-gather (NCCL ring / NVLS collective over NVSwitch) instead of a rooted gather: the
+            # rooted gather is a set of point-to-point send/recv pairs and measured ~8x slower here
+            gat["own_recv"] = torch.empty((world * gat["own_cap"], 4), dtype=torch.float32, device=dev)
 
-    def dev_step():
+    def ensure_node_buffers(tn):
+        if "nodes" in gat and gat["node_cap"] >= tn:
+            return
+        t = torch.tensor([int(tn * 1.25) + 1024], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gat["node_cap"] = int(t.item())
+        with torch.cuda.stream(stream):
+            gat["nodes"] = torch.zeros((3, gat["node_cap"] + 1), dtype=torch.float64, device=dev)  # [:,0] = node count
+            gat["nodes_recv"] = torch.empty((world * 3, gat["node_cap"] + 1), dtype=torch.float64, device=dev)
+
+    do_gather = not os.environ.get("PPP_BENCH_NOGATHER")
+
+    def dev_step(gather=True):
+        gather = gather and do_gather
         c = api.Cloud(ctx, device_ptr=raw_d.data_ptr(), n=n_local, stride_bytes=32)
-        c.dev_normals_knn(K_NEIGH, normals_d.data_ptr(), 32, idx_ptr=idx_d.data_ptr())
+        c.dev_normals_knn(K_NEIGH, normals_d.data_ptr(), nstride * 4, idx_ptr=idx_d.data_ptr())
+        if world > 1 and gather:
+            # results to rank 0 (the reference's Spline / path connection run on the host of rank 0):
+            # owned normals in original index order; issued before the slicing so the NVLink
+            # transfer (NCCL's own stream) overlaps the band / contour kernels
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gat["own_recv"], gat["own"])
         res = c.dev_slice_contours(planes, PAIRING, HALF_WIDTH, True)
         last["nodes"] = res["total_nodes"]
         last["members"] = res["total_members"]
-        if world > 1:
-            # results to rank 0: owned normals (compact nx,ny,nz,curv) + contour nodes (y,x,z)
+        if world > 1 and gather:
+            # contour nodes (y, x, z) of the owned planes
+            tn = res["total_nodes"]
+            ensure_node_buffers(tn)
             with torch.cuda.stream(stream):
-                own = normals_d.index_select(0, owned_d)[:, [0, 1, 2, 4]].contiguous()
-                tn = res["total_nodes"]
-                nodes = torch.empty((3, max(tn, 1)), dtype=torch.float64, device=dev)
+                nb = gat["nodes"]
+                nb[:, 0] = float(tn)
                 if tn:
                     for j, key in enumerate(("y", "x", "z")):
-                        src = _wrap_f64(torch, res[key], tn, dev)
-                        nodes[j, :tn] = src
-                parallel.gather_to_rank0(dist, [own], rank, world, device=dev)
-                parallel.gather_to_rank0(dist, [nodes.t().contiguous()[:tn]], rank, world, device=dev)
+                        nb[j, 1:tn + 1] = _wrap_f64(torch, res[key], tn, dev)
+                dist.all_gather_into_tensor(gat["nodes_recv"], nb)
         c.close()
 
     def sync_all():
