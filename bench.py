@@ -347,12 +347,18 @@ def run_ours(args):
     pin_cloud = ctx.pinned_empty(cloud.shape, np.float32)
     pin_cloud[...] = cloud
     pin_normals = ctx.pinned_empty((n_local, 8), np.float32)
+    node_cap = int(max(last.get("nodes", 0), 1024) * 1.25)
+    pin_nodes = tuple(ctx.pinned_empty((node_cap,), np.float64) for _ in range(3))
     e2e_bytes = {}
 
     def host_step():
+        # the reference's call sequence: constructor/Set_kdtree (upload + index), getMinMax3D + plane
+        # positions on the host, then estimate_normal + the sweep (one combined C-ABI call)
         c = api.Cloud(ctx, pin_cloud)
-        c.normals_knn(K_NEIGH, out=pin_normals)
-        off, y, x, z = c.slice_contours(planes, PAIRING, HALF_WIDTH, True, node_cap=max(last.get("nodes", 0), 1024))
+        mn, mx = c.bbox()
+        pl = planes if world > 1 else make_planes(mn[0], mx[0], S_total)
+        _, off, y, x, z = c.normals_and_contours(pl, PAIRING, k=K_NEIGH, half_width=HALF_WIDTH, truncate_center=True,
+                                                 normals_out=pin_normals, nodes_out=pin_nodes)
         e2e_bytes["h2d"] = pin_cloud.nbytes + planes.nbytes * 5 + 4 * len(planes)
         e2e_bytes["d2h"] = pin_normals.nbytes + off.nbytes + 3 * y.nbytes
         c.close()

@@ -128,6 +128,16 @@ int ppp_slice_contours(ppp_cloud* cloud, const float* plane_x, int S, float half
                        int pairing_mode, int64_t* node_offsets, double* y, double* x, double* z,
                        int64_t node_cap);
 
+/* estimate_normal() followed by the plane sweep, as one call: what SectPath-derived GenPath does
+ * (src/Path_Alg/path_dynamic_alg.cpp:343-366: estimate_normal(); kdtree.setInputCloud; sweep).
+ * Exactly the results of ppp_normals_knn (k >= 1, radius = 0) or ppp_normals_radius (k = 0,
+ * radius > 0) followed by ppp_slice_contours, but the device->host copy of the normals overlaps
+ * the slicing kernels.                                                                          */
+int ppp_normals_and_contours(ppp_cloud* cloud, int k, double radius, const float viewpoint[3], unsigned flags,
+                             void* normals_out, size_t normal_stride_bytes, const float* plane_x, int S,
+                             float half_width, int truncate_center, int pairing_mode, int64_t* node_offsets,
+                             double* y, double* x, double* z, int64_t node_cap);
+
 /* ------------------------------------------------------------------------------------------ */
 /* device API (results stay in HBM; used by bench.py's device-resident leg and the multi-GPU
  * sharding in polishpathplanning_b200/parallel.py).  Query sub-ranges are given in SORTED

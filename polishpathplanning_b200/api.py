@@ -188,8 +188,9 @@ class Cloud:
                                        idx.shape[0]))
         return off, idx
 
-    def slice_contours(self, planes, mode, half_width=2.0, truncate_center=True, node_cap=None):
-        """mode: PPP_PAIR_GEN2 ('A') or PPP_PAIR_SECT ('B'). Returns (node_offsets, y, x, z)."""
+    def slice_contours(self, planes, mode, half_width=2.0, truncate_center=True, node_cap=None, out=None):
+        """mode: PPP_PAIR_GEN2 ('A') or PPP_PAIR_SECT ('B'). Returns (node_offsets, y, x, z).
+        out: optional (y, x, z) float64 buffers (e.g. pinned) to write into."""
         if isinstance(mode, str):
             mode = PPP_PAIR_GEN2 if mode.upper() == "A" else PPP_PAIR_SECT
         planes = np.ascontiguousarray(planes, np.float32)
@@ -197,17 +198,48 @@ class Cloud:
         off = np.zeros(S + 1, np.int64)
         cap = int(node_cap) if node_cap else max(self.n // 4, 1024)
         while True:
-            y = np.empty(cap, np.float64)
-            x = np.empty(cap, np.float64)
-            z = np.empty(cap, np.float64)
+            if out is not None and out[0].shape[0] >= cap:
+                y, x, z = out
+                cap = y.shape[0]
+            else:
+                y = np.empty(cap, np.float64)
+                x = np.empty(cap, np.float64)
+                z = np.empty(cap, np.float64)
             st = self.lib.ppp_slice_contours(self._h, _ptr(planes), S, half_width, int(truncate_center), mode, _ptr(off),
                                              _ptr(y), _ptr(x), _ptr(z), cap)
             if st == _lib.PPP_ERR_CAPACITY:
                 cap = int(off[-1])
+                out = None
                 continue
             check(st)
             t = int(off[-1])
             return off, y[:t], x[:t], z[:t]
+
+    def normals_and_contours(self, planes, mode, k=0, radius=0.0, viewpoint=(0.0, 0.0, 0.0), flags=PPP_COV_PCL110,
+                             half_width=2.0, truncate_center=True, normals_out=None, nodes_out=None, stride_floats=8):
+        """estimate_normal + plane sweep in one call (normals D2H overlaps the slicing kernels).
+        Returns (normals, node_offsets, y, x, z)."""
+        if isinstance(mode, str):
+            mode = PPP_PAIR_GEN2 if mode.upper() == "A" else PPP_PAIR_SECT
+        planes = np.ascontiguousarray(planes, np.float32)
+        S = planes.shape[0]
+        vp = np.asarray(viewpoint, np.float32)
+        nrm = normals_out if normals_out is not None else np.empty((self.n, stride_floats), np.float32)
+        off = np.zeros(S + 1, np.int64)
+        if nodes_out is not None:
+            y, x, z = nodes_out
+        else:
+            cap = max(self.n // 4, 1024)
+            y, x, z = (np.empty(cap, np.float64) for _ in range(3))
+        st = self.lib.ppp_normals_and_contours(self._h, int(k), float(radius), vp.ctypes.data_as(_lib._f32p), flags,
+                                               _ptr(nrm), nrm.shape[1] * 4, _ptr(planes), S, half_width,
+                                               int(truncate_center), mode, _ptr(off), _ptr(y), _ptr(x), _ptr(z), y.shape[0])
+        if st == _lib.PPP_ERR_CAPACITY:   # normals are valid; fetch the contours again with enough room
+            off, y, x, z = self.slice_contours(planes, mode, half_width, truncate_center, node_cap=int(off[-1]))
+            return nrm, off, y, x, z
+        check(st)
+        t = int(off[-1])
+        return nrm, off, y[:t], x[:t], z[:t]
 
     # ---- device-resident pipeline ---------------------------------------------------------------
     def dev_index(self, k_hint=16, radius_hint=0.0):

@@ -59,6 +59,7 @@ int ppp_create(int device, ppp_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   PPP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  PPP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   cudaMemPool_t pool;
   PPP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t thr = UINT64_MAX;  // keep freed blocks cached: temporaries are re-used every call
@@ -76,6 +77,7 @@ void ppp_destroy(ppp_ctx* ctx) {
   for (int t = 0; t < 16; t++)
     for (auto& p : ctx->t_pending[t]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 
@@ -480,6 +482,45 @@ int ppp_slice_contours(ppp_cloud* c, const float* plane_x, int S, float half_wid
   }
   PPP_CUDA(cudaStreamSynchronize(ctx->stream));
   return st;
+}
+
+// estimate_normal() + the whole plane sweep in one call (the gen-3 GenPath does exactly this
+// sequence: src/Path_Alg/path_dynamic_alg.cpp:343 then the sweep).  Same results as
+// ppp_normals_knn / ppp_normals_radius followed by ppp_slice_contours; the device->host copy of
+// the normals runs on a second stream while the band / pairing / ordering kernels execute.
+int ppp_normals_and_contours(ppp_cloud* c, int k, double radius, const float vp[3], unsigned flags, void* normals_out,
+                             size_t stride, const float* plane_x, int S, float half_width, int truncate_center,
+                             int pairing_mode, int64_t* node_offsets, double* y, double* x, double* z, int64_t node_cap) {
+  REQUIRE(c && node_offsets && (normals_out || c->n == 0), "NULL argument");
+  REQUIRE((k >= 1) != (radius > 0), "give either k >= 1 or radius > 0");
+  REQUIRE(stride >= 16 && stride % 4 == 0, "normal stride must be >= 16 and a multiple of 4");
+  REQUIRE(!y || (x && z), "y, x, z must be given together");
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  float* n_d = nullptr;
+  size_t nbytes = (size_t)c->n * stride;
+  cudaEvent_t ev = nullptr;
+  int st = PPP_OK;
+  if (c->n > 0) {
+    PPP_TRY(dev_alloc(ctx, (char**)&n_d, std::max<size_t>(nbytes, 16)));
+    if (stride > 32) PPP_CUDA(cudaMemsetAsync(n_d, 0, nbytes, ctx->stream));
+    st = k >= 1 ? ppp_dev_normals_knn(c, k, vp, flags, 0, -1, n_d, stride, nullptr, nullptr)
+                : ppp_dev_normals_radius(c, radius, vp, flags, 0, -1, n_d, stride);
+    if (st == PPP_OK) {
+      PPP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      PPP_CUDA(cudaEventRecord(ev, ctx->stream));
+      PPP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+      PPP_CUDA(cudaMemcpyAsync(normals_out, n_d, nbytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+  }
+  if (st == PPP_OK) st = ppp_slice_contours(c, plane_x, S, half_width, truncate_center, pairing_mode, node_offsets, y, x, z, node_cap);
+  cudaError_t e = cudaStreamSynchronize(ctx->copy_stream);
+  if (ev) cudaEventDestroy(ev);
+  dev_free(ctx, (char*)n_d);
+  if (st != PPP_OK) return st;
+  PPP_CUDA(e);
+  return PPP_OK;
 }
 
 }  // extern "C"

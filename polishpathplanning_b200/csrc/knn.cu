@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
 // ring-expanding kernel through redo_list; everything it does finish is exact.
 // ---------------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(128, (K <= 16 ? 5 : 2)) k_knn_fast(SearchParams P) {
+__global__ void __launch_bounds__(128, (K <= 16 ? 6 : 2)) k_knn_fast(SearchParams P) {
   extern __shared__ u64 s_keys[];
   constexpr int BD = 128;  // launch block size (immediate shared-memory offsets)
   const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;

@@ -45,6 +45,7 @@ struct ppp_ctx {
   int sm_count = 148;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap later kernels
   std::recursive_mutex mu;
   int64_t launches = 0;
   bool profile = false;

@@ -282,3 +282,21 @@ def test_full_size_properties(ctx):
     for j, s in enumerate((3, 100, 198)):
         assert np.array_equal(y[noff[s]:noff[s + 1]], o[1][o[0][j]:o[0][j + 1]])
     gc.close()
+
+
+def test_combined_call_equals_separate_calls(ctx):
+    c = synth.panel(50000, 31)
+    gc = api.Cloud(ctx, c)
+    planes = synth.even_planes(c, 25)
+    for kw in (dict(k=16), dict(radius=2.5)):
+        nrm, off, y, x, z = gc.normals_and_contours(planes, "B", **kw)
+        ref_n = gc.normals_knn(16) if "k" in kw else gc.normals_radius(2.5)
+        ro, ry, rx, rz = gc.slice_contours(planes, "B")
+        assert np.array_equal(nrm.view(np.uint32), ref_n.view(np.uint32))
+        assert np.array_equal(off, ro) and np.array_equal(y, ry) and np.array_equal(x, rx) and np.array_equal(z, rz)
+    # too small node buffers: normals still delivered, contours re-fetched
+    small = tuple(np.empty(8, np.float64) for _ in range(3))
+    nrm, off, y, x, z = gc.normals_and_contours(planes, "A", k=16, nodes_out=small)
+    ro, ry, rx, rz = gc.slice_contours(planes, "A")
+    assert np.array_equal(off, ro) and np.array_equal(y, ry) and np.array_equal(z, rz)
+    gc.close()
