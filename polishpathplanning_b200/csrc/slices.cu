@@ -427,22 +427,53 @@ struct PairParams {
   float* zs;
 };
 
-__global__ void __launch_bounds__(128) k_pair_nodes(PairParams P) {
-  int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= P.M) return;
-  // slice of member m: last s with band_off[s] <= m
-  int l = 0, r = P.S;
-  while (l < r) { int mid = (l + r) >> 1; if (__ldg(P.band_off + mid + 1) <= m) l = mid + 1; else r = mid; }
-  const int s = l;
-  const float plane = __ldg(P.planes + s), lo = __ldg(P.lo + s), hi = __ldg(P.hi + s);
-  const int idx = __ldg(P.band_idx + m);
-  float4 pl = __ldg(P.xyz4 + idx);
-  u64 key = PPP_KEY_INF;
-  float y = 0.f, z = 0.f;
-  if (__fsub_rn(pl.x, plane) > 0.0f) {
-    const int32_t* band = P.band_idx + __ldg(P.band_off + s);
-    const int B = (int)(__ldg(P.band_off + s + 1) - __ldg(P.band_off + s));
-    const bool dups = P.dup_flag ? (*P.dup_flag != 0) : true;
+// Each warp takes PAIR_CHUNK consecutive members, keeps the left ones (about half) in a small
+// shared-memory list and then works on that list with all lanes busy: a thread-per-member
+// mapping leaves the lanes of right members idle during the long nearest-neighbour searches.
+constexpr int PAIR_CHUNK = 56;   // ~28 left members per chunk: usually one full round of 32 lanes
+constexpr int PAIR_WARPS = 4;
+
+__global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
+  __shared__ int64_t s_m[PAIR_WARPS][64];
+  __shared__ int s_s[PAIR_WARPS][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t base = ((int64_t)blockIdx.x * PAIR_WARPS + w) * PAIR_CHUNK;
+  if (base >= P.M) return;
+  const bool dups = P.dup_flag ? (*P.dup_flag != 0) : true;
+  int cnt = 0;
+  for (int half = 0; half < 2; half++) {
+    const int off = half * 32 + lane;
+    const int64_t m = base + off;
+    bool isL = false;
+    int s = 0;
+    if (off < PAIR_CHUNK && m < P.M) {
+      // slice of member m: last s with band_off[s] <= m
+      int l = 0, r = P.S;
+      while (l < r) { int mid = (l + r) >> 1; if (__ldg(P.band_off + mid + 1) <= m) l = mid + 1; else r = mid; }
+      s = l;
+      const float x = __ldg(&P.xyz4[__ldg(P.band_idx + m)].x);
+      isL = __fsub_rn(x, __ldg(P.planes + s)) > 0.0f;
+      if (!isL) { P.keys[m] = PPP_KEY_INF; P.ys[m] = 0.f; P.zs[m] = 0.f; }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, isL);
+    if (isL) {
+      const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+      s_m[w][pos] = m;
+      s_s[w][pos] = s;
+    }
+    cnt += __popc(bal);
+  }
+  __syncwarp();
+  for (int i = lane; i < cnt; i += 32) {
+    const int64_t m = s_m[w][i];
+    const int s = s_s[w][i];
+    const float plane = __ldg(P.planes + s), lo = __ldg(P.lo + s), hi = __ldg(P.hi + s);
+    const int64_t bo = __ldg(P.band_off + s);
+    const int32_t* band = P.band_idx + bo;
+    const int B = (int)(__ldg(P.band_off + s + 1) - bo);
+    const float4 pl = __ldg(P.xyz4 + __ldg(P.band_idx + m));
+    u64 key = PPP_KEY_INF;
+    float y = 0.f, z = 0.f;
     int ri = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, band, B);
     if (ri >= 0) {
       float4 pr = __ldg(P.xyz4 + ri);
@@ -457,12 +488,12 @@ __global__ void __launch_bounds__(128) k_pair_nodes(PairParams P) {
       z = __fadd_rn(a.z, __fmul_rn(t, __fsub_rn(b.z, a.z)));
       // low word = slot inside the band (the payload address); equal-y ties are resolved by
       // original index in k_slice_order
-      key = ((u64)f2ord_dev(__fadd_rn(y, 0.0f)) << 32) | (u64)(uint32_t)(m - __ldg(P.band_off + s));
+      key = ((u64)f2ord_dev(__fadd_rn(y, 0.0f)) << 32) | (u64)(uint32_t)(m - bo);
     }
+    P.keys[m] = key;
+    P.ys[m] = y;
+    P.zs[m] = z;
   }
-  P.keys[m] = key;
-  P.ys[m] = y;
-  P.zs[m] = z;
 }
 
 // CTA per slice: sort the slice's node keys (INF = not a node) by (y, slot), then keep one node
@@ -685,7 +716,8 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     P.dup_flag = c->dup_known ? c->dup_flag : nullptr;
     PPP_TRY(dev_alloc(ctx, &P.keys, M)); PPP_TRY(dev_alloc(ctx, &P.ys, M)); PPP_TRY(dev_alloc(ctx, &P.zs, M));
     if (band_total > 0) {
-      PPP_LAUNCH(ctx, "pair_nodes", k_pair_nodes, (unsigned)((band_total + 127) / 128), 128, 0, P);
+      const int64_t per_block = (int64_t)PAIR_WARPS * PAIR_CHUNK;
+      PPP_LAUNCH(ctx, "pair_nodes", k_pair_nodes, (unsigned)((band_total + per_block - 1) / per_block), PAIR_WARPS * 32, 0, P);
       PPP_CHECK_LAUNCH();
     }
     int64_t maxB = 0;
