@@ -171,8 +171,11 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
 // of the neighbourhood), so a query that does not collect k candidates is handed to the generic
 // ring-expanding kernel through redo_list; everything it does finish is exact.
 // ---------------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(128, (K <= 16 ? 6 : 2)) k_knn_fast(SearchParams P) {
+// K = list length kept in registers (8, 16, 32, 64), PB = pending batch merged per flush.
+// RADIUS = true: fixed-radius mode (NormalEstimation::setRadiusSearch): every candidate with
+// d2 < r2 is wanted; a query with more than K of them is handed over to the generic kernel.
+template <int K, int PB, bool RADIUS>
+__global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_fast(SearchParams P) {
   extern __shared__ u64 s_keys[];
   constexpr int BD = 128;  // launch block size (immediate shared-memory offsets)
   const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : 2)) k_knn_fast(SearchParam
 #pragma unroll
   for (int i = 0; i < K; i++) best[i] = PPP_KEY_INF;
   int pc = 0;
+  int nacc = 0;  // RADIUS: number of in-radius candidates seen (overflow detection)
   bool dup_seen = false;
   const int R = P.R0;
   int cu = 0, cv = 0;
@@ -206,22 +210,28 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : 2)) k_knn_fast(SearchParam
   if (act) {
     cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
     cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
-    tau = make_key(ring_bound2(g, R, cu, cv), 0);
+    tau = RADIUS ? make_key(P.r2, 0) : make_key(ring_bound2(g, R, cu, cv), 0);
   }
 
-  // Merge the pending buffers into `best` (INF-padded load, sort network, bitonic merge).  One
-  // straight-line copy of the networks only: duplicated copies thrash the instruction cache.
+  // Merge the pending batch into `best`: INF-padded load, sort network on PB keys, half-cleaner
+  // against the top PB entries of `best`, bitonic merge of all K.  One straight-line copy of the
+  // networks only: duplicated copies thrash the instruction cache.
   auto flush = [&]() {
-    u64 pend[K];
+    u64 pend[PB];
 #pragma unroll
-    for (int i = 0; i < K; i++) {
+    for (int i = 0; i < PB; i++) {
       u64 v = pend_s[i * BD];  // unconditional load (stale slots are ignored), then pad
       pend[i] = i < pc ? v : PPP_KEY_INF;
     }
-    SortNet<K>::sort(pend);
-    SortNet<K>::merge_keep_smallest(best, pend);
+    SortNet<PB>::sort(pend);
+#pragma unroll
+    for (int i = 0; i < PB; i++) {
+      u64 o = pend[PB - 1 - i];
+      best[K - PB + i] = o < best[K - PB + i] ? o : best[K - PB + i];
+    }
+    SortNet<K>::bitonic_merge(best);
     pc = 0;
-    if (best[K - 1] < tau) tau = best[K - 1];
+    if (!RADIUS && best[K - 1] < tau) tau = best[K - 1];
   };
 
   // rows dv = -R..R, plus one pseudo-row (dv = R+1) whose single empty iteration drains the
@@ -249,7 +259,7 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : 2)) k_knn_fast(SearchParam
     // drain row: one empty iteration with trigger level 0.  Written arithmetically (no select on
     // `drain`) so the compiler does not clone the loop body, and with it the flush networks.
     const int n_it = (__reduce_max_sync(0xffffffffu, e - s) + U - 1) / U + (j - 2 * R > 0 ? 1 : 0);
-    const int trig = min(K - U, (2 * R + 1 - j) * K);  // flush when some lane could overflow next iteration
+    const int trig = min(PB - U, (2 * R + 1 - j) * PB);  // flush when some lane could overflow next iteration
 #pragma unroll 1
     for (int it = 0; it < n_it; it++) {
       float4 c[U];
@@ -270,7 +280,9 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : 2)) k_knn_fast(SearchParam
           wptr += BD;
         }
       }
-      pc = (int)(wptr - pend_s) / BD;
+      const int pc_new = (int)(wptr - pend_s) / BD;
+      nacc += pc_new - pc;
+      pc = pc_new;
       if (__any_sync(0xffffffffu, pc > trig)) { flush(); wptr = pend_s; }
     }
   }
@@ -279,16 +291,24 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : 2)) k_knn_fast(SearchParam
   if (dup_seen && P.dup_flag) *P.dup_flag = 1;
   if (!valid) return;
 
-  // complete iff kk candidates were found inside the bound (then the kk-th is < bound by construction)
-  const int kk = P.kk;
-  bool complete = !act || kk == 0;
-  if (!complete) {
-    u64 kth = PPP_KEY_INF;
+  bool complete;
+  int m;  // neighbours found
+  if (RADIUS) {
+    complete = nacc <= K;
+    m = nacc;
+  } else {
+    // complete iff kk candidates were found inside the bound (then the kk-th is < bound by construction)
+    const int kk = P.kk;
+    complete = !act || kk == 0;
+    if (!complete) {
+      u64 kth = PPP_KEY_INF;
 #pragma unroll
-    for (int i = 0; i < K; i++) if (i == kk - 1) kth = best[i];
-    complete = kth != PPP_KEY_INF;
-    // the whole grid inside the block: nothing else exists, whatever was found is final.  (The
-    // bound prefilter may have rejected far candidates, so this only helps when kk exceeds the cloud.)
+      for (int i = 0; i < K; i++) if (i == kk - 1) kth = best[i];
+      complete = kth != PPP_KEY_INF;
+    }
+    m = 0;
+#pragma unroll
+    for (int j = 0; j < K; j++) m += (j < P.cap && best[j] != PPP_KEY_INF) ? 1 : 0;
   }
   if (!complete) {
     int slot = atomicAdd(P.redo_count, 1);
@@ -296,47 +316,99 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : 2)) k_knn_fast(SearchParam
     return;
   }
   const int k = P.cap;
-  if (P.idx_out) {
-    int32_t* io = P.idx_out + row * (int64_t)k;
-    float* dout = P.d2_out ? P.d2_out + row * (int64_t)k : nullptr;
-#pragma unroll
-    for (int j = 0; j < K; j++) {
-      if (j < k) {
-        bool has = best[j] != PPP_KEY_INF;
-        io[j] = has ? key_idx(best[j]) : -1;
-        if (dout) dout[j] = has ? key_d2(best[j]) : CUDART_INF_F;
-      }
-    }
-  }
-  if (P.normals) {
-    float o[4];
-    int m = 0;
-#pragma unroll
-    for (int j = 0; j < K; j++) m += (j < k && best[j] != PPP_KEY_INF) ? 1 : 0;
-    if (!fin || m < 3) {
-      o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
-    } else {
-      float4 nb[K];
-#pragma unroll
-      for (int j = 0; j < K; j++)
-        if (j < m) nb[j] = __ldg(P.xyz4 + key_idx(best[j]));
-      float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
-      float kx = shifted ? nb[0].x : 0.f, ky = shifted ? nb[0].y : 0.f, kz = shifted ? nb[0].z : 0.f;
+  float o[4];
+  if (K <= 16 && !RADIUS) {
+    // short lists: everything from registers, all gathers in flight at once
+    if (P.idx_out) {
+      int32_t* io = P.idx_out + row * (int64_t)k;
+      float* dout = P.d2_out ? P.d2_out + row * (int64_t)k : nullptr;
 #pragma unroll
       for (int j = 0; j < K; j++) {
-        if (j < m) {
-          float x = nb[j].x, y = nb[j].y, z = nb[j].z;
-          if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
-          accumulate_point(acc, x, y, z);
+        if (j < k) {
+          bool has = best[j] != PPP_KEY_INF;
+          io[j] = has ? key_idx(best[j]) : -1;
+          if (dout) dout[j] = has ? key_d2(best[j]) : CUDART_INF_F;
         }
       }
-      normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
     }
-    store_normal(P.normals, row, P.nsf, o);
+    if (P.normals) {
+      if (!fin || m < 3) {
+        o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
+      } else {
+        float4 nb[K];
+#pragma unroll
+        for (int j = 0; j < K; j++)
+          if (j < m) nb[j] = __ldg(P.xyz4 + key_idx(best[j]));
+        float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
+        float kx = shifted ? nb[0].x : 0.f, ky = shifted ? nb[0].y : 0.f, kz = shifted ? nb[0].z : 0.f;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          if (j < m) {
+            float x = nb[j].x, y = nb[j].y, z = nb[j].z;
+            if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
+            accumulate_point(acc, x, y, z);
+          }
+        }
+        normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
+      }
+      store_normal(P.normals, row, P.nsf, o);
+    }
+  } else {
+    // long lists: park the sorted keys in this thread's shared-memory column (K slots) and walk
+    // them with rolled loops, which bounds registers and code size
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < K; j++) pend_s[j * BD] = best[j];
+    if (P.idx_out && !RADIUS) {
+      int32_t* io = P.idx_out + row * (int64_t)k;
+      float* dout = P.d2_out ? P.d2_out + row * (int64_t)k : nullptr;
+      for (int j = 0; j < k; j++) {
+        u64 key = pend_s[j * BD];
+        bool has = key != PPP_KEY_INF;
+        io[j] = has ? key_idx(key) : -1;
+        if (dout) dout[j] = has ? key_d2(key) : CUDART_INF_F;
+      }
+    }
+    if (P.normals) {
+      if (!fin || m < 3) {
+        o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
+      } else {
+        float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
+        float kx = 0.f, ky = 0.f, kz = 0.f;
+        if (shifted) {
+          float4 f = __ldg(P.xyz4 + key_idx(pend_s[0]));
+          kx = f.x; ky = f.y; kz = f.z;
+        }
+        int j = 0;
+        for (; j + 4 <= m; j += 4) {
+          float4 a0 = __ldg(P.xyz4 + key_idx(pend_s[(j + 0) * BD]));
+          float4 a1 = __ldg(P.xyz4 + key_idx(pend_s[(j + 1) * BD]));
+          float4 a2 = __ldg(P.xyz4 + key_idx(pend_s[(j + 2) * BD]));
+          float4 a3 = __ldg(P.xyz4 + key_idx(pend_s[(j + 3) * BD]));
+          if (shifted) {
+            a0.x = __fsub_rn(a0.x, kx); a0.y = __fsub_rn(a0.y, ky); a0.z = __fsub_rn(a0.z, kz);
+            a1.x = __fsub_rn(a1.x, kx); a1.y = __fsub_rn(a1.y, ky); a1.z = __fsub_rn(a1.z, kz);
+            a2.x = __fsub_rn(a2.x, kx); a2.y = __fsub_rn(a2.y, ky); a2.z = __fsub_rn(a2.z, kz);
+            a3.x = __fsub_rn(a3.x, kx); a3.y = __fsub_rn(a3.y, ky); a3.z = __fsub_rn(a3.z, kz);
+          }
+          accumulate_point(acc, a0.x, a0.y, a0.z);
+          accumulate_point(acc, a1.x, a1.y, a1.z);
+          accumulate_point(acc, a2.x, a2.y, a2.z);
+          accumulate_point(acc, a3.x, a3.y, a3.z);
+        }
+        for (; j < m; j++) {
+          float4 a = __ldg(P.xyz4 + key_idx(pend_s[j * BD]));
+          if (shifted) { a.x = __fsub_rn(a.x, kx); a.y = __fsub_rn(a.y, ky); a.z = __fsub_rn(a.z, kz); }
+          accumulate_point(acc, a.x, a.y, a.z);
+        }
+        normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
+      }
+      store_normal(P.normals, row, P.nsf, o);
+    }
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // Ring-expanding k-nearest search, one WARP per query: the hand-over path of k_knn_fast (sparse
@@ -382,7 +454,8 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
   const int cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
   int cnt = 0;
   u64 tau = PPP_KEY_INF;  // warp-uniform acceptance threshold (k-th best after the last ring)
-  u64 mine = PPP_KEY_INF; // lane j ends up holding the j-th nearest key
+  u64 mine = PPP_KEY_INF;  // lane j ends up holding the j-th nearest key ...
+  u64 mine2 = PPP_KEY_INF; // ... and the (32+j)-th (k <= 64)
   int du = max(max(-cu, cu - (g.nu - 1)), 0), dv0 = max(max(-cv, cv - (g.nv - 1)), 0);
   int R = max(P.R0, max(du, dv0));
   int R_prev = -1;
@@ -412,12 +485,13 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
     int head = 0;
     u64 kth = PPP_KEY_INF;
     mine = PPP_KEY_INF;
+    mine2 = PPP_KEY_INF;
     for (int j = 0; j < kk; j++) {
       u64 h = head < cnt ? L[head * 32] : PPP_KEY_INF;
       u64 m = warp_min_u64(h);
       if (m == PPP_KEY_INF) break;
       if (h == m) head++;  // keys are unique (distinct point indices)
-      if (lane == j) mine = m;
+      if (lane == (j & 31)) { if (j < 32) mine = m; else mine2 = m; }
       kth = (j == kk - 1) ? m : kth;
     }
     if (kth != PPP_KEY_INF && key_d2(kth) < ring_bound2(g, R, cu, cv)) break;
@@ -426,10 +500,15 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
     R_prev = R;
     R++;
   }
-  const int have = __popc(__ballot_sync(0xffffffffu, mine != PPP_KEY_INF));
+  const int have = __popc(__ballot_sync(0xffffffffu, mine != PPP_KEY_INF)) +
+                   __popc(__ballot_sync(0xffffffffu, mine2 != PPP_KEY_INF));
   if (P.idx_out && lane < k) {
     P.idx_out[row * (int64_t)k + lane] = mine != PPP_KEY_INF ? key_idx(mine) : -1;
     if (P.d2_out) P.d2_out[row * (int64_t)k + lane] = mine != PPP_KEY_INF ? key_d2(mine) : CUDART_INF_F;
+  }
+  if (P.idx_out && 32 + lane < k) {
+    P.idx_out[row * (int64_t)k + 32 + lane] = mine2 != PPP_KEY_INF ? key_idx(mine2) : -1;
+    if (P.d2_out) P.d2_out[row * (int64_t)k + 32 + lane] = mine2 != PPP_KEY_INF ? key_d2(mine2) : CUDART_INF_F;
   }
   if (P.normals) {
     float o[4];
@@ -441,8 +520,9 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
       const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
       float kx = 0.f, ky = 0.f, kz = 0.f;
       const int my_idx = mine != PPP_KEY_INF ? key_idx(mine) : 0;
+      const int my_idx2 = mine2 != PPP_KEY_INF ? key_idx(mine2) : 0;
       for (int j = 0; j < have; j++) {
-        int idx = __shfl_sync(0xffffffffu, my_idx, j);
+        int idx = __shfl_sync(0xffffffffu, j < 32 ? my_idx : my_idx2, j & 31);
         float4 a = __ldg(P.xyz4 + idx);
         if (shifted && j == 0) { kx = a.x; ky = a.y; kz = a.z; }
         float x = a.x, y = a.y, z = a.z;
@@ -460,7 +540,12 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
 __global__ void __launch_bounds__(128) k_radius_count(SearchParams P, int32_t* __restrict__ counts, int32_t* __restrict__ max_count) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int cnt = 0;
-  if (t < P.nq) {
+  bool have = t < P.nq;
+  if (P.use_redo) {
+    have = t < *P.redo_count;
+    if (have) t = P.redo_list[t];
+  }
+  if (have) {
     const GridView& g = P.g;
     float qx, qy, qz;
     int64_t row;
@@ -565,21 +650,20 @@ static int launch_search(ppp_cloud* c, SearchParams& P) {
   return PPP_OK;
 }
 
-template <int K>
+template <int K, int PB, bool RADIUS>
 static int launch_knn_fast_k(ppp_cloud* c, SearchParams& P) {
   ppp_ctx* ctx = c->ctx;
-  auto kern = k_knn_fast<K>;
+  auto kern = k_knn_fast<K, PB, RADIUS>;
   const int block = 128;
-  size_t smem = (size_t)K * 8 * block;
+  size_t smem = (size_t)((K > 16 || RADIUS) ? (K > PB ? K : PB) : PB) * 8 * block;
   if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned blocks = (unsigned)((P.nq + block - 1) / block);
-  PPP_LAUNCH(ctx, P.normals ? "knn_normals" : "knn", kern, blocks, block, smem, P);
+  PPP_LAUNCH(ctx, RADIUS ? "radius_normals" : (P.normals ? "knn_normals" : "knn"), kern, blocks, block, smem, P);
   PPP_CHECK_LAUNCH();
   return PPP_OK;
 }
 
-// fast fixed-block kernel, then the generic ring-expanding kernel on whatever it handed over
-static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
+static int prepare_fast(ppp_cloud* c, SearchParams& P, int32_t** redo_out) {
   ppp_ctx* ctx = c->ctx;
   if (!P.q) {
     if (!c->dup_flag) {
@@ -595,16 +679,25 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
   P.redo_count = redo;
   P.redo_list = redo + 1;
   P.use_redo = 0;
+  *redo_out = redo;
+  return PPP_OK;
+}
+
+// fast fixed-block kernel, then the ring-expanding warp kernel on whatever it handed over
+static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
+  ppp_ctx* ctx = c->ctx;
+  int32_t* redo = nullptr;
+  PPP_TRY(prepare_fast(c, P, &redo));
   int st;
-  if (P.cap <= 8) st = launch_knn_fast_k<8>(c, P);
-  else if (P.cap <= 16) st = launch_knn_fast_k<16>(c, P);
-  else st = launch_knn_fast_k<32>(c, P);
+  if (P.cap <= 8) st = launch_knn_fast_k<8, 8, false>(c, P);
+  else if (P.cap <= 16) st = launch_knn_fast_k<16, 16, false>(c, P);
+  else if (P.cap <= 32) st = launch_knn_fast_k<32, 16, false>(c, P);
+  else st = launch_knn_fast_k<64, 16, false>(c, P);
   if (st == PPP_OK) {
-    // hand-over queries: one warp each (grid sized for the worst case; surplus warps exit at once)
+    // hand-over queries: one warp each, persistent warps (their number is only known on the device)
     P.use_redo = 1;
     size_t smem = (size_t)WARPQ_WARPS * 32 * P.cap * 8;
     if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(k_knn_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // more than ~1/8 of the queries failing means the cell size is badly matched; still correct, just slower
     unsigned blocks = (unsigned)std::min<int64_t>((P.nq + WARPQ_WARPS - 1) / WARPQ_WARPS, (int64_t)ctx->sm_count * 8);
     PPP_LAUNCH(ctx, "knn_redo", k_knn_warp, blocks, WARPQ_WARPS * 32, smem, P);
     PPP_CHECK_LAUNCH();
@@ -636,7 +729,7 @@ int knn_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq
                P.normals, normal_stride_f);
     PPP_CHECK_LAUNCH();
   }
-  if (k <= 32 && nq > 0 && !getenv("PPP_KNN_GENERIC")) return launch_knn_fast(c, P);
+  if (k <= 64 && nq > 0 && !getenv("PPP_KNN_GENERIC")) return launch_knn_fast(c, P);
   return launch_search(c, P);
 }
 
@@ -682,11 +775,9 @@ int radius_fill_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, in
 int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int64_t count, float r2,
                           const float vp[3], unsigned flags, float* normals_dev, int normal_stride_f) {
   ppp_ctx* ctx = c->ctx;
-  int mx = radius_count_launch(c, gs, nullptr, count, 0, first, r2, nullptr);
-  if (mx < 0) return mx;
   SearchParams P{};
   P.g = gs.v; P.xyz4 = c->xyz4; P.q = nullptr; P.nq = count; P.first = first;
-  P.cap = std::max(mx, 1); P.mode = 1; P.r2 = r2; P.R0 = radius_rings(gs.v, std::sqrt((double)r2));
+  P.mode = 1; P.r2 = r2; P.R0 = radius_rings(gs.v, std::sqrt((double)r2));
   P.normals = normals_dev; P.nsf = normal_stride_f;
   P.vpx = vp ? vp[0] : 0; P.vpy = vp ? vp[1] : 0; P.vpz = vp ? vp[2] : 0; P.flags = flags;
   if (c->n_finite < c->n && first == 0) {
@@ -695,5 +786,40 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int6
                (float*)nullptr, normals_dev, normal_stride_f);
     PPP_CHECK_LAUNCH();
   }
-  return launch_search(c, P);
+  if (count <= 0) return PPP_OK;
+  // expected neighbours per query from the surface density; the fixed-capacity fast kernel pays
+  // off while most queries stay within its 32-entry lists
+  const double expect = c->density * 3.14159265358979 * (double)r2;
+  const bool fast = expect <= 24.0 && !getenv("PPP_KNN_GENERIC");
+  int32_t* redo = nullptr;
+  int n_redo = 0;
+  if (fast) {
+    PPP_TRY(prepare_fast(c, P, &redo));
+    P.cap = 32;
+    PPP_TRY((launch_knn_fast_k<32, 16, true>(c, P)));
+    PPP_CUDA(cudaMemcpyAsync(&n_redo, redo, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_redo == 0) { dev_free(ctx, redo); return PPP_OK; }
+    P.use_redo = 1;
+  }
+  // generic path: all queries, or only the ones the fast kernel handed over
+  const int64_t nq = fast ? n_redo : count;
+  SearchParams C = P;
+  C.nq = nq;
+  int32_t* mx = nullptr;
+  PPP_TRY(dev_alloc(ctx, &mx, 1));
+  PPP_CUDA(cudaMemsetAsync(mx, 0, 4, ctx->stream));
+  {
+    unsigned blocks = (unsigned)((nq + 127) / 128);
+    PPP_LAUNCH(ctx, "radius_count", k_radius_count, blocks, 128, 0, C, (int32_t*)nullptr, mx);
+    PPP_CHECK_LAUNCH();
+  }
+  int hmx = 0;
+  PPP_CUDA(cudaMemcpyAsync(&hmx, mx, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  dev_free(ctx, mx);
+  C.cap = std::max(hmx, 1);
+  int st = launch_search(c, C);
+  dev_free(ctx, redo);
+  return st;
 }
