@@ -52,7 +52,8 @@ def halo_violations(local_cloud, owned, kth_d2, cuts, rank, halo):
     x = local_cloud[:, 0].astype(np.float64)
     lo, hi = cuts[rank] - halo, cuts[rank + 1] + halo
     reach = np.sqrt(np.maximum(kth_d2.astype(np.float64), 0.0)) * (1.0 + 1e-6)
-    bad = owned & (((x - reach) < lo) & np.isfinite(lo) | ((x + reach) >= hi) & np.isfinite(hi))
+    bad = owned & np.isfinite(reach) & np.isfinite(x)   # non-finite points have no neighbours at all
+    bad &= ((x - reach) < lo) & np.isfinite(lo) | ((x + reach) >= hi) & np.isfinite(hi)
     return np.nonzero(bad)[0]
 
 
@@ -108,3 +109,77 @@ def assemble_contours(S, per_rank):
             x[goff[s]:goff[s + 1]] = xx[a:b]
             z[goff[s]:goff[s + 1]] = zz[a:b]
     return goff, y, x, z
+
+
+# -------------------------------------------------------------------------------------------------
+# Device-side redistribution: the exchange step of the multi-GPU path (NCCL all-to-all-v).
+# -------------------------------------------------------------------------------------------------
+IDX_COL = 5    # pcl::PointXYZRGB padding floats carry the global point index (as int32 bits) ...
+OWNED_COL = 6  # ... and the "owned by this rank" flag while a record travels between ranks
+
+
+def redistribute(dist, chunk, global_start, rank, world, halo, bins=4096):
+    """Spatial redistribution of a cloud that starts out split by ORIGINAL INDEX (rank r holds the
+    records [global_start, global_start + len(chunk)) of the file, in order), e.g. each rank read
+    its share of the PCD.  Afterwards rank r holds every point of its x-slab plus the halo copies
+    from its neighbours, still in ascending global index order (so index tie-breaks are those of
+    the single-GPU run).
+
+    chunk: torch float32 (n_r, 8) PointXYZRGB records on the rank's device (or CPU with gloo).
+    Collectives: all_reduce (x range, 4096-bin x histogram -> equal-count cuts), all_to_all_single
+    (counts, then the records: the halo exchange).  Returns (local_records, global_idx int64,
+    owned bool, cuts float64 tensor on CPU)."""
+    import torch
+    dev = chunk.device
+    n = chunk.shape[0]
+    x = chunk[:, 0]
+    fin = torch.isfinite(chunk[:, 0]) & torch.isfinite(chunk[:, 1]) & torch.isfinite(chunk[:, 2])
+    big = torch.finfo(torch.float32).max
+    lo = torch.where(fin, x, torch.full_like(x, big)).min() if n else torch.tensor(big, device=dev)
+    hi = torch.where(fin, x, torch.full_like(x, -big)).max() if n else torch.tensor(-big, device=dev)
+    rng = torch.stack([lo, -hi]).to(torch.float64)
+    dist.all_reduce(rng, op=dist.ReduceOp.MIN)
+    x_min, x_max = float(rng[0]), float(-rng[1])
+    span = max(x_max - x_min, 1e-9)
+    # equal-count cuts from a global histogram (identical on every rank)
+    b = torch.clamp(((x.to(torch.float64) - x_min) / span * bins).floor().to(torch.int64), 0, bins - 1)
+    hist = torch.bincount(b[fin], minlength=bins).to(torch.int64)
+    dist.all_reduce(hist)
+    cum = torch.cumsum(hist, 0).cpu().numpy()
+    total = int(cum[-1])
+    cuts = [-np.inf]
+    for r in range(1, world):
+        k = int(np.searchsorted(cum, total * r / world, side="left"))
+        cuts.append(x_min + span * (k + 1) / bins)
+    cuts.append(np.inf)
+    cuts = np.asarray(cuts, np.float64)
+    cuts_t = torch.tensor(cuts[1:-1], dtype=torch.float64, device=dev)
+    x64 = x.to(torch.float64)
+    owner = torch.bucketize(x64, cuts_t, right=True)           # cut[r] <= x < cut[r+1]
+    owner = torch.where(fin, owner, torch.zeros_like(owner))      # non-finite points stay with rank 0
+    rec = chunk.clone()
+    gidx = torch.arange(global_start, global_start + n, device=dev, dtype=torch.int32)
+    rec[:, IDX_COL] = gidx.view(torch.float32)
+    send_parts, counts = [], []
+    cl = torch.tensor(cuts, dtype=torch.float64, device=dev)
+    for d in range(world):
+        own = owner == d
+        near = fin & ~own & (x64 >= cl[d] - halo) & (x64 < cl[d + 1] + halo)
+        sel = own | near
+        part = rec[sel]
+        part[:, OWNED_COL] = own[sel].to(torch.float32)
+        send_parts.append(part)
+        counts.append(part.shape[0])
+    send = torch.cat(send_parts, 0) if send_parts else rec[:0]
+    cnt_s = torch.tensor(counts, dtype=torch.int64, device=dev)
+    cnt_r = torch.empty_like(cnt_s)
+    dist.all_to_all_single(cnt_r, cnt_s)
+    rc = [int(v) for v in cnt_r.cpu()]
+    recv = torch.empty((sum(rc), chunk.shape[1]), dtype=chunk.dtype, device=dev)
+    dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=counts)
+    g = recv[:, IDX_COL].contiguous().view(torch.int32).to(torch.int64)
+    owned = recv[:, OWNED_COL] > 0.5
+    local = recv.clone()
+    local[:, IDX_COL] = 0.0
+    local[:, OWNED_COL] = 0.0
+    return local, g, owned, cuts

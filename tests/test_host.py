@@ -117,3 +117,42 @@ def test_gloo_world2_gather(tmp_path):
     ref_c = oc.slice_contours(planes, "B")
     assert np.array_equal(got["normals"].view(np.uint32), ref_n.view(np.uint32))
     assert np.array_equal(got["off"], ref_c[0]) and np.array_equal(got["y"], ref_c[1]) and np.array_equal(got["z"], ref_c[3])
+
+
+def _redistribute_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cloud = synth.panel(12000, 17)
+    cloud[100, 1] = np.nan
+    n = cloud.shape[0]
+    a, b = (n * rank) // world, (n * (rank + 1)) // world
+    local, g, owned, cuts = parallel.redistribute(dist, torch.from_numpy(cloud[a:b].copy()), a, rank, world, 12.0)
+    local, g, owned = local.numpy(), g.numpy(), owned.numpy()
+    assert np.all(np.diff(g) > 0)                                    # ascending global index
+    assert np.array_equal(local[:, :5].view(np.uint32), cloud[g][:, :5].view(np.uint32))   # records intact
+    oc = po.OracleCloud(local)
+    nrm, _ = oc.normals(k=16)
+    _, d2 = oc.knn(16)
+    assert len(parallel.halo_violations(local, owned, d2[:, -1], cuts, rank, 12.0)) == 0
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), g=g[owned], nrm=nrm[owned])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_redistribute_exchange(tmp_path):
+    """The all-to-all-v halo exchange (CPU tensors over gloo): ownership partitions the cloud and the
+    sharded normals equal the single-process ones bit for bit."""
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_redistribute_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    cloud = synth.panel(12000, 17)
+    cloud[100, 1] = np.nan
+    ref, _ = po.OracleCloud(cloud).normals(k=16)
+    parts = [np.load(str(tmp_path / ("r%d.npz" % r))) for r in range(2)]
+    allg = np.concatenate([p["g"] for p in parts])
+    assert np.array_equal(np.sort(allg), np.arange(cloud.shape[0]))  # every point owned exactly once
+    full = parallel.assemble_normals(cloud.shape[0], 4, [(p["g"], p["nrm"]) for p in parts])
+    assert np.array_equal(full.view(np.uint32), ref.view(np.uint32))
