@@ -58,8 +58,12 @@ int ppp_create(int device, ppp_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
-  PPP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;
+  PPP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  PPP_CUDA(cudaStreamCreateWithPriority(&ctx->main_stream, cudaStreamNonBlocking, prio_lo));
+  PPP_CUDA(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi));
   PPP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->main_stream;
   cudaMemPool_t pool;
   PPP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t thr = UINT64_MAX;  // keep freed blocks cached: temporaries are re-used every call
@@ -71,21 +75,23 @@ int ppp_create(int device, ppp_ctx** out) {
 void ppp_destroy(ppp_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->main_stream);
+  cudaStreamSynchronize(ctx->aux_stream);
   for (auto& kv : ctx->kstats)
     for (auto& p : kv.second.pending) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
   for (int t = 0; t < 16; t++)
     for (auto& p : ctx->t_pending[t]) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->main_stream);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
 }
 
-void* ppp_stream(ppp_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+void* ppp_stream(ppp_ctx* ctx) { return ctx ? (void*)ctx->main_stream : nullptr; }
 
 int ppp_sync(ppp_ctx* ctx) {
   REQUIRE(ctx, "ctx is NULL");
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->main_stream));
   return PPP_OK;
 }
 
@@ -104,7 +110,7 @@ int ppp_timer_begin(ppp_ctx* ctx, int tag) {
   cudaEvent_t a, b;
   PPP_CUDA(cudaEventCreate(&a));
   PPP_CUDA(cudaEventCreate(&b));
-  PPP_CUDA(cudaEventRecord(a, ctx->stream));
+  PPP_CUDA(cudaEventRecord(a, ctx->main_stream));
   ctx->t_pending[tag].emplace_back(a, b);
   return PPP_OK;
 }
@@ -112,13 +118,13 @@ int ppp_timer_end(ppp_ctx* ctx, int tag) {
   REQUIRE(ctx && tag >= 0 && tag < 16, "bad ctx/tag");
   LOCK(ctx);
   REQUIRE(!ctx->t_pending[tag].empty(), "timer_end without timer_begin");
-  PPP_CUDA(cudaEventRecord(ctx->t_pending[tag].back().second, ctx->stream));
+  PPP_CUDA(cudaEventRecord(ctx->t_pending[tag].back().second, ctx->main_stream));
   return PPP_OK;
 }
 int ppp_timer_read(ppp_ctx* ctx, int tag, double* total_ms, int64_t* regions, int reset) {
   REQUIRE(ctx && tag >= 0 && tag < 16, "bad ctx/tag");
   LOCK(ctx);
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->main_stream));
   for (auto& p : ctx->t_pending[tag]) {
     float ms = 0;
     PPP_CUDA(cudaEventElapsedTime(&ms, p.first, p.second));
@@ -143,7 +149,8 @@ int ppp_kernel_profile(ppp_ctx* ctx, int enable) {
 int ppp_kernel_profile_read(ppp_ctx* ctx, char* buf, size_t cap, int reset) {
   REQUIRE(ctx && buf && cap > 0, "bad arguments");
   LOCK(ctx);
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->main_stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->aux_stream));
   std::string s;
   for (auto& kv : ctx->kstats) {
     KernelStat& st = kv.second;
@@ -210,9 +217,11 @@ int ppp_cloud_free(ppp_cloud* c) {
   LOCK(ctx);
   cudaSetDevice(ctx->device);
   dev_free(ctx, c->xyz4);
-  for (auto& g : c->grids) { dev_free(ctx, g.sorted); dev_free(ctx, g.cell_start); dev_free(ctx, g.order); }
+  for (auto& g : c->grids) {
+    dev_free(ctx, g.sorted); dev_free(ctx, g.cell_start); dev_free(ctx, g.order);
+    if (g.ready) cudaEventDestroy(g.ready);
+  }
   dev_free(ctx, c->c_node_off); dev_free(ctx, c->c_y); dev_free(ctx, c->c_x); dev_free(ctx, c->c_z);
-  dev_free(ctx, c->dup_flag);
   delete c;
   return PPP_OK;
 }
@@ -295,15 +304,22 @@ int ppp_dev_slice_contours(ppp_cloud* c, const float* plane_x_host, int S, float
   ppp_ctx* ctx = c->ctx;
   LOCK(ctx);
   PPP_CUDA(cudaSetDevice(ctx->device));
-  int64_t* boff = nullptr; int32_t* bidx = nullptr; float* planes = nullptr; int64_t M = 0;
-  std::vector<int64_t> off_h;
-  PPP_TRY(bands_launch(c, plane_x_host, S, half_width, truncate_center, pairing_mode == PPP_PAIR_GEN2, &boff, &bidx, &M,
-                       &planes, &off_h));
   GridStore* g;
-  int st = pick_any_grid(c, &g);
-  int64_t total = 0;
-  if (st == PPP_OK) st = contours_launch(c, *g, planes, S, boff, bidx, M, off_h, pairing_mode, &total);
-  dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, planes);
+  PPP_TRY(pick_any_grid(c, &g));
+  int st;
+  int64_t M = 0, total = 0;
+  {
+    // The slicing chain depends on the packed cloud and the grid only, not on the neighbour
+    // search: it runs on the high-priority auxiliary stream, concurrently with a kNN / normals
+    // kernel still executing on the main stream; the main stream waits for it on scope exit.
+    AuxScope aux(ctx, g->ready);
+    int64_t* boff = nullptr; int32_t* bidx = nullptr; float* planes = nullptr;
+    std::vector<int64_t> off_h;
+    st = bands_launch(c, plane_x_host, S, half_width, truncate_center, pairing_mode == PPP_PAIR_GEN2, &boff, &bidx, &M,
+                      &planes, &off_h);
+    if (st == PPP_OK) st = contours_launch(c, *g, planes, S, boff, bidx, M, off_h, pairing_mode, &total);
+    dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, planes);
+  }
   if (st != PPP_OK) return st;
   if (node_offsets_dev) *node_offsets_dev = c->c_node_off;
   if (y_dev) *y_dev = c->c_y;

@@ -237,6 +237,8 @@ int cloud_get_grid(ppp_cloud* c, double h, GridStore** out) {
     PPP_CHECK_LAUNCH();
   }
   dev_free(ctx, counts);
+  PPP_CUDA(cudaEventCreateWithFlags(&gs.ready, cudaEventDisableTiming));
+  PPP_CUDA(cudaEventRecord(gs.ready, ctx->stream));
   c->grids.push_back(gs);
   *out = &c->grids.back();
   return PPP_OK;

@@ -37,7 +37,6 @@ struct SearchParams {
   int nsf;
   float vpx, vpy, vpz;
   unsigned flags;
-  int32_t* dup_flag;    // self mode: set to 1 if a different point lies at float distance 0
   // fast path -> generic path hand-over: queries the fixed-radius fast kernel could not finish
   int32_t* redo_list;   // query numbers t (fast kernel appends; generic kernel consumes)
   int32_t* redo_count;
@@ -79,7 +78,6 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
   }
   u64* L = s_keys + threadIdx.x;
   int cnt = 0;
-  bool dup_seen = false;
   const bool self = P.q == nullptr;
   const bool fin = finite3(qx, qy, qz);
   if (fin && g.n_sorted > 0) {
@@ -90,7 +88,6 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
       visit_annulus(g, cu, cv, -1, P.R0, [&](float4 c) {
         u64 key = make_key(d2_flann(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
         if (key < tau) {
-          dup_seen |= (key >> 32) == 0 && self && __float_as_int(c.w) != (int)row;
           list_insert(L, BD, cnt, P.cap, key);
           if (cnt == P.cap) tau = min(tau, L[(P.cap - 1) * BD] + 1);  // full: keep the cap smallest
         }
@@ -104,7 +101,6 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
       while (true) {
         visit_annulus(g, cu, cv, R_prev, R, [&](float4 c) {
           u64 key = make_key(d2_flann(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
-          dup_seen |= (key >> 32) == 0 && self && __float_as_int(c.w) != (int)row;
           if (key < tau) {
             list_insert(L, BD, cnt, P.cap, key);
             if (cnt == P.cap) tau = L[(P.cap - 1) * BD];
@@ -117,7 +113,6 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
       }
     }
   }
-  if (dup_seen && P.dup_flag) *P.dup_flag = 1;
   // ---- outputs ----
   if (P.idx_out) {
     if (P.mode == 0) {
@@ -203,7 +198,6 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
   for (int i = 0; i < K; i++) best[i] = PPP_KEY_INF;
   int pc = 0;
   int nacc = 0;  // RADIUS: number of in-radius candidates seen (overflow detection)
-  bool dup_seen = false;
   const int R = P.R0;
   int cu = 0, cv = 0;
   u64 tau = 0;  // inactive lanes accept nothing
@@ -238,7 +232,6 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
   // pending buffers: one flush site keeps the unrolled networks in the instruction cache once.
   // U candidates per iteration: the loads are issued together, then consumed.
   constexpr int U = 4;
-  int zero_cnt = 0;
   u64* wptr = pend_s;  // next free pending slot of this thread (= pend_s + pc * BD)
 #pragma unroll 1
   for (int j = 0; j <= 2 * R + 1; j++) {
@@ -274,7 +267,6 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
       for (int u = 0; u < U; u++) {
         float d2 = d2_flann(qx, qy, qz, c[u].x, c[u].y, c[u].z);
         u64 key = make_key(d2, __float_as_int(c[u].w));
-        zero_cnt += (in[u] && d2 == 0.0f) ? 1 : 0;
         if (in[u] && key < tau) {
           *wptr = key;
           wptr += BD;
@@ -286,9 +278,6 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
       if (__any_sync(0xffffffffu, pc > trig)) { flush(); wptr = pend_s; }
     }
   }
-  // a self query always sees itself at distance 0; a second zero-distance point is a duplicate
-  dup_seen = self && zero_cnt >= 2;
-  if (dup_seen && P.dup_flag) *P.dup_flag = 1;
   if (!valid) return;
 
   bool complete;
@@ -624,15 +613,6 @@ int radius_rings(const GridView& g, double r) {
 
 static int launch_search(ppp_cloud* c, SearchParams& P) {
   ppp_ctx* ctx = c->ctx;
-  if (!P.q) {
-    if (!c->dup_flag) {
-      PPP_TRY(dev_alloc(ctx, &c->dup_flag, 1));
-      PPP_CUDA(cudaMemsetAsync(c->dup_flag, 0, sizeof(int32_t), ctx->stream));
-    }
-    P.dup_flag = c->dup_flag;
-    // the flag is complete once every indexed point has been a query of a search with >= 1 ring
-    if (P.first == 0 && P.nq == c->n_finite && P.R0 >= 1 && (P.mode == 1 || P.cap >= 2)) c->dup_known = true;
-  }
   int block; size_t smem;
   PPP_TRY(pick_block(ctx, std::max(P.cap, 1), &block, &smem));
   if (P.use_redo) {  // few, scattered queries: small blocks spread them over all SMs
@@ -665,14 +645,6 @@ static int launch_knn_fast_k(ppp_cloud* c, SearchParams& P) {
 
 static int prepare_fast(ppp_cloud* c, SearchParams& P, int32_t** redo_out) {
   ppp_ctx* ctx = c->ctx;
-  if (!P.q) {
-    if (!c->dup_flag) {
-      PPP_TRY(dev_alloc(ctx, &c->dup_flag, 1));
-      PPP_CUDA(cudaMemsetAsync(c->dup_flag, 0, sizeof(int32_t), ctx->stream));
-    }
-    P.dup_flag = c->dup_flag;
-    if (P.first == 0 && P.nq == c->n_finite) c->dup_known = true;
-  }
   int32_t* redo = nullptr;
   PPP_TRY(dev_alloc(ctx, &redo, (size_t)P.nq + 1));
   PPP_CUDA(cudaMemsetAsync(redo, 0, sizeof(int32_t), ctx->stream));

@@ -44,7 +44,9 @@ struct ppp_ctx {
   int device = 0;
   int sm_count = 148;
   size_t smem_optin = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // CURRENT working stream (launches, stream-ordered allocations)
+  cudaStream_t main_stream = nullptr;  // what ppp_stream() returns; timers and ppp_sync refer to it
+  cudaStream_t aux_stream = nullptr;   // high priority: the slicing chain runs here, concurrently with the kNN kernel
   cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap later kernels
   std::recursive_mutex mu;
   int64_t launches = 0;
@@ -76,6 +78,33 @@ struct GridStore {
   int32_t* cell_start = nullptr;
   int32_t* order = nullptr;  // original index per sorted position
   double h = 0;
+  cudaEvent_t ready = nullptr;  // recorded after the build: consumers on other streams wait on it
+};
+
+// Runs a section of host code with ctx->stream switched to the auxiliary stream (after it has
+// waited on `after`), then makes the main stream wait for everything the section enqueued.
+// Calls into the library are serialised by the context mutex, so the swap is race-free.
+struct AuxScope {
+  ppp_ctx* ctx;
+  cudaStream_t saved;
+  bool active;
+  // While per-kernel profiling is on everything stays on the main stream, so that each kernel's
+  // CUDA-event duration is that of the kernel running alone (overlapped kernels share the SMs).
+  AuxScope(ppp_ctx* c, cudaEvent_t after) : ctx(c), saved(c->stream), active(!c->profile) {
+    if (!active) return;
+    if (after) cudaStreamWaitEvent(ctx->aux_stream, after, 0);
+    ctx->stream = ctx->aux_stream;
+  }
+  ~AuxScope() {
+    if (!active) return;
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) {
+      cudaEventRecord(ev, ctx->aux_stream);
+      cudaStreamWaitEvent(ctx->main_stream, ev, 0);
+      cudaEventDestroy(ev);
+    }
+    ctx->stream = saved;
+  }
 };
 
 struct ppp_cloud {
@@ -93,9 +122,6 @@ struct ppp_cloud {
   double *c_y = nullptr, *c_x = nullptr, *c_z = nullptr;
   int64_t c_cap = 0;
   int c_S_cap = 0;
-  // set by the self-query searches: the cloud holds distinct points at float distance 0
-  int32_t* dup_flag = nullptr;
-  bool dup_known = false;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -257,24 +257,22 @@ __device__ int nn_side(const GridView& g, const float4* __restrict__ xyz4, float
   return metric == 0 ? (int)low : (int)(~low);
 }
 
-// kdtree.nearestKSearch(p, 1): global nearest under (d2, idx): for a cloud point, the lowest index
-// among the points at float distance 0 from it (itself unless the cloud has duplicates).
-__device__ int nn_full(const GridView& g, float qx, float qy, float qz) {
-  u64 best = PPP_KEY_INF;
-  int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
-  int cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
-  int R = 1, R_prev = -1;
-  while (true) {
-    visit_annulus(g, cu, cv, R_prev, R, [&](float4 c) {
-      u64 key = make_key(d2_flann(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
-      if (key < best) best = key;
-    });
-    if (best != PPP_KEY_INF && key_d2(best) < ring_bound2(g, R, cu, cv)) break;
-    if (block_covers_grid(g, cu, cv, R)) break;
-    R_prev = R;
-    R++;
+// kdtree.nearestKSearch(p, 1) for a CLOUD POINT p: the lowest index among the points at float
+// distance 0 from it (itself unless the cloud has duplicates).  Such points always share p's
+// cell: d2 == 0 in float needs every coordinate difference below ~3.7e-23, which distinct floats
+// only manage below 1e-15 in magnitude, far from any cell boundary other than the grid origin
+// (and nothing lies below the origin: it is the cloud minimum).  So the own cell is enough.
+__device__ int nn_full(const GridView& g, float qx, float qy, float qz, int self_idx) {
+  int cu = clampi(cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h), 0, g.nu - 1);
+  int cv = clampi(cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h), 0, g.nv - 1);
+  const int32_t* cs = g.cell_start + (int64_t)cv * g.nu + cu;
+  int best = self_idx;
+  for (int i = __ldg(cs), e = __ldg(cs + 1); i < e; i++) {
+    float4 c = __ldg(g.sorted + i);
+    int idx = __float_as_int(c.w);
+    if (idx < best && d2_flann(qx, qy, qz, c.x, c.y, c.z) == 0.0f) best = idx;
   }
-  return best == PPP_KEY_INF ? -1 : key_idx(best);
+  return best;
 }
 
 __device__ __forceinline__ int lower_pos(const int32_t* a, int n, int v) {
@@ -324,10 +322,10 @@ __global__ void __launch_bounds__(CT_THREADS) k_contour(ContourParams P) {
         float4 pl = __ldg(P.xyz4 + El[i]);
         int r = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, Er, nR);
         float4 pr = __ldg(P.xyz4 + r);
-        int rc = nn_full(P.g, pr.x, pr.y, pr.z);
+        int rc = nn_full(P.g, pr.x, pr.y, pr.z, r);
         int l2 = nn_side(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, El, nL);
         float4 pl2 = __ldg(P.xyz4 + l2);
-        int lc = nn_full(P.g, pl2.x, pl2.y, pl2.z);
+        int lc = nn_full(P.g, pl2.x, pl2.y, pl2.z, l2);
         P.lp[o + i] = lc;
         P.rp[o + i] = rc;
       }
@@ -421,7 +419,6 @@ struct PairParams {
   const int32_t* band_idx;
   int S;
   int64_t M;
-  const int32_t* dup_flag;  // device flag: cloud has distinct points at float distance 0 (nullptr: assume yes)
   u64* keys;
   float* ys;
   float* zs;
@@ -439,7 +436,6 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t base = ((int64_t)blockIdx.x * PAIR_WARPS + w) * PAIR_CHUNK;
   if (base >= P.M) return;
-  const bool dups = P.dup_flag ? (*P.dup_flag != 0) : true;
   int cnt = 0;
   for (int half = 0; half < 2; half++) {
     const int off = half * 32 + lane;
@@ -477,10 +473,10 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
     int ri = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, band, B);
     if (ri >= 0) {
       float4 pr = __ldg(P.xyz4 + ri);
-      int rc = dups ? nn_full(P.g, pr.x, pr.y, pr.z) : ri;
+      int rc = nn_full(P.g, pr.x, pr.y, pr.z, ri);
       int li = nn_side(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, band, B);
       float4 pl2 = __ldg(P.xyz4 + li);
-      int lc = dups ? nn_full(P.g, pl2.x, pl2.y, pl2.z) : li;
+      int lc = nn_full(P.g, pl2.x, pl2.y, pl2.z, li);
       float4 a = __ldg(P.xyz4 + rc);  // index_right
       float4 b = __ldg(P.xyz4 + lc);  // index_left
       float t = __fdiv_rn(__fsub_rn(plane, a.x), __fsub_rn(b.x, a.x));
@@ -713,7 +709,6 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     P.g = gs.v; P.xyz4 = c->xyz4;
     P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
     P.band_off = band_off_dev; P.band_idx = band_idx_dev; P.S = S; P.M = band_total;
-    P.dup_flag = c->dup_known ? c->dup_flag : nullptr;
     PPP_TRY(dev_alloc(ctx, &P.keys, M)); PPP_TRY(dev_alloc(ctx, &P.ys, M)); PPP_TRY(dev_alloc(ctx, &P.zs, M));
     if (band_total > 0) {
       const int64_t per_block = (int64_t)PAIR_WARPS * PAIR_CHUNK;
