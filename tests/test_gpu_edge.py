@@ -300,3 +300,72 @@ def test_combined_call_equals_separate_calls(ctx):
     ro, ry, rx, rz = gc.slice_contours(planes, "A")
     assert np.array_equal(off, ro) and np.array_equal(y, ry) and np.array_equal(z, rz)
     gc.close()
+
+
+@pytest.mark.parametrize("density,noise", [(4.0, 0.0), (0.25, 0.05), (1.0, 0.3)])
+def test_density_and_noise_variants(ctx, density, noise):
+    """Dense scans (78 radius neighbours: generic radius path), sparse scans, noisy surfaces."""
+    c = synth.panel(40000, 41, density=density, noise_sigma=noise)
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    gi, gd = gc.knn(16)
+    oi, od = oc.knn(16)
+    assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    _same_normals(gc.normals_radius(2.5), oc.normals(radius=2.5)[0])
+    _same_normals(gc.normals_knn(32), oc.normals(k=32)[0])
+    planes = synth.even_planes(c, 9)
+    for mode in "AB":
+        g = gc.slice_contours(planes, mode)
+        o = oc.slice_contours(planes, mode)
+        assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[3], o[3])
+    gc.close()
+
+
+def test_large_offsets_and_clusters(ctx):
+    """Coordinates far from the origin (float32 cancellation regime) and a strongly non-uniform cloud."""
+    rng = np.random.default_rng(3)
+    c = synth.panel(30000, 42)
+    c[:, 0] += np.float32(3000.0)
+    c[:, 1] -= np.float32(2500.0)
+    c[:, 2] += np.float32(50.0)
+    # a dense cluster (10x density) in one corner and a hole in the middle
+    cl = c[:3000].copy()
+    cl[:, 0:2] = c[0, 0:2] + (rng.random((3000, 2)).astype(np.float32) * 10)
+    keep = ~((np.abs(c[:, 0] - 3090) < 15) & (np.abs(c[:, 1] + 2420) < 15))
+    c2 = np.ascontiguousarray(np.concatenate([c[keep], cl]))
+    gc = api.Cloud(ctx, c2)
+    oc = po.OracleCloud(c2)
+    for k in (10, 16, 50):
+        gi, gd = gc.knn(k)
+        oi, od = oc.knn(k)
+        assert np.array_equal(gi, oi) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    _same_normals(gc.normals_radius(2.5), oc.normals(radius=2.5)[0])
+    _same_normals(gc.normals_knn(16), oc.normals(k=16)[0])
+    gcnt, _, gidx, _ = gc.radius(2.5)
+    ocnt, _, oidx, _ = oc.radius(2.5)
+    assert np.array_equal(gcnt, ocnt) and np.array_equal(gidx, oidx)
+    mn, mx = gc.bbox()
+    planes = po.planes("sectpath", mn[0], mx[0], 12.0)
+    for mode in "AB":
+        g = gc.slice_contours(planes, mode)
+        o = oc.slice_contours(planes, mode)
+        assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[3], o[3])
+    gc.close()
+
+
+def test_many_overlapping_planes(ctx):
+    """cfg4-style: plane spacing below the band width, every point in several bands; > 3072 planes
+    takes the global-atomic band path."""
+    c = synth.panel(60000, 43)
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    for S in (300, 4000):
+        planes = synth.even_planes(c, S)
+        goff, gidx = gc.slice_bands(planes)
+        ooff, oidx = oc.slice_bands(planes)
+        assert np.array_equal(goff, ooff) and np.array_equal(gidx, oidx)
+    planes = synth.even_planes(c, 300)
+    g = gc.slice_contours(planes, "B")
+    o = oc.slice_contours(planes, "B")
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[3], o[3])
+    gc.close()
