@@ -41,8 +41,8 @@ S_PER_MILLION = 200       # 5 mm plane spacing on the 1000 mm panel
 HALF_WIDTH = 2.0
 HALO_MM = 12.0
 PAIRING = "B"             # SectPath::insert_point (src/contour_alg.cpp:165-237)
-CPU_SAMPLE_N = 250_000    # bounded CPU sample: same density, same plane spacing
-CPU_SAMPLE_S = 100
+CPU_SAMPLE_N = 1_000_000  # CPU arm: the full cfg2 workload (seconds of CPU work per step)
+CPU_SAMPLE_S = 200
 
 
 def read_peaks():
@@ -153,8 +153,8 @@ def run_reference(args):
         cpu_step(po, cloud, planes, cores)
     dt = time.perf_counter() - t0
     v = CPU_SAMPLE_N * args.steps / dt
-    sample = ("oracle port of the reference CPU path, %d-point panel (same density and plane spacing as the GPU "
-              "workload), k=%d normals + %d slices, pairing %s, OpenMP over points/slices"
+    sample = ("oracle port of the reference CPU path on the full workload: %d-point panel (seed 0), "
+              "k=%d normals + %d slices, pairing %s, OpenMP over points/slices"
               % (CPU_SAMPLE_N, K_NEIGH, CPU_SAMPLE_S, PAIRING))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -410,8 +410,8 @@ def run_ours(args):
             v_all, cores, secs = cpu_baseline(True)
             v_one, _, secs1 = cpu_baseline(False)
             cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "oracle port of the reference CPU path on a %d-point panel (same density/plane spacing), "
-                             "k=%d normals + %d slices pairing %s; %.2f s with %d threads, %.2f s single-thread"
+                   "sample": "oracle port of the reference CPU path on the full workload (%d-point panel, "
+                             "k=%d normals + %d slices pairing %s); %.2f s with %d threads, %.2f s single-thread"
                              % (CPU_SAMPLE_N, K_NEIGH, CPU_SAMPLE_S, PAIRING, secs, cores, secs1),
                    "single_thread_value": v_one}
         line = {
