@@ -128,6 +128,12 @@ int ppp_slice_contours(ppp_cloud* cloud, const float* plane_x, int S, float half
                        int pairing_mode, int64_t* node_offsets, double* y, double* x, double* z,
                        int64_t node_cap);
 
+/* "next" row of SURVEY.md §8f: compute_coverage (src/Path_Generation.cpp:483-496) for a batch of
+ * path nodes.  flags: N bytes (host, in/out); flags[i] = 1 for every point i within `radius` of a
+ * query (kdtree.radiusSearch membership).  get_coverage() is the mean of the flags.            */
+int ppp_coverage_mark(ppp_cloud* cloud, const float* q, size_t nq, size_t q_stride_bytes, double radius,
+                      unsigned char* flags);
+
 /* estimate_normal() followed by the plane sweep, as one call: what SectPath-derived GenPath does
  * (src/Path_Alg/path_dynamic_alg.cpp:343-366: estimate_normal(); kdtree.setInputCloud; sweep).
  * Exactly the results of ppp_normals_knn (k >= 1, radius = 0) or ppp_normals_radius (k = 0,

@@ -690,4 +690,60 @@ int ppo_planes(int variant, float min_x, float max_x, double tool_radius, float*
   return n;
 }
 
+// ---------------------------------------------------------------------------------------------
+// "next" rows — restated for the host-side consumers of the hot path's output.
+// ---------------------------------------------------------------------------------------------
+
+// gsl_interp_steffen (GSL >= 2.0, interpolation/steffen.c) [upstream, recalled; GSL is not in the
+// image]: monotone cubic Hermite spline of Steffen (1990).  include/Spline.h:10-29 builds two of
+// them, x(y) and z(y), over the ordered contour nodes.  Evaluates nq abscissae; returns -1 if
+// n < 3 or the abscissae are not strictly increasing (GSL's error handler would abort), and
+// writes NaN for queries outside [xa[0], xa[n-1]] (gsl_spline_eval domain error).
+int ppo_steffen_eval(const double* xa, const double* ya, int64_t n, const double* xq, int64_t nq, double* out) {
+  if (n < 3) return -1;
+  for (int64_t i = 1; i < n; i++) if (!(xa[i] > xa[i - 1])) return -1;
+  std::vector<double> yp(n), a(n - 1), b(n - 1), c(n - 1), d(n - 1);
+  auto cps = [](double v) { return std::copysign(1.0, v); };
+  double h0 = xa[1] - xa[0];
+  yp[0] = (ya[1] - ya[0]) / h0;
+  for (int64_t i = 1; i < n - 1; i++) {
+    double hi = xa[i + 1] - xa[i], him1 = xa[i] - xa[i - 1];
+    double si = (ya[i + 1] - ya[i]) / hi, sim1 = (ya[i] - ya[i - 1]) / him1;
+    double pi = (sim1 * hi + si * him1) / (him1 + hi);
+    yp[i] = (cps(sim1) + cps(si)) * std::min(std::fabs(sim1), std::min(std::fabs(si), 0.5 * std::fabs(pi)));
+  }
+  yp[n - 1] = (ya[n - 1] - ya[n - 2]) / (xa[n - 1] - xa[n - 2]);
+  for (int64_t i = 0; i < n - 1; i++) {
+    double hi = xa[i + 1] - xa[i], si = (ya[i + 1] - ya[i]) / hi;
+    a[i] = (yp[i] + yp[i + 1] - 2 * si) / hi / hi;
+    b[i] = (3 * si - 2 * yp[i] - yp[i + 1]) / hi;
+    c[i] = yp[i];
+    d[i] = ya[i];
+  }
+  for (int64_t q = 0; q < nq; q++) {
+    double x = xq[q];
+    if (!(x >= xa[0] && x <= xa[n - 1])) { out[q] = std::numeric_limits<double>::quiet_NaN(); continue; }
+    int64_t i = std::upper_bound(xa, xa + n, x) - xa - 1;  // gsl_interp_bsearch: xa[i] <= x < xa[i+1]
+    if (i > n - 2) i = n - 2;
+    double dx = x - xa[i];
+    out[q] = d[i] + dx * (c[i] + dx * (b[i] + dx * a[i]));
+  }
+  return 0;
+}
+
+// compute_coverage (src/Path_Generation.cpp:483-496): kdtree.radiusSearch(node, radius) and
+// coverage_flag[i] = 1 for every neighbour; flags is in/out (N bytes).
+int ppo_coverage_mark(void* h, const float* q, int64_t nq, int64_t qsf, double radius, unsigned char* flags) {
+  Cloud* C = (Cloud*)h;
+  float r2 = (float)(radius * radius);
+  std::vector<Key> buf;
+  for (int64_t i = 0; i < nq; i++) {
+    const float* p = q + i * qsf;
+    if (!finite3(p)) continue;
+    C->tree.radius(p, r2, buf);
+    for (auto& k : buf) flags[k.idx] = 1;
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -54,6 +54,8 @@ def lib():
                                          _f64p, _f64p, C.c_int64, C.c_int]
         L.ppo_planes.argtypes = [C.c_int, C.c_float, C.c_float, C.c_double, _f32p, C.c_int]
         L.ppo_num_threads.restype = C.c_int
+        L.ppo_steffen_eval.argtypes = [_f64p, _f64p, C.c_int64, _f64p, C.c_int64, _f64p]
+        L.ppo_coverage_mark.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_ubyte)]
         _lib = L
     return _lib
 
@@ -165,6 +167,14 @@ class OracleCloud:
                               _lp(off), _ip(idx), threads)
         return off, idx
 
+    def coverage_mark(self, queries, radius, flags=None):
+        queries = np.ascontiguousarray(queries, np.float32)
+        if flags is None:
+            flags = np.zeros(self.n, np.uint8)
+        lib().ppo_coverage_mark(self._h, _fp(queries), queries.shape[0], queries.shape[1], float(radius),
+                                flags.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        return flags
+
     def insert_point(self, indices, plane_x, mode):
         """mode 'A' (gen-2) or 'B' (SectPath). Returns (y, x, z, left_pair, right_pair)."""
         indices = np.ascontiguousarray(indices, np.int32)
@@ -195,6 +205,17 @@ class OracleCloud:
             if tot <= cap:
                 return off, y[:tot].copy(), x[:tot].copy(), z[:tot].copy()
             cap = int(tot)
+
+
+def steffen_eval(xa, ya, xq):
+    xa = np.ascontiguousarray(xa, np.float64)
+    ya = np.ascontiguousarray(ya, np.float64)
+    xq = np.ascontiguousarray(xq, np.float64)
+    out = np.empty(xq.shape[0], np.float64)
+    st = lib().ppo_steffen_eval(_dp(xa), _dp(ya), xa.shape[0], _dp(xq), xq.shape[0], _dp(out))
+    if st != 0:
+        raise ValueError("steffen: need >= 3 strictly increasing abscissae")
+    return out
 
 
 def normal_from_list(pts, nb, q, viewpoint=(0, 0, 0), cov_variant=0):

@@ -241,6 +241,15 @@ class Cloud:
         t = int(off[-1])
         return nrm, off, y[:t], x[:t], z[:t]
 
+    def coverage_mark(self, queries, radius, flags=None):
+        """compute_coverage for a batch of nodes; flags (uint8, N) is updated in place and returned."""
+        queries = np.ascontiguousarray(queries, np.float32)
+        if flags is None:
+            flags = np.zeros(self.n, np.uint8)
+        check(self.lib.ppp_coverage_mark(self._h, _ptr(queries), queries.shape[0], queries.shape[1] * 4, float(radius),
+                                         _ptr(flags)))
+        return flags
+
     # ---- device-resident pipeline ---------------------------------------------------------------
     def dev_index(self, k_hint=16, radius_hint=0.0):
         check(self.lib.ppp_dev_index(self._h, int(k_hint), float(radius_hint)))

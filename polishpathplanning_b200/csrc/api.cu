@@ -539,4 +539,31 @@ int ppp_normals_and_contours(ppp_cloud* c, int k, double radius, const float vp[
   return PPP_OK;
 }
 
+// compute_coverage (src/Path_Generation.cpp:483-496) for a batch of nodes: flags (N bytes, host,
+// in/out) gets 1 for every point within `radius` (d2 < (float)(r*r)) of any query.
+int ppp_coverage_mark(ppp_cloud* c, const float* q, size_t nq, size_t q_stride_bytes, double radius, unsigned char* flags) {
+  REQUIRE(c && (flags || c->n == 0), "NULL argument");
+  REQUIRE(nq == 0 || q, "queries are NULL");
+  REQUIRE(radius > 0 && std::isfinite(radius), "radius must be > 0");
+  REQUIRE(q_stride_bytes >= 12 && q_stride_bytes % 4 == 0, "query stride must be >= 12 and a multiple of 4");
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  if (c->n == 0 || nq == 0) return PPP_OK;
+  GridStore* g;
+  PPP_TRY(cloud_get_grid(c, cloud_cell_for_radius(c, radius), &g));
+  unsigned char* f_d = nullptr; float* q_d = nullptr;
+  PPP_TRY(dev_alloc(ctx, &f_d, (size_t)c->n));
+  PPP_TRY(dev_alloc(ctx, (char**)&q_d, nq * q_stride_bytes + 16));
+  PPP_CUDA(cudaMemcpyAsync(f_d, flags, (size_t)c->n, cudaMemcpyHostToDevice, ctx->stream));
+  PPP_CUDA(cudaMemcpyAsync(q_d, q, nq * q_stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int st = coverage_mark_launch(c, *g, q_d, (int64_t)nq, (int)(q_stride_bytes / 4), (float)(radius * radius), f_d);
+  if (st == PPP_OK) PPP_CUDA(cudaMemcpyAsync(flags, f_d, (size_t)c->n, cudaMemcpyDeviceToHost, ctx->stream));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, f_d); dev_free(ctx, (char*)q_d);
+  if (st != PPP_OK) return st;
+  PPP_CUDA(e);
+  return PPP_OK;
+}
+
 }  // extern "C"

@@ -194,6 +194,9 @@ int radius_fill_launch(ppp_cloud* c, const GridStore& g, const float* q_dev, int
 int normals_radius_launch(ppp_cloud* c, const GridStore& g, int64_t first, int64_t count, float r2,
                           const float vp[3], unsigned flags, float* normals_dev, int normal_stride_f);
 
+int coverage_mark_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq, int q_stride_f, float r2,
+                         unsigned char* flags_dev);
+
 // slices.cu
 int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center, int sort_bands,
                  int64_t** offsets_dev_out, int32_t** idx_dev_out, int64_t* total_out, float** planes_dev_out,

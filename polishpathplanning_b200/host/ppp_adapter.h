@@ -9,7 +9,10 @@
 // host code: Spline(n, y, x, z) is constructed from the three double arrays returned here
 // (include/Spline.h:10-20).  Without GSL in this image `Spline` is the node triple itself.
 #pragma once
+#include <algorithm>
 #include <chrono>
+#include <cmath>
+#include <limits>
 #include <cstdio>
 #include <fstream>
 #include <map>
@@ -27,14 +30,55 @@ typedef std::map<double, std::vector<double>> MAP;
 
 #ifndef PPP_HAVE_GSL
 // Stand-in for include/Spline.h when GSL is absent: the ordered nodes a Spline is built from.
+// point(y) evaluates gsl_interp_steffen restated (Steffen 1990 monotone cubic; [upstream, recalled]).
 class Spline {
 public:
   Spline() {}
   Spline(int number, const double* point_y, const double* point_x, const double* point_z)
-      : y(point_y, point_y + number), x(point_x, point_x + number), z(point_z, point_z + number) {}
+      : y(point_y, point_y + number), x(point_x, point_x + number), z(point_z, point_z + number) {
+    ok_ = number >= 3;
+    for (int i = 1; i < number && ok_; i++) ok_ = y[i] > y[i - 1];
+    if (ok_) { coeffs(x, cx_); coeffs(z, cz_); }
+  }
+  bool valid() const { return ok_; }  // GSL aborts on < 3 nodes or non-increasing y; here: check before use
+  Eigen::Vector3d point(double yy) const { return Eigen::Vector3d(eval(cx_, yy), yy, eval(cz_, yy)); }
   double miny() const { return y.empty() ? 0.0 : y.front(); }
   double bigy() const { return y.empty() ? 0.0 : y.back(); }
   std::vector<double> y, x, z;
+
+private:
+  struct C { std::vector<double> a, b, c, d; };
+  static double cps(double v) { return std::copysign(1.0, v); }
+  void coeffs(const std::vector<double>& ya, C& o) const {
+    size_t n = y.size();
+    std::vector<double> yp(n);
+    yp[0] = (ya[1] - ya[0]) / (y[1] - y[0]);
+    for (size_t i = 1; i + 1 < n; i++) {
+      double hi = y[i + 1] - y[i], him1 = y[i] - y[i - 1];
+      double si = (ya[i + 1] - ya[i]) / hi, sim1 = (ya[i] - ya[i - 1]) / him1;
+      double pi = (sim1 * hi + si * him1) / (him1 + hi);
+      yp[i] = (cps(sim1) + cps(si)) * std::min(std::fabs(sim1), std::min(std::fabs(si), 0.5 * std::fabs(pi)));
+    }
+    yp[n - 1] = (ya[n - 1] - ya[n - 2]) / (y[n - 1] - y[n - 2]);
+    o.a.resize(n - 1); o.b.resize(n - 1); o.c.resize(n - 1); o.d.resize(n - 1);
+    for (size_t i = 0; i + 1 < n; i++) {
+      double hi = y[i + 1] - y[i], si = (ya[i + 1] - ya[i]) / hi;
+      o.a[i] = (yp[i] + yp[i + 1] - 2 * si) / hi / hi;
+      o.b[i] = (3 * si - 2 * yp[i] - yp[i + 1]) / hi;
+      o.c[i] = yp[i];
+      o.d[i] = ya[i];
+    }
+  }
+  double eval(const C& o, double yy) const {
+    if (!ok_ || !(yy >= y.front() && yy <= y.back())) return std::numeric_limits<double>::quiet_NaN();
+    size_t i = std::upper_bound(y.begin(), y.end(), yy) - y.begin();
+    i = i ? i - 1 : 0;
+    if (i > y.size() - 2) i = y.size() - 2;
+    double dx = yy - y[i];
+    return o.d[i] + dx * (o.c[i] + dx * (o.b[i] + dx * o.a[i]));
+  }
+  bool ok_ = false;
+  C cx_, cz_;
 };
 #endif
 

@@ -70,6 +70,55 @@ def planes_sectpath(min_x, max_x, tool_radius):
     return np.asarray(front + back, _f32)
 
 
+class Spline:
+    """include/Spline.h:7-51 — two GSL Steffen splines x(y), z(y) over the ordered contour nodes.
+    gsl_interp_steffen [upstream, recalled: GSL is not in the image]: monotone cubic Hermite of
+    Steffen (1990); same arithmetic order as the oracle restatement, in float64."""
+
+    def __init__(self, point_y, point_x, point_z):
+        y = np.ascontiguousarray(point_y, np.float64)
+        if y.shape[0] < 3 or not np.all(np.diff(y) > 0):
+            raise ValueError("Spline needs >= 3 strictly increasing y (GSL would abort)")
+        self.y = y
+        self._cx = self._coeffs(y, np.ascontiguousarray(point_x, np.float64))
+        self._cz = self._coeffs(y, np.ascontiguousarray(point_z, np.float64))
+        self.small_y, self.big_y = float(y[0]), float(y[-1])
+
+    @staticmethod
+    def _coeffs(xa, ya):
+        n = xa.shape[0]
+        h = xa[1:] - xa[:-1]
+        s = (ya[1:] - ya[:-1]) / h
+        yp = np.empty(n, np.float64)
+        yp[0] = s[0]
+        hi, him1, si, sim1 = h[1:], h[:-1], s[1:], s[:-1]
+        pi = (sim1 * hi + si * him1) / (him1 + hi)
+        yp[1:-1] = (np.copysign(1.0, sim1) + np.copysign(1.0, si)) * np.minimum(np.abs(sim1), np.minimum(np.abs(si), 0.5 * np.abs(pi)))
+        yp[-1] = s[-1]
+        a = (yp[:-1] + yp[1:] - 2 * s) / h / h
+        b = (3 * s - 2 * yp[:-1] - yp[1:]) / h
+        return a, b, yp[:-1].copy(), ya[:-1].copy()
+
+    def _eval(self, c, yq):
+        a, b, cc, d = c
+        yq = np.asarray(yq, np.float64)
+        i = np.clip(np.searchsorted(self.y, yq, side="right") - 1, 0, self.y.shape[0] - 2)
+        dx = yq - self.y[i]
+        out = d[i] + dx * (cc[i] + dx * (b[i] + dx * a[i]))
+        return np.where((yq >= self.y[0]) & (yq <= self.y[-1]), out, np.nan)
+
+    def point(self, y):
+        """Eigen::Vector3d point(double y): (x(y), y, z(y)); vectorised over y."""
+        y = np.atleast_1d(np.asarray(y, np.float64))
+        return np.stack([self._eval(self._cx, y), y, self._eval(self._cz, y)], axis=1)
+
+    def miny(self):
+        return self.small_y
+
+    def bigy(self):
+        return self.big_y
+
+
 class _Base:
     NORMAL_RADIUS = 2.5   # normal_estimation.setRadiusSearch(2.5): src/Path_Generation.cpp:329
     BAND_HALF_WIDTH = 2.0  # setFilterLimits(-2 + position, 2 + position): src/Path_Generation.cpp:100
@@ -128,6 +177,44 @@ class _Base:
 
     def _contours(self, planes, mode):
         return self._dev().slice_contours(np.asarray(planes, _f32), mode, self.BAND_HALF_WIDTH, True)
+
+    # -- "next" rows: consumers of the ordered contours --------------------------------
+    def splines(self):
+        """Spline objects of Path_set (paths with < 3 nodes are skipped, GSL would abort on them)."""
+        return [Spline(y, x, z) for (y, x, z) in self.Path_set if len(y) >= 3]
+
+    def drawpath_samples(self, path, gen2=True):
+        """The sample points drawpath snaps to the cloud: gen-2 takes 200 samples
+        dy = (maxy-miny)/200*i + miny (src/Path_Generation.cpp:644-646); SectPath steps dy += 1
+        while dy < maxy (src/contour_alg.cpp:273-283)."""
+        miny, maxy = path.miny(), path.bigy()
+        if gen2:
+            dy = (maxy - miny) / 200 * np.arange(200) + miny
+        else:
+            dy = miny + np.arange(int(np.ceil(maxy - miny)) + 1, dtype=np.float64)
+            dy = dy[dy < maxy]
+        return path.point(dy)
+
+    def drawpath(self, path, gen2=True):
+        """Indices of the cloud points drawpath recolours: nearestKSearch(point, k)[0] per sample
+        (k = 3 in gen-2, 1 in SectPath: only element [0] is used)."""
+        pts = self.drawpath_samples(path, gen2).astype(np.float32)   # PCLp.x = pathPoint[0] (double -> float)
+        idx, _ = self._dev().knn(1, queries=np.ascontiguousarray(pts), want_d2=False)
+        return idx[:, 0]
+
+    def compute_coverage(self, nodes, radius):
+        """compute_coverage for a batch of nodes (src/Path_Generation.cpp:483-496)."""
+        if not hasattr(self, "coverage_flag") or self.coverage_flag.shape[0] != self.cloud.shape[0]:
+            self.coverage_flag = np.zeros(self.cloud.shape[0], np.uint8)
+        q = np.ascontiguousarray(np.asarray(nodes, np.float64).astype(np.float32).reshape(-1, 3))
+        self._dev().coverage_mark(q, radius, self.coverage_flag)
+        return self.coverage_flag
+
+    def get_coverage(self):
+        """get_coverage (src/Path_Generation.cpp:757-771): rate = yes / (yes + no), float arithmetic."""
+        yes = _f32(int(self.coverage_flag.sum()))
+        no = _f32(int(self.coverage_flag.shape[0] - self.coverage_flag.sum()))
+        return float(yes / (yes + no))
 
 
 class path_generater(_Base):

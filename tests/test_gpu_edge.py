@@ -369,3 +369,32 @@ def test_many_overlapping_planes(ctx):
     o = oc.slice_contours(planes, "B")
     assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and np.array_equal(g[3], o[3])
     gc.close()
+
+
+def test_next_rows_drawpath_and_coverage(ctx):
+    """spline sampling + nearest-point snaps (drawpath) and compute_coverage flags."""
+    c = synth.panel(40000, 51)
+    pg = ra.path_generater(c.copy() / np.float32(1000.0) * np.float32(1.0), 15, ctx=ctx)  # ctor rescales by 1000
+    pg.cloud[:, :3] = c[:, :3]
+    pg._invalidate()
+    oc = po.OracleCloud(pg.cloud)
+    pg.Contact_Path_Generation()
+    paths = pg.splines()
+    assert len(paths) >= 3
+    sp = paths[1]
+    # drawpath: 200 samples along the spline, each snapped to its nearest cloud point
+    pts = pg.drawpath_samples(sp, gen2=True)
+    assert pts.shape == (200, 3)
+    assert np.array_equal(pts[:, 2].view(np.uint64), po.steffen_eval(sp.y, pg.Path_set[1][2], pts[:, 1]).view(np.uint64))
+    got = pg.drawpath(sp, gen2=True)
+    want, _ = oc.knn(3, queries=pts.astype(np.float32))
+    assert np.array_equal(got, want[:, 0])
+    # compute_coverage: union of radius neighbourhoods of a batch of nodes, accumulated over calls
+    nodes = pts[::10]
+    flags = pg.compute_coverage(nodes, 7.5).copy()
+    oflags = oc.coverage_mark(nodes.astype(np.float32), 7.5)
+    assert np.array_equal(flags, oflags)
+    flags2 = pg.compute_coverage(pts[5::10], 3.0)
+    oflags = oc.coverage_mark(pts[5::10].astype(np.float32), 3.0, oflags)
+    assert np.array_equal(flags2, oflags)
+    assert abs(pg.get_coverage() - float(oflags.mean())) < 1e-6

@@ -156,3 +156,30 @@ def test_gloo_redistribute_exchange(tmp_path):
     assert np.array_equal(np.sort(allg), np.arange(cloud.shape[0]))  # every point owned exactly once
     full = parallel.assemble_normals(cloud.shape[0], 4, [(p["g"], p["nrm"]) for p in parts])
     assert np.array_equal(full.view(np.uint32), ref.view(np.uint32))
+
+
+def test_steffen_spline_restatements_agree():
+    """Spline.h's gsl_interp_steffen: the product's numpy mirror equals the oracle restatement bit for
+    bit, interpolates the nodes, stays monotone between monotone nodes (Steffen 1990) and rejects what
+    GSL aborts on."""
+    from polishpathplanning_b200 import reference_api as ra
+    rng = np.random.default_rng(0)
+    y = np.cumsum(rng.random(40) + 0.05)
+    x = np.full(40, 12.5)
+    z = np.sin(y / 3) * 5 + rng.normal(0, 0.05, 40)
+    sp = ra.Spline(y, x, z)
+    q = np.linspace(y[0], y[-1], 1001)
+    p = sp.point(q)
+    assert np.array_equal(p[:, 2].view(np.uint64), po.steffen_eval(y, z, q).view(np.uint64))
+    assert np.array_equal(p[:, 0], np.full(1001, 12.5)) and np.array_equal(p[:, 1], q)
+    assert np.allclose(sp.point(y)[:, 2], z, rtol=0, atol=1e-12)
+    zm = np.cumsum(rng.random(40))                       # monotone data -> monotone spline
+    pm = ra.Spline(y, x, zm).point(q)[:, 2]
+    assert np.all(np.diff(pm) >= -1e-12)
+    assert np.isnan(sp.point([y[0] - 1.0, y[-1] + 1.0])[:, 2]).all()
+    with pytest.raises(ValueError):
+        ra.Spline(y[:2], x[:2], z[:2])
+    with pytest.raises(ValueError):
+        ra.Spline(y[::-1], x, z)
+    with pytest.raises(ValueError):
+        po.steffen_eval(y[:2], z[:2], q)
