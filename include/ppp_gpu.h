@@ -128,6 +128,14 @@ int ppp_slice_contours(ppp_cloud* cloud, const float* plane_x, int S, float half
                        int pairing_mode, int64_t* node_offsets, double* y, double* x, double* z,
                        int64_t node_cap);
 
+/* "next" row of SURVEY.md §8f: the device part of compute_transform (src/Path_Generation.cpp:362-400,
+ * k = 10; src/Path_Alg/path_dynamic_alg.cpp:77-110, k = 50) for a batch of query points:
+ * kdtree.nearestKSearch(point, k) + PrincipalCurvaturesEstimation::computePointPrincipalCurvatures
+ * around neighbour [0].  normals: n host records (nx ny nz first).  out: nq x 5 floats
+ * (pcx, pcy, pcz, pc1, pc2); nn0 (nullable): nearest point index per query.                    */
+int ppp_principal_curvatures(ppp_cloud* cloud, const void* normals, size_t normal_stride_bytes, const float* q,
+                             size_t nq, size_t q_stride_bytes, int k, float* out, int32_t* nn0);
+
 /* "next" row of SURVEY.md §8f: compute_coverage (src/Path_Generation.cpp:483-496) for a batch of
  * path nodes.  flags: N bytes (host, in/out); flags[i] = 1 for every point i within `radius` of a
  * query (kdtree.radiusSearch membership).  get_coverage() is the mean of the flags.            */

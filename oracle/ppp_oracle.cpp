@@ -746,4 +746,83 @@ int ppo_coverage_mark(void* h, const float* q, int64_t nq, int64_t qsf, double r
   return 0;
 }
 
+// pcl::PrincipalCurvaturesEstimation::computePointPrincipalCurvatures [upstream, recalled, PCL 1.10
+// features/impl/principal_curvatures.hpp] as called by compute_transform
+// (src/Path_Generation.cpp:362-400 with k = 10, src/Path_Alg/path_dynamic_alg.cpp:77-110 with k = 50):
+// kNN of the query, normals of the neighbours projected into the tangent plane of neighbour [0],
+// 3x3 covariance of the projections, eigen33 (values) + computeCorrespondingEigenVector for the
+// largest eigenvalue.  out per query: pcx, pcy, pcz, pc1, pc2; nn0 = nearest point index.
+// normals: n x nsf floats (nx, ny, nz at 0..2).
+namespace {
+inline void eigen33_values(const float m[9], float evals[3]) {
+  float scale = 0.0f;
+  for (int i = 0; i < 9; i++) scale = std::max(scale, std::fabs(m[i]));
+  if (scale <= std::numeric_limits<float>::min()) scale = 1.0f;
+  float s[6] = {m[0] / scale, m[1] / scale, m[2] / scale, m[4] / scale, m[5] / scale, m[8] / scale};
+  compute_roots(s, evals);
+  for (int i = 0; i < 3; i++) evals[i] *= scale;
+}
+inline void corresponding_eigenvector(const float m[9], float eigenvalue, float v[3]) {
+  float scale = 0.0f;
+  for (int i = 0; i < 9; i++) scale = std::max(scale, std::fabs(m[i]));
+  if (scale <= std::numeric_limits<float>::min()) scale = 1.0f;
+  float a[9];
+  for (int i = 0; i < 9; i++) a[i] = m[i] / scale;
+  float ev = eigenvalue / scale;
+  a[0] -= ev; a[4] -= ev; a[8] -= ev;
+  float v1[3], v2[3], v3[3];
+  cross3(&a[0], &a[3], v1); cross3(&a[0], &a[6], v2); cross3(&a[3], &a[6], v3);
+  float l1 = sqnorm3(v1), l2 = sqnorm3(v2), l3 = sqnorm3(v3);
+  const float* w; float l;
+  if (l1 >= l2 && l1 >= l3) { w = v1; l = l1; }
+  else if (l2 >= l1 && l2 >= l3) { w = v2; l = l2; }
+  else { w = v3; l = l3; }
+  float sl = std::sqrt(l);
+  v[0] = w[0] / sl; v[1] = w[1] / sl; v[2] = w[2] / sl;
+}
+}  // namespace
+
+int ppo_principal_curvatures(void* h, const float* normals, int64_t nsf, const float* q, int64_t nq, int64_t qsf, int k,
+                             float* out /* nq x 5 */, int32_t* nn0) {
+  Cloud* C = (Cloud*)h;
+  std::vector<Key> nb(std::max(k, 1));
+  const float nan = std::numeric_limits<float>::quiet_NaN();
+  for (int64_t t = 0; t < nq; t++) {
+    const float* p = q + t * qsf;
+    float* o = out + 5 * t;
+    int m = finite3(p) ? C->tree.knn(p, k, nb.data()) : 0;
+    if (m == 0) { for (int i = 0; i < 5; i++) o[i] = nan; if (nn0) nn0[t] = -1; continue; }
+    if (nn0) nn0[t] = nb[0].idx;
+    const float* n0 = normals + (int64_t)nb[0].idx * nsf;
+    // M = I - n n^T  (row-major 3x3)
+    float M[9];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) M[3 * i + j] = (i == j ? 1.0f : 0.0f) - n0[i] * n0[j];
+    std::vector<std::array<float, 3>> proj(m);
+    float cen[3] = {0, 0, 0};
+    for (int j = 0; j < m; j++) {
+      const float* nj = normals + (int64_t)nb[j].idx * nsf;
+      for (int i = 0; i < 3; i++) proj[j][i] = M[3 * i] * nj[0] + (M[3 * i + 1] * nj[1] + M[3 * i + 2] * nj[2]);
+      for (int i = 0; i < 3; i++) cen[i] += proj[j][i];
+    }
+    for (int i = 0; i < 3; i++) cen[i] /= (float)m;
+    float cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < m; j++) {
+      float d[3] = {proj[j][0] - cen[0], proj[j][1] - cen[1], proj[j][2] - cen[2]};
+      float xy = d[0] * d[1], xz = d[0] * d[2], yz = d[1] * d[2];
+      cov[0] += d[0] * d[0]; cov[1] += xy; cov[2] += xz;
+      cov[3] += xy; cov[4] += d[1] * d[1]; cov[5] += yz;
+      cov[6] += xz; cov[7] += yz; cov[8] += d[2] * d[2];
+    }
+    float ev[3], vec[3];
+    eigen33_values(cov, ev);
+    corresponding_eigenvector(cov, ev[2], vec);
+    float inv = 1.0f / (float)m;
+    o[0] = vec[0]; o[1] = vec[1]; o[2] = vec[2];
+    o[3] = ev[2] * inv;
+    o[4] = ev[1] * inv;
+  }
+  return 0;
+}
+
 }  // extern "C"

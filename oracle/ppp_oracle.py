@@ -55,6 +55,7 @@ def lib():
         L.ppo_planes.argtypes = [C.c_int, C.c_float, C.c_float, C.c_double, _f32p, C.c_int]
         L.ppo_num_threads.restype = C.c_int
         L.ppo_steffen_eval.argtypes = [_f64p, _f64p, C.c_int64, _f64p, C.c_int64, _f64p]
+        L.ppo_principal_curvatures.argtypes = [C.c_void_p, _f32p, C.c_int64, _f32p, C.c_int64, C.c_int64, C.c_int, _f32p, _i32p]
         L.ppo_coverage_mark.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_ubyte)]
         _lib = L
     return _lib
@@ -166,6 +167,15 @@ class OracleCloud:
         lib().ppo_slice_bands(_fp(self.pts), self.n, self.sf, _fp(planes), S, half_width, int(truncate_center),
                               _lp(off), _ip(idx), threads)
         return off, idx
+
+    def principal_curvatures(self, normals, queries, k):
+        normals = np.ascontiguousarray(normals, np.float32)
+        queries = np.ascontiguousarray(queries, np.float32)
+        out = np.empty((queries.shape[0], 5), np.float32)
+        nn0 = np.empty(queries.shape[0], np.int32)
+        lib().ppo_principal_curvatures(self._h, _fp(normals), normals.shape[1], _fp(queries), queries.shape[0],
+                                       queries.shape[1], int(k), _fp(out), _ip(nn0))
+        return out, nn0
 
     def coverage_mark(self, queries, radius, flags=None):
         queries = np.ascontiguousarray(queries, np.float32)

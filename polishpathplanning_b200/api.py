@@ -241,6 +241,16 @@ class Cloud:
         t = int(off[-1])
         return nrm, off, y[:t], x[:t], z[:t]
 
+    def principal_curvatures(self, normals, queries, k):
+        """compute_transform's device part: returns (out[nq,5] = pcx,pcy,pcz,pc1,pc2, nn0[nq])."""
+        normals = np.ascontiguousarray(normals, np.float32)
+        queries = np.ascontiguousarray(queries, np.float32)
+        out = np.empty((queries.shape[0], 5), np.float32)
+        nn0 = np.empty(queries.shape[0], np.int32)
+        check(self.lib.ppp_principal_curvatures(self._h, _ptr(normals), normals.shape[1] * 4, _ptr(queries),
+                                                queries.shape[0], queries.shape[1] * 4, int(k), _ptr(out), _ptr(nn0)))
+        return out, nn0
+
     def coverage_mark(self, queries, radius, flags=None):
         """compute_coverage for a batch of nodes; flags (uint8, N) is updated in place and returned."""
         queries = np.ascontiguousarray(queries, np.float32)

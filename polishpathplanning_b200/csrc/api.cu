@@ -566,4 +566,44 @@ int ppp_coverage_mark(ppp_cloud* c, const float* q, size_t nq, size_t q_stride_b
   return PPP_OK;
 }
 
+// compute_transform's device part for a batch of query points (src/Path_Generation.cpp:362-400):
+// kNN(k) of each query, then computePointPrincipalCurvatures around neighbour [0] on the given
+// normals (n records of normal_stride_bytes, nx ny nz first).  out: nq x 5 floats
+// (pcx, pcy, pcz, pc1, pc2); nn0 (nullable): index of the nearest point (whose normal the caller
+// crosses with the curvature direction).
+int ppp_principal_curvatures(ppp_cloud* c, const void* normals, size_t normal_stride_bytes, const float* q, size_t nq,
+                             size_t q_stride_bytes, int k, float* out, int32_t* nn0) {
+  REQUIRE(c && normals && (nq == 0 || (q && out)), "NULL argument");
+  REQUIRE(k >= 1, "k must be >= 1");
+  REQUIRE(normal_stride_bytes >= 12 && normal_stride_bytes % 4 == 0, "normal stride must be >= 12 and a multiple of 4");
+  REQUIRE(q_stride_bytes >= 12 && q_stride_bytes % 4 == 0, "query stride must be >= 12 and a multiple of 4");
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  if (nq == 0) return PPP_OK;
+  GridStore* g;
+  PPP_TRY(cloud_get_grid(c, cloud_cell_for_k(c, k), &g));
+  float *q_d = nullptr, *n_d = nullptr, *o_d = nullptr;
+  int32_t *idx_d = nullptr, *nn0_d = nullptr;
+  PPP_TRY(dev_alloc(ctx, (char**)&q_d, nq * q_stride_bytes + 16));
+  PPP_TRY(dev_alloc(ctx, (char**)&n_d, (size_t)c->n * normal_stride_bytes + 16));
+  PPP_TRY(dev_alloc(ctx, &o_d, nq * 5));
+  PPP_TRY(dev_alloc(ctx, &idx_d, nq * (size_t)k));
+  PPP_TRY(dev_alloc(ctx, &nn0_d, nq));
+  PPP_CUDA(cudaMemcpyAsync(q_d, q, nq * q_stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PPP_CUDA(cudaMemcpyAsync(n_d, normals, (size_t)c->n * normal_stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int st = knn_launch(c, *g, q_d, (int64_t)nq, (int)(q_stride_bytes / 4), 0, k, idx_d, nullptr, false, nullptr, 0, nullptr, 0);
+  if (st == PPP_OK)
+    st = principal_curvatures_launch(c, idx_d, (int64_t)nq, k, n_d, (int)(normal_stride_bytes / 4), o_d, nn0_d);
+  if (st == PPP_OK) {
+    PPP_CUDA(cudaMemcpyAsync(out, o_d, nq * 5 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nn0) PPP_CUDA(cudaMemcpyAsync(nn0, nn0_d, nq * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, (char*)q_d); dev_free(ctx, (char*)n_d); dev_free(ctx, o_d); dev_free(ctx, idx_d); dev_free(ctx, nn0_d);
+  if (st != PPP_OK) return st;
+  PPP_CUDA(e);
+  return PPP_OK;
+}
+
 }  // extern "C"

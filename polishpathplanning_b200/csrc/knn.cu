@@ -739,6 +739,88 @@ __global__ void __launch_bounds__(128) k_radius_count(SearchParams P, int32_t* _
   if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_count, m);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// "next" row 1 of SURVEY.md §8f: principal curvatures at arbitrary query points, the device side
+// of compute_transform (src/Path_Generation.cpp:362-400, k = 10;
+// src/Path_Alg/path_dynamic_alg.cpp:77-110, k = 50): kNN of the query (done by the search
+// kernels into idx), then pcl::PrincipalCurvaturesEstimation::computePointPrincipalCurvatures
+// [upstream, recalled] with neighbour [0] as the centre.  One thread per query.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_principal_curvatures(const int32_t* __restrict__ idx, int64_t nq, int k,
+                                                              const float* __restrict__ normals, int nsf,
+                                                              float* __restrict__ out, int32_t* __restrict__ nn0) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nq) return;
+  const int32_t* nb = idx + t * (int64_t)k;
+  float* o = out + 5 * t;
+  int m = 0;
+  while (m < k && nb[m] >= 0) m++;
+  if (m == 0) {
+    for (int i = 0; i < 5; i++) o[i] = CUDART_NAN_F;
+    if (nn0) nn0[t] = -1;
+    return;
+  }
+  if (nn0) nn0[t] = nb[0];
+  const float* n0 = normals + (int64_t)nb[0] * nsf;
+  const float a0 = __ldg(n0), a1 = __ldg(n0 + 1), a2 = __ldg(n0 + 2);
+  float M[9];
+  const float nn[3] = {a0, a1, a2};
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) M[3 * i + j] = __fsub_rn(i == j ? 1.0f : 0.0f, __fmul_rn(nn[i], nn[j]));
+  auto project = [&](int j, float p[3]) {
+    const float* nj = normals + (int64_t)nb[j] * nsf;
+    const float b0 = __ldg(nj), b1 = __ldg(nj + 1), b2 = __ldg(nj + 2);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      p[i] = __fadd_rn(__fmul_rn(M[3 * i], b0), __fadd_rn(__fmul_rn(M[3 * i + 1], b1), __fmul_rn(M[3 * i + 2], b2)));
+  };
+  float cen[3] = {0.f, 0.f, 0.f};
+  for (int j = 0; j < m; j++) {
+    float p[3];
+    project(j, p);
+    cen[0] = __fadd_rn(cen[0], p[0]); cen[1] = __fadd_rn(cen[1], p[1]); cen[2] = __fadd_rn(cen[2], p[2]);
+  }
+  const float fm = (float)m;
+  cen[0] = __fdiv_rn(cen[0], fm); cen[1] = __fdiv_rn(cen[1], fm); cen[2] = __fdiv_rn(cen[2], fm);
+  float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
+  for (int j = 0; j < m; j++) {
+    float p[3];
+    project(j, p);
+    float d0 = __fsub_rn(p[0], cen[0]), d1 = __fsub_rn(p[1], cen[1]), d2 = __fsub_rn(p[2], cen[2]);
+    c00 = __fadd_rn(c00, __fmul_rn(d0, d0)); c01 = __fadd_rn(c01, __fmul_rn(d0, d1)); c02 = __fadd_rn(c02, __fmul_rn(d0, d2));
+    c11 = __fadd_rn(c11, __fmul_rn(d1, d1)); c12 = __fadd_rn(c12, __fmul_rn(d1, d2)); c22 = __fadd_rn(c22, __fmul_rn(d2, d2));
+  }
+  // eigen33 (values): scale, roots of the scaled matrix, rescale
+  float scale = fmaxf(fmaxf(fmaxf(fabsf(c00), fabsf(c01)), fmaxf(fabsf(c02), fabsf(c11))), fmaxf(fabsf(c12), fabsf(c22)));
+  if (scale <= 1.17549435e-38f) scale = 1.0f;
+  float ev[3];
+  compute_roots(__fdiv_rn(c00, scale), __fdiv_rn(c01, scale), __fdiv_rn(c02, scale), __fdiv_rn(c11, scale),
+                __fdiv_rn(c12, scale), __fdiv_rn(c22, scale), ev);
+  ev[0] = __fmul_rn(ev[0], scale); ev[1] = __fmul_rn(ev[1], scale); ev[2] = __fmul_rn(ev[2], scale);
+  // computeCorrespondingEigenVector for the largest eigenvalue
+  const float e = __fdiv_rn(ev[2], scale);
+  const float s00 = __fsub_rn(__fdiv_rn(c00, scale), e), s11 = __fsub_rn(__fdiv_rn(c11, scale), e),
+              s22 = __fsub_rn(__fdiv_rn(c22, scale), e);
+  const float s01 = __fdiv_rn(c01, scale), s02 = __fdiv_rn(c02, scale), s12 = __fdiv_rn(c12, scale);
+  float v1[3], v2[3], v3[3];
+  cross3(s00, s01, s02, s01, s11, s12, v1);
+  cross3(s00, s01, s02, s02, s12, s22, v2);
+  cross3(s01, s11, s12, s02, s12, s22, v3);
+  float l1 = sqnorm3(v1), l2 = sqnorm3(v2), l3 = sqnorm3(v3);
+  float vx, vy, vz, l;
+  if (l1 >= l2 && l1 >= l3) { vx = v1[0]; vy = v1[1]; vz = v1[2]; l = l1; }
+  else if (l2 >= l1 && l2 >= l3) { vx = v2[0]; vy = v2[1]; vz = v2[2]; l = l2; }
+  else { vx = v3[0]; vy = v3[1]; vz = v3[2]; l = l3; }
+  const float sl = __fsqrt_rn(l);
+  const float inv = __fdiv_rn(1.0f, fm);
+  o[0] = __fdiv_rn(vx, sl); o[1] = __fdiv_rn(vy, sl); o[2] = __fdiv_rn(vz, sl);
+  o[3] = __fmul_rn(ev[2], inv);
+  o[4] = __fmul_rn(ev[1], inv);
+}
+
 // compute_coverage (src/Path_Generation.cpp:483-496): every point within `radius` of a query gets
 // its coverage flag set.  No ordering is needed, so candidates are marked as they are scanned.
 __global__ void __launch_bounds__(128) k_coverage_mark(SearchParams P, unsigned char* __restrict__ flags) {
@@ -1007,6 +1089,17 @@ int coverage_mark_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, 
   P.mode = 1; P.r2 = r2; P.R0 = radius_rings(gs.v, std::sqrt((double)r2));
   unsigned blocks = (unsigned)((nq + 127) / 128);
   PPP_LAUNCH(ctx, "coverage_mark", k_coverage_mark, blocks, 128, 0, P, flags_dev);
+  PPP_CHECK_LAUNCH();
+  return PPP_OK;
+}
+
+int principal_curvatures_launch(ppp_cloud* c, const int32_t* idx_dev, int64_t nq, int k, const float* normals_dev,
+                                int normal_stride_f, float* out_dev, int32_t* nn0_dev) {
+  ppp_ctx* ctx = c->ctx;
+  if (nq <= 0) return PPP_OK;
+  unsigned blocks = (unsigned)((nq + 127) / 128);
+  PPP_LAUNCH(ctx, "principal_curvatures", k_principal_curvatures, blocks, 128, 0, idx_dev, nq, k, normals_dev,
+             normal_stride_f, out_dev, nn0_dev);
   PPP_CHECK_LAUNCH();
   return PPP_OK;
 }

@@ -194,6 +194,8 @@ int radius_fill_launch(ppp_cloud* c, const GridStore& g, const float* q_dev, int
 int normals_radius_launch(ppp_cloud* c, const GridStore& g, int64_t first, int64_t count, float r2,
                           const float vp[3], unsigned flags, float* normals_dev, int normal_stride_f);
 
+int principal_curvatures_launch(ppp_cloud* c, const int32_t* idx_dev, int64_t nq, int k, const float* normals_dev,
+                                int normal_stride_f, float* out_dev, int32_t* nn0_dev);
 int coverage_mark_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq, int q_stride_f, float r2,
                          unsigned char* flags_dev);
 

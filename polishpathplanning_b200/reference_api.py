@@ -202,6 +202,20 @@ class _Base:
         idx, _ = self._dev().knn(1, queries=np.ascontiguousarray(pts), want_d2=False)
         return idx[:, 0]
 
+    def compute_transform(self, points, k=10):
+        """Batched compute_transform (src/Path_Generation.cpp:362-400; k = 50 in the gen-3 planner):
+        returns (pt2Base matrices (n,4,4) float32, principle_curvature (n,2))."""
+        pts = np.ascontiguousarray(np.asarray(points, np.float32).reshape(-1, 3))
+        out, nn0 = self._dev().principal_curvatures(self.cloud_with_normals, pts, k)
+        nrm = self.cloud_with_normals[nn0, 0:3]
+        cur = out[:, 0:3]
+        # Eigen cross: normalVector.cross(curvatureVector), float32
+        cr = np.stack([nrm[:, 1] * cur[:, 2] - nrm[:, 2] * cur[:, 1], nrm[:, 2] * cur[:, 0] - nrm[:, 0] * cur[:, 2],
+                       nrm[:, 0] * cur[:, 1] - nrm[:, 1] * cur[:, 0]], axis=1).astype(np.float32)
+        Y = np.zeros((pts.shape[0], 4, 4), np.float32)
+        Y[:, :3, 0], Y[:, :3, 1], Y[:, :3, 2], Y[:, :3, 3], Y[:, 3, 3] = cr, cur, nrm, pts, 1.0
+        return Y, out[:, 3:5]
+
     def compute_coverage(self, nodes, radius):
         """compute_coverage for a batch of nodes (src/Path_Generation.cpp:483-496)."""
         if not hasattr(self, "coverage_flag") or self.coverage_flag.shape[0] != self.cloud.shape[0]:

@@ -398,3 +398,24 @@ def test_next_rows_drawpath_and_coverage(ctx):
     oflags = oc.coverage_mark(pts[5::10].astype(np.float32), 3.0, oflags)
     assert np.array_equal(flags2, oflags)
     assert abs(pg.get_coverage() - float(oflags.mean())) < 1e-6
+
+
+@pytest.mark.parametrize("k", [10, 50])
+def test_next_row_principal_curvatures(ctx, k):
+    """compute_transform's kNN + computePointPrincipalCurvatures for a batch of spline points."""
+    c = synth.panel(40000, 52)
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    nrm = gc.normals_radius(2.5)
+    rng = np.random.default_rng(2)
+    q = c[rng.integers(0, c.shape[0], 400), :3] + rng.normal(0, 0.3, (400, 3)).astype(np.float32)
+    out, nn0 = gc.principal_curvatures(nrm, q, k)
+    oout, onn0 = oc.principal_curvatures(nrm, q, k)   # same normals in: isolates the curvature arithmetic
+    assert np.array_equal(nn0, onn0)
+    ok = ~np.isnan(oout).any(axis=1) & ~np.isnan(nrm[onn0, 0])
+    # eigenvector sign is a property of the cross products and identical; values agree to float rounding
+    assert np.abs(out[ok, 3:5] - oout[ok, 3:5]).max() <= 1e-6
+    well = ok & (oout[:, 3] > 1.5 * oout[:, 4])          # distinct principal curvatures: direction is well defined
+    assert np.abs(out[well, 0:3] - oout[well, 0:3]).max() <= 1e-4
+    assert np.array_equal(np.isnan(out).any(axis=1), np.isnan(oout).any(axis=1))
+    gc.close()
