@@ -411,7 +411,8 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
 // (measured: well under 0.1 % of the queries), so every delivered list is in the exact
 // (d2, index) order.
 // ---------------------------------------------------------------------------------------------
-constexpr int C_SLOTS = 32;
+constexpr int C_SLOTS = 32;   // keys ordered per network pass
+constexpr int C_STORE = 36;   // storage slots: U spare ones, so a pass is only forced beyond 32 occupied
 
 __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
   extern __shared__ u64 s_keys[];
@@ -573,6 +574,126 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
     }
     store_normal(P.normals, row, P.nsf, o);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-radius normals (NormalEstimation::setRadiusSearch, the reference's default r = 2.5) with
+// the same composite-key idea: every candidate with d2 < r2 is parked in one of 32 slots, ONE
+// 32-input network on 32-bit composite keys orders them at the end, and the covariance is
+// accumulated by walking the sorted slots.  A query with more than 32 - U neighbours, or with two
+// neighbours whose d2 agree in the upper 27 bits, goes to the generic kernel (exact for any count).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 6) k_radius_normals32(SearchParams P) {
+  extern __shared__ u64 s_keys[];
+  constexpr int BD = 128;
+  constexpr int U = 4;
+  const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
+  const GridView& g = P.g;
+  const bool valid = t < P.nq;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  int64_t row = 0;
+  if (valid) {
+    float4 p = __ldg(g.sorted + P.first + t);
+    qx = p.x; qy = p.y; qz = p.z;
+    row = __float_as_int(p.w);
+  }
+  const bool act = valid && g.n_sorted > 0;  // self queries are finite by construction
+  u64* store = s_keys + threadIdx.x;
+  const int R = P.R0;
+  int cu = 0, cv = 0;
+  u64 tau = 0;
+  if (act) {
+    cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
+    cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
+    tau = make_key(P.r2, 0);
+  }
+  int ns = 0;
+  bool overflow = false;
+#pragma unroll 1
+  for (int dv = -R; dv <= R; dv++) {
+    int s = 0, e = 0;
+    int v = cv + dv;
+    if (act && v >= 0 && v < g.nv) {
+      int a = max(cu - R, 0), b = min(cu + R, g.nu - 1);
+      if (a <= b) {
+        const int32_t* rowp = g.cell_start + (int64_t)v * g.nu;
+        s = __ldg(rowp + a);
+        e = __ldg(rowp + b + 1);
+      }
+    }
+    const int n_it = (__reduce_max_sync(0xffffffffu, e - s) + U - 1) / U;
+#pragma unroll 1
+    for (int it = 0; it < n_it; it++) {
+      float4 c4[U];
+      bool in[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        int i = s + it * U + u;
+        in[u] = i < e;
+        c4[u] = __ldg(g.sorted + (in[u] ? i : 0));
+      }
+      u64* wptr = store + ns * BD;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        float d2 = d2_flann(qx, qy, qz, c4[u].x, c4[u].y, c4[u].z);
+        u64 key = make_key(d2, __float_as_int(c4[u].w));
+        if (in[u] && key < tau) {
+          *wptr = key;
+          wptr += BD;
+        }
+      }
+      ns = (int)(wptr - store) / BD;
+      if (ns > C_STORE - U) { overflow = true; tau = 0; }  // no room for another U candidates: hand over
+    }
+  }
+  if (!valid) return;
+  unsigned c[C_SLOTS];
+#pragma unroll
+  for (int i = 0; i < C_SLOTS; i++) {
+    unsigned hi = (unsigned)(store[i * BD] >> 32);
+    c[i] = i < ns ? ((hi & 0xFFFFFFE0u) | (unsigned)i) : 0xFFFFFFFFu;
+  }
+  SortNetU32<C_SLOTS>::sort(c);
+  bool ambiguous = false;
+#pragma unroll
+  for (int i = 0; i + 1 < C_SLOTS; i++) ambiguous |= (i + 1 < ns) && ((c[i] ^ c[i + 1]) < 32u);
+  if (overflow || ns > C_SLOTS || ambiguous) {
+    int slot = atomicAdd(P.redo_count, 1);
+    P.redo_list[slot] = (int32_t)t;
+    return;
+  }
+  float o[4];
+  const int m = ns;
+  if (!act || m < 3) {
+    o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
+  } else {
+    float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
+    float kx = 0.f, ky = 0.f, kz = 0.f;
+    if (shifted) {
+      float4 f = __ldg(P.xyz4 + key_idx(store[(c[0] & 31u) * BD]));
+      kx = f.x; ky = f.y; kz = f.z;
+    }
+#pragma unroll
+    for (int jb = 0; jb < C_SLOTS; jb += 4) {
+      if (jb < m) {
+        float4 a[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (jb + u < m) a[u] = __ldg(P.xyz4 + key_idx(store[(c[jb + u] & 31u) * BD]));
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (jb + u < m) {
+            float x = a[u].x, y = a[u].y, z = a[u].z;
+            if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
+            accumulate_point(acc, x, y, z);
+          }
+        }
+      }
+    }
+    normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
+  }
+  store_normal(P.normals, row, P.nsf, o);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1052,7 +1173,15 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int6
   if (fast) {
     PPP_TRY(prepare_fast(c, P, &redo));
     P.cap = 32;
-    PPP_TRY((launch_knn_fast_k<32, 16, true>(c, P)));
+    if (getenv("PPP_KNN_V4")) {
+      PPP_TRY((launch_knn_fast_k<32, 16, true>(c, P)));
+    } else {
+      size_t smem = (size_t)C_STORE * 8 * 128;
+      PPP_CUDA(cudaFuncSetAttribute(k_radius_normals32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      unsigned blocks = (unsigned)((P.nq + 127) / 128);
+      PPP_LAUNCH(ctx, "radius_normals", k_radius_normals32, blocks, 128, smem, P);
+      PPP_CHECK_LAUNCH();
+    }
     PPP_CUDA(cudaMemcpyAsync(&n_redo, redo, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PPP_CUDA(cudaStreamSynchronize(ctx->stream));
     if (n_redo == 0) { dev_free(ctx, redo); return PPP_OK; }
