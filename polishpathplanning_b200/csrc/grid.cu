@@ -6,6 +6,8 @@
 // histogram (atomics) -> exclusive scan -> scatter.  Rows of cells are contiguous in the sorted
 // array, so a query's candidates are (2R+1) contiguous ranges that consecutive (sorted) queries
 // share: coalesced float4 loads, L1/L2 reuse, no tree walk.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cmath>
 
@@ -185,7 +187,9 @@ double cloud_cell_for_k(const ppp_cloud* c, int k) {
   if (c->cell_hint > 0) return c->cell_hint;
   double rho = c->density > 0 ? c->density : 1.0;
   double rk = std::sqrt((double)std::max(k, 1) / (3.14159265358979 * rho));
-  return 1.35 * rk / 2.0;
+  double f = 1.35;
+  if (const char* e = getenv("PPP_CELL_FACTOR")) { double v = atof(e); if (v > 0.5 && v < 4.0) f = v; }  // tuning aid
+  return f * rk / 2.0;
 }
 // Cell size for a radius search: R = 2 rings cover r exactly (plus rounding slack).
 double cloud_cell_for_radius(const ppp_cloud* c, double r) {
