@@ -419,3 +419,32 @@ def test_next_row_principal_curvatures(ctx, k):
     assert np.abs(out[well, 0:3] - oout[well, 0:3]).max() <= 1e-4
     assert np.array_equal(np.isnan(out).any(axis=1), np.isnan(oout).any(axis=1))
     gc.close()
+
+
+def test_two_host_threads_share_a_cloud(ctx):
+    """The reference's gen-3 sweep queries one kd-tree from two threads
+    (src/Path_Alg/path_dynamic_alg.cpp:308-334): concurrent calls on one handle must be safe."""
+    import threading
+    c = synth.panel(30000, 61)
+    gc = api.Cloud(ctx, c)
+    rng = np.random.default_rng(4)
+    qs = [c[rng.integers(0, c.shape[0], 300), :3] + np.float32(0.1) for _ in range(2)]
+    want = [gc.knn(3, queries=q)[0] for q in qs]
+    planes = synth.even_planes(c, 5)
+    want_c = gc.slice_contours(planes, "B")
+    errs = []
+
+    def worker(i):
+        try:
+            for _ in range(15):
+                assert np.array_equal(gc.knn(3, queries=qs[i])[0], want[i])
+                o = gc.slice_contours(planes, "B")
+                assert np.array_equal(o[1], want_c[1])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    gc.close()
