@@ -448,3 +448,42 @@ def test_two_host_threads_share_a_cloud(ctx):
     [t.join() for t in th]
     assert not errs, errs
     gc.close()
+
+
+def test_cfg3_shape_10m_points_k32_1000_slices(ctx):
+    """BASELINE.json configs[2] shape on one GPU: 10M points, k = 32 normals, 1000 slices.
+    Sampled exactness against the oracle plus size-independent properties."""
+    n = 10_000_000
+    c = synth.panel(n, 0)
+    gc = api.Cloud(ctx, c)
+    nrm, idx = gc.normals_knn(32, return_idx=True, stride_floats=4)
+    assert np.all(idx[:, 0] == np.arange(n))
+    assert idx.min() >= 0 and idx.max() < n
+    # At ~3000 mm PCL 1.10's single-pass float32 covariance is mostly rounding noise (SURVEY §7.3): a
+    # few neighbourhoods come out exactly rank-deficient and PCL's eigen33 then yields NaN.  That is
+    # the reference's behaviour; it must be reproduced, not "fixed".
+    ok = ~np.isnan(nrm[:, 0])
+    assert ok.mean() > 0.99
+    assert np.all(np.abs(np.linalg.norm(nrm[ok, :3], axis=1) - 1) < 1e-5)
+    oc = po.OracleCloud(c)
+    sub = np.arange(0, n, 9973)
+    oi, _ = oc.knn(32, queries=c[sub][:, :3].copy())
+    assert np.array_equal(idx[sub], oi)
+    # normals of sampled rows (and of every NaN row among the first million) from the oracle's formula
+    rows = np.concatenate([sub[::50], np.nonzero(~ok[:1_000_000])[0][:200]])
+    for i in rows:
+        o = po.normal_from_list(c, idx[i], c[i, :3])
+        assert np.array_equal(np.isnan(o), np.isnan(nrm[i]))
+        if not np.isnan(o[0]):
+            assert np.abs(o - nrm[i]).max() <= 1e-5
+    planes = synth.even_planes(c, 1000)
+    noff, y, x, z = gc.slice_contours(planes, "B")
+    assert noff[-1] > 0 and np.all(np.diff(noff) > 100)
+    for s in (0, 499, 999):
+        ys = y[noff[s]:noff[s + 1]]
+        assert np.all(np.diff(ys) > 0)
+    o = oc.slice_contours(planes[[17, 640]], "B")
+    for j, s in enumerate((17, 640)):
+        assert np.array_equal(y[noff[s]:noff[s + 1]], o[1][o[0][j]:o[0][j + 1]])
+        assert np.array_equal(z[noff[s]:noff[s + 1]], o[3][o[0][j]:o[0][j + 1]])
+    gc.close()
