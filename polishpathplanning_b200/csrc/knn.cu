@@ -823,6 +823,78 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
   }  // slot loop
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fixed-radius normals, one WARP per query: hand-over path of k_radius_normals32 (queries with
+// more than 32 neighbours or a near-tie).  Lanes stride over the candidates of the (2R0+1)^2
+// block, each keeping its in-radius keys sorted in a small shared-memory list; the lists are then
+// merged by repeated warp-wide 64-bit min, and every lane accumulates the covariance in that
+// (d2, index) order.  Queries whose neighbours overflow a lane list (hundreds of neighbours) are
+// passed on to the generic kernel through redo2.
+// ---------------------------------------------------------------------------------------------
+constexpr int RW_CAPL = 16;  // keys per lane: up to 512 neighbours per query if evenly spread
+
+__global__ void __launch_bounds__(WARPQ_WARPS * 32) k_radius_warp(SearchParams P, int32_t* __restrict__ redo2_count,
+                                                                  int32_t* __restrict__ redo2_list) {
+  __shared__ u64 s_l[WARPQ_WARPS * 32 * RW_CAPL];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const GridView& g = P.g;
+  u64* L = s_l + (size_t)w * 32 * RW_CAPL + lane;
+  const int n_redo = *P.redo_count;
+  const u64 tau = make_key(P.r2, 0);
+  for (int64_t slot = (int64_t)blockIdx.x * WARPQ_WARPS + w; slot < n_redo; slot += (int64_t)gridDim.x * WARPQ_WARPS) {
+    const int64_t t = P.redo_list[slot];
+    float4 p = __ldg(g.sorted + P.first + t);
+    const float qx = p.x, qy = p.y, qz = p.z;
+    const int64_t row = __float_as_int(p.w);
+    const int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
+    const int cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
+    const int R = P.R0;
+    int cnt = 0;
+    bool over = false;
+    const int v0 = max(cv - R, 0), v1 = min(cv + R, g.nv - 1);
+    for (int v = v0; v <= v1; v++) {
+      const int32_t* rowp = g.cell_start + (int64_t)v * g.nu;
+      int a = max(cu - R, 0), b = min(cu + R, g.nu - 1);
+      if (a > b) continue;
+      const int s = __ldg(rowp + a), e = __ldg(rowp + b + 1);
+      for (int i = s + lane; i < e; i += 32) {
+        float4 c = __ldg(g.sorted + i);
+        u64 key = make_key(d2_flann(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+        if (key < tau) {
+          if (cnt == RW_CAPL) over = true;
+          else list_insert(L, 32, cnt, RW_CAPL, key);
+        }
+      }
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, over)) {
+      if (lane == 0) redo2_list[atomicAdd(redo2_count, 1)] = (int32_t)t;
+      continue;
+    }
+    float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
+    float kx = 0.f, ky = 0.f, kz = 0.f;
+    int head = 0, m = 0;
+    while (true) {
+      u64 h = head < cnt ? L[head * 32] : PPP_KEY_INF;
+      u64 mn = warp_min_u64(h);
+      if (mn == PPP_KEY_INF) break;
+      if (h == mn) head++;
+      float4 a = __ldg(P.xyz4 + key_idx(mn));
+      if (shifted && m == 0) { kx = a.x; ky = a.y; kz = a.z; }
+      float x = a.x, y = a.y, z = a.z;
+      if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
+      accumulate_point(acc, x, y, z);
+      m++;
+    }
+    float o[4];
+    if (m < 3) o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
+    else normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
+    if (lane == 0) store_normal(P.normals, row, P.nsf, o);
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(128) k_radius_count(SearchParams P, int32_t* __restrict__ counts, int32_t* __restrict__ max_count) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int cnt = 0;
@@ -1182,9 +1254,23 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int6
       PPP_LAUNCH(ctx, "radius_normals", k_radius_normals32, blocks, 128, smem, P);
       PPP_CHECK_LAUNCH();
     }
-    PPP_CUDA(cudaMemcpyAsync(&n_redo, redo, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    // hand-over queries: one warp each (persistent warps); what even that cannot hold goes on to the
+    // generic kernel through a second list
+    int32_t* redo2 = nullptr;
+    PPP_TRY(dev_alloc(ctx, &redo2, (size_t)P.nq + 1));
+    PPP_CUDA(cudaMemsetAsync(redo2, 0, sizeof(int32_t), ctx->stream));
+    {
+      unsigned blocks = (unsigned)std::min<int64_t>((P.nq + WARPQ_WARPS - 1) / WARPQ_WARPS, (int64_t)ctx->sm_count * 8);
+      PPP_LAUNCH(ctx, "radius_redo", k_radius_warp, blocks, WARPQ_WARPS * 32, 0, P, redo2, redo2 + 1);
+      PPP_CHECK_LAUNCH();
+    }
+    PPP_CUDA(cudaMemcpyAsync(&n_redo, redo2, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, redo);
+    redo = redo2;
     if (n_redo == 0) { dev_free(ctx, redo); return PPP_OK; }
+    P.redo_count = redo2;
+    P.redo_list = redo2 + 1;
     P.use_redo = 1;
   }
   // generic path: all queries, or only the ones the fast kernel handed over
