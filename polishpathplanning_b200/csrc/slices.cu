@@ -135,7 +135,7 @@ __device__ void cta_sort(T* a, int n) {
   }
 }
 
-__global__ void __launch_bounds__(CT_THREADS) k_band_sort(const int64_t* __restrict__ offsets, int32_t* __restrict__ idx, int smem_cap) {
+__global__ void __launch_bounds__(1024) k_band_sort(const int64_t* __restrict__ offsets, int32_t* __restrict__ idx, int smem_cap) {
   extern __shared__ int32_t s_idx[];
   int s = blockIdx.x;
   int64_t o = offsets[s];
@@ -281,90 +281,101 @@ __device__ __forceinline__ int lower_pos(const int32_t* a, int n, int v) {
   return l;
 }
 
-__global__ void __launch_bounds__(CT_THREADS) k_contour(ContourParams P) {
+// gen-2 pairing (variant A).  CTA per slice.  The index lists, nearest-neighbour positions, flags
+// and sort keys of a slice live in shared memory when they fit (9 bytes per band member), so the
+// order-dependent greedy flag pass — one thread replaying src/Path_Generation.cpp:137-179 — runs
+// at shared-memory latency; larger bands use the global scratch arrays with the same code.
+__global__ void __launch_bounds__(1024) k_contour(ContourParams P, int smem_cap) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ int s_warp[32];
-  __shared__ int s_npairs;
+  __shared__ int s_npairs, s_nl, s_nr;
   const int s = blockIdx.x;
   const int64_t o = P.band_off[s];
   const int B = (int)(P.band_off[s + 1] - o);
   const float plane = P.planes[s], lo = P.lo[s], hi = P.hi[s];
   const int32_t* band = P.band_idx + o;
-  int32_t* El = P.El + o;
-  int32_t* Er = P.Er + o;
+  const int Bp = (B + 1) & ~1;
+  const bool in_smem = B <= smem_cap;
+  int32_t* ids = in_smem ? reinterpret_cast<int32_t*>(s_dyn) : P.El + o;          // El then Er
+  int32_t* pos = in_smem ? reinterpret_cast<int32_t*>(s_dyn) + Bp : P.posR + o;   // posR then posL
+  unsigned char* flg = in_smem ? s_dyn + 8 * (size_t)Bp : P.fl + o;               // fl then fr
+  u64* keys = in_smem ? reinterpret_cast<u64*>(s_dyn + 4 * (size_t)Bp) : P.keys + o;  // aliases pos after the greedy pass
   // ---- classify: El (x > plane), Er (x < plane), order preserved; x == plane dropped ----
-  int nL = 0, nR = 0;
-  for (int base = 0; base < B; base += CT_THREADS) {
-    int i = base + threadIdx.x;
-    int idx = -1;
-    bool isL = false, isR = false;
-    if (i < B) {
-      idx = band[i];
-      float x = __ldg(&P.xyz4[idx].x);
-      // (point - PlanePoint).dot((1,0,0)): sign of (x - plane) for finite points
-      float d = __fsub_rn(x, plane);
-      isL = d > 0.0f;
-      isR = d < 0.0f;
+  if (threadIdx.x == 0) { s_nl = 0; s_nr = 0; }
+  __syncthreads();
+  {
+    int cl = 0, cr = 0;
+    for (int i = threadIdx.x; i < B; i += (int)blockDim.x) {
+      float d = __fsub_rn(__ldg(&P.xyz4[band[i]].x), plane);  // (point - PlanePoint).dot((1,0,0))
+      cl += d > 0.0f;
+      cr += d < 0.0f;
     }
-    int rl = cta_flag_rank(isL, s_warp, nL);
-    int rr = cta_flag_rank(isR, s_warp, nR);
-    if (isL) El[rl] = idx;
-    if (isR) Er[rr] = idx;
+    if (cl) atomicAdd(&s_nl, cl);
+    if (cr) atomicAdd(&s_nr, cr);
+  }
+  __syncthreads();
+  const int nL = s_nl, nR = s_nr;
+  int32_t* El = ids;
+  int32_t* Er = ids + nL;
+  int32_t* posR = pos;
+  int32_t* posL = pos + nL;
+  unsigned char* fl = flg;
+  unsigned char* fr = flg + nL;
+  {
+    int rl_run = 0, rr_run = 0;
+    for (int base = 0; base < B; base += (int)blockDim.x) {
+      int i = base + threadIdx.x;
+      int idx = -1;
+      bool isL = false, isR = false;
+      if (i < B) {
+        idx = band[i];
+        float d = __fsub_rn(__ldg(&P.xyz4[idx].x), plane);
+        isL = d > 0.0f;
+        isR = d < 0.0f;
+      }
+      int rl = cta_flag_rank(isL, s_warp, rl_run);
+      int rr = cta_flag_rank(isR, s_warp, rr_run);
+      if (isL) El[rl] = idx;
+      if (isR) Er[rr] = idx;
+    }
   }
   __syncthreads();
   int npairs = 0;
   float* ys = P.ys + o;
   float* zs = P.zs + o;
-  u64* keys = P.keys + o;
   if (nL > 0 && nR > 0) {
-    if (P.mode == PPP_PAIR_SECT) {
-      // one pair per left point, no flags (src/contour_alg.cpp:185-211)
-      for (int i = threadIdx.x; i < nL; i += CT_THREADS) {
-        float4 pl = __ldg(P.xyz4 + El[i]);
-        int r = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, Er, nR);
-        float4 pr = __ldg(P.xyz4 + r);
-        int rc = nn_full(P.g, pr.x, pr.y, pr.z, r);
-        int l2 = nn_side(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, El, nL);
-        float4 pl2 = __ldg(P.xyz4 + l2);
-        int lc = nn_full(P.g, pl2.x, pl2.y, pl2.z, l2);
-        P.lp[o + i] = lc;
-        P.rp[o + i] = rc;
-      }
-      npairs = nL;
-      __syncthreads();
-    } else {
-      // gen-2: nearest right of every left, nearest left of every right (flag-independent),
-      // then the order-dependent greedy flag pass replayed by one thread.
-      for (int i = threadIdx.x; i < nL; i += CT_THREADS) {
-        float4 pl = __ldg(P.xyz4 + El[i]);
-        int r = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 1, Er, nR);
-        P.posR[o + i] = lower_pos(Er, nR, r);
-        P.fl[o + i] = 0;
-      }
-      for (int j = threadIdx.x; j < nR; j += CT_THREADS) {
-        float4 pr = __ldg(P.xyz4 + Er[j]);
-        int l = nn_side(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 1, El, nL);
-        P.posL[o + j] = lower_pos(El, nL, l);
-        P.fr[o + j] = 0;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int nl = 0, nr = 0;
-        for (int i = 0; i < nL; i++) {
-          if (P.fl[o + i]) continue;
-          int j = P.posR[o + i];
-          if (P.fr[o + j]) continue;
-          P.rp[o + nr++] = Er[j];
-          P.fr[o + j] = 1;
-          int i2 = P.posL[o + j];
-          if (!P.fl[o + i2]) { P.lp[o + nl++] = El[i2]; P.fl[o + i2] = 1; }
-        }
-        s_npairs = nl;  // interpolation runs over left_pair.size() (src/Path_Generation.cpp:189)
-      }
-      __syncthreads();
-      npairs = s_npairs;
+    // nearest right of every left, nearest left of every right (flag-independent) ...
+    for (int i = threadIdx.x; i < nL; i += (int)blockDim.x) {
+      float4 pl = __ldg(P.xyz4 + El[i]);
+      int r = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 1, Er, nR);
+      posR[i] = lower_pos(Er, nR, r);
+      fl[i] = 0;
     }
+    for (int j = threadIdx.x; j < nR; j += (int)blockDim.x) {
+      float4 pr = __ldg(P.xyz4 + Er[j]);
+      int l = nn_side(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 1, El, nL);
+      posL[j] = lower_pos(El, nL, l);
+      fr[j] = 0;
+    }
+    __syncthreads();
+    // ... then the order-dependent greedy flag pass, replayed by one thread
+    if (threadIdx.x == 0) {
+      int nl = 0, nr = 0;
+      for (int i = 0; i < nL; i++) {
+        if (fl[i]) continue;
+        int j = posR[i];
+        if (fr[j]) continue;
+        P.rp[o + nr++] = Er[j];
+        fr[j] = 1;
+        int i2 = posL[j];
+        if (!fl[i2]) { P.lp[o + nl++] = El[i2]; fl[i2] = 1; }
+      }
+      s_npairs = nl;  // interpolation runs over left_pair.size() (src/Path_Generation.cpp:189)
+    }
+    __syncthreads();
+    npairs = s_npairs;
     // ---- interpolate onto the plane (float32, no FMA) ----
-    for (int i = threadIdx.x; i < npairs; i += CT_THREADS) {
+    for (int i = threadIdx.x; i < npairs; i += (int)blockDim.x) {
       float4 r = __ldg(P.xyz4 + P.rp[o + i]);
       float4 l = __ldg(P.xyz4 + P.lp[o + i]);
       float t = __fdiv_rn(__fsub_rn(plane, r.x), __fsub_rn(l.x, r.x));
@@ -382,7 +393,7 @@ __global__ void __launch_bounds__(CT_THREADS) k_contour(ContourParams P) {
   int nodes = 0;
   double* ty = P.ty + o;
   double* tz = P.tz + o;
-  for (int base = 0; base < npairs; base += CT_THREADS) {
+  for (int base = 0; base < npairs; base += (int)blockDim.x) {
     int i = base + threadIdx.x;
     bool first = false, last = false;
     u64 k = 0;
@@ -650,7 +661,7 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
       int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(maxB, 1), 49152);  // <= 192 KB of int32
       if (smem_cap * 4 > 48 * 1024)
         PPP_CUDA(cudaFuncSetAttribute(k_band_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 4));
-      PPP_LAUNCH(ctx, "band_sort", k_band_sort, (unsigned)S, CT_THREADS, (size_t)smem_cap * 4, (const int64_t*)offsets, idx,
+      PPP_LAUNCH(ctx, "band_sort", k_band_sort, (unsigned)S, 1024, (size_t)smem_cap * 4, (const int64_t*)offsets, idx,
                  smem_cap);
       PPP_CHECK_LAUNCH();
     }
@@ -742,7 +753,12 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     PPP_TRY(dev_alloc(ctx, &P.posR, M)); PPP_TRY(dev_alloc(ctx, &P.posL, M));
     PPP_TRY(dev_alloc(ctx, &P.fl, M)); PPP_TRY(dev_alloc(ctx, &P.fr, M));
     if (S > 0) {
-      PPP_LAUNCH(ctx, "contour_gen2", k_contour, (unsigned)S, CT_THREADS, 0, P);
+      int64_t maxB = 0;
+      for (int s = 0; s < S; s++) maxB = std::max(maxB, band_off_host[s + 1] - band_off_host[s]);
+      int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(maxB, 2), 22000);  // 9 bytes per member, <= 198 KB
+      size_t smem = 9 * (size_t)((smem_cap + 1) & ~1) + 16;
+      if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(k_contour, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PPP_LAUNCH(ctx, "contour_gen2", k_contour, (unsigned)S, 1024, smem, P, smem_cap);
       PPP_CHECK_LAUNCH();
     }
     st = finish_nodes(c, S, band_off_dev, planes_dev, n_nodes, ty, tz, total_nodes_out);

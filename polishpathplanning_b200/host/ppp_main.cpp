@@ -36,6 +36,12 @@ int main(int argc, char** argv) {
       }
       return 0;
     }
+    if (argc >= 3 && !strcmp(argv[1], "--slicing")) {  // the sweep main.cpp:28 leaves commented out
+      path_generater pg(argv[2], 15);
+      pg.slicing_method();
+      if (argc >= 4) dump_contours(argv[3], pg.last_contours());
+      return 0;
+    }
     if (argc < 2) {
       printf("Usage: %s workpiece.pcd [out_prefix] | --sect config.txt workpiece.pcd [out_prefix]\n", argv[0]);
       return -1;

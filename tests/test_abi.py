@@ -55,3 +55,13 @@ def test_argument_validation_without_device():
     assert L.ppp_cloud_size(None) == -1
     assert L.ppp_cloud_free(None) == _lib.PPP_OK
     assert L.ppp_sync(None) == _lib.PPP_ERR_INVALID
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/ppp_gpu.h must be consumable from C (and C++) with nothing but the standard headers."""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "ppp_gpu.h"\nint main(void) { ppp_ctx* c = 0; (void)c; return PPP_OK + PPP_PAIR_SECT - 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, "-fsyntax-only", str(src)])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-x", "c++", "-fsyntax-only", str(src)])

@@ -79,3 +79,22 @@ def test_missing_file_does_not_abort(tmp_path):
     _build()
     r = subprocess.run([EXE, str(tmp_path / "nope.pcd")], capture_output=True, text=True, cwd=str(tmp_path), timeout=120)
     assert r.returncode == 0 and "read file" in r.stderr
+
+
+def test_slicing_method_flow(tmp_path):
+    """path_generater::slicing_method (src/Path_Generation.cpp:282-321): first plane min.x + int(2R)/2."""
+    _build()
+    pcd = str(tmp_path / "workpiece.pcd")
+    synth.write_pcd(pcd, synth.to_pointxyzrgb(synth.panel_metres(50000, 9)))
+    out = str(tmp_path / "sl")
+    r = subprocess.run([EXE, "--slicing", pcd, out], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "number of paths" in r.stdout
+    off = np.fromfile(out + ".off.i64", np.int64)
+    y = np.fromfile(out + ".y.f64", np.float64)
+    z = np.fromfile(out + ".z.f64", np.float64)
+    oc = po.OracleCloud(synth.panel(50000, 9))
+    mn, mx = oc.minmax()
+    planes = po.planes("gen2_slicing", mn[0], mx[0], 15.0)
+    ooff, oy, ox, oz = oc.slice_contours(planes, "A")
+    assert np.array_equal(off, ooff) and np.array_equal(y, oy) and np.array_equal(z, oz)
