@@ -1129,7 +1129,7 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
   int32_t* redo = nullptr;
   PPP_TRY(prepare_fast(c, P, &redo));
   int st;
-  if (P.cap <= 16 && !getenv("PPP_KNN_V4")) {
+  if (P.cap <= 16) {
     const int block = 128;
     size_t smem = (size_t)C_SLOTS * 8 * block;
     PPP_CUDA(cudaFuncSetAttribute(k_knn16c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1138,8 +1138,6 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
     PPP_CHECK_LAUNCH();
     st = PPP_OK;
   }
-  else if (P.cap <= 8) st = launch_knn_fast_k<8, 8, false>(c, P);
-  else if (P.cap <= 16) st = launch_knn_fast_k<16, 16, false>(c, P);
   else if (P.cap <= 32) st = launch_knn_fast_k<32, 16, false>(c, P);
   else st = launch_knn_fast_k<64, 16, false>(c, P);
   if (st == PPP_OK) {
@@ -1245,9 +1243,7 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int6
   if (fast) {
     PPP_TRY(prepare_fast(c, P, &redo));
     P.cap = 32;
-    if (getenv("PPP_KNN_V4")) {
-      PPP_TRY((launch_knn_fast_k<32, 16, true>(c, P)));
-    } else {
+    {
       size_t smem = (size_t)C_STORE * 8 * 128;
       PPP_CUDA(cudaFuncSetAttribute(k_radius_normals32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       unsigned blocks = (unsigned)((P.nq + 127) / 128);

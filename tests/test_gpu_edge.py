@@ -277,10 +277,17 @@ def test_full_size_properties(ctx):
     # idempotence: a second call gives identical bytes
     noff2, y2, _, z2 = gc.slice_contours(planes, "B")
     assert np.array_equal(noff, noff2) and np.array_equal(y, y2) and np.array_equal(z, z2)
-    # three slices against the oracle at full size
-    o = oc.slice_contours(planes[[3, 100, 198]], "B")
-    for j, s in enumerate((3, 100, 198)):
-        assert np.array_equal(y[noff[s]:noff[s + 1]], o[1][o[0][j]:o[0][j + 1]])
+    # ... and the whole cfg2 workload against the oracle: every neighbour list, every normal, every node
+    oi, _ = oc.knn(16, want_d2=False)
+    assert np.array_equal(idx, oi)
+    on, _ = oc.normals(k=16)
+    assert np.array_equal(np.isnan(on[:, 0]), np.isnan(n4[:, 0]))
+    okn = ~np.isnan(on[:, 0])
+    dn = np.abs(n4[okn] - on[okn])
+    print("1M normals: max|diff| = %.3g, bit-identical rows = %.4f" % (dn.max(), (n4[okn] == on[okn]).all(axis=1).mean()))
+    assert dn.max() <= 1e-5
+    ooff, oy, ox, oz = oc.slice_contours(planes, "B")
+    assert np.array_equal(noff, ooff) and np.array_equal(y, oy) and np.array_equal(xx, ox) and np.array_equal(z, oz)
     gc.close()
 
 
