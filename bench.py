@@ -269,17 +269,22 @@ def run_ours(args):
             # transfer (NCCL's own stream) overlaps the band / contour kernels
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(gat["own_recv"], gat["own"])
+        if world > 1 and gather and "nodes" in gat:
+            nb = gat["nodes"]   # rows y, x, z; column 0 = node count: the library writes the nodes in place
+            esz, cap = nb.element_size(), gat["node_cap"]
+            c.dev_set_contour_buffers(nb[0].data_ptr() + esz, nb[1].data_ptr() + esz, nb[2].data_ptr() + esz, cap)
         res = c.dev_slice_contours(planes, PAIRING, HALF_WIDTH, True)
         last["nodes"] = res["total_nodes"]
         last["members"] = res["total_members"]
         if world > 1 and gather:
             # contour nodes (y, x, z) of the owned planes
             tn = res["total_nodes"]
+            had = "nodes" in gat and gat["node_cap"] >= tn
             ensure_node_buffers(tn)
             with torch.cuda.stream(stream):
                 nb = gat["nodes"]
                 nb[:, 0] = float(tn)
-                if tn:
+                if tn and not had:   # first step (or growth): copy from the cloud-owned buffers
                     for j, key in enumerate(("y", "x", "z")):
                         nb[j, 1:tn + 1] = _wrap_f64(torch, res[key], tn, dev)
                 dist.all_gather_into_tensor(gat["nodes_recv"], nb)

@@ -170,6 +170,9 @@ int ppp_dev_slice_contours(ppp_cloud* cloud, const float* plane_x_host, int S, f
                            int truncate_center, int pairing_mode, const int64_t** node_offsets_dev,
                            const double** y_dev, const double** x_dev, const double** z_dev,
                            int64_t* total_nodes, int64_t* total_band_members);
+/* Optional: caller-owned device buffers (cap doubles each) that ppp_dev_slice_contours fills
+ * instead of the cloud-owned ones whenever the node total fits (e.g. an NCCL gather buffer). */
+int ppp_dev_set_contour_buffers(ppp_cloud* cloud, double* y_dev, double* x_dev, double* z_dev, int64_t cap);
 /* original index of the point at sorted position p (device array of n int32) */
 const int32_t* ppp_dev_sorted_order(ppp_cloud* cloud);
 

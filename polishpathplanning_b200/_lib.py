@@ -61,6 +61,7 @@ SIGNATURES = {
     "ppp_dev_normals_radius": (C.c_int, [_vp, C.c_double, _f32p, C.c_uint, C.c_int64, C.c_int64, _vp, C.c_size_t]),
     "ppp_dev_slice_contours": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp),
                                          C.POINTER(_vp), C.POINTER(_vp), _i64p, _i64p]),
+    "ppp_dev_set_contour_buffers": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64]),
     "ppp_dev_sorted_order": (_vp, [_vp]),
 }
 

@@ -277,6 +277,10 @@ class Cloud:
         check(self.lib.ppp_dev_normals_radius(self._h, float(r), vp.ctypes.data_as(_lib._f32p), flags, int(first),
                                               int(count), _vp(normals_ptr), int(normal_stride_bytes)))
 
+    def dev_set_contour_buffers(self, y_ptr, x_ptr, z_ptr, cap):
+        check(self.lib.ppp_dev_set_contour_buffers(self._h, _vp(y_ptr) if y_ptr else None, _vp(x_ptr) if x_ptr else None,
+                                                   _vp(z_ptr) if z_ptr else None, int(cap)))
+
     def dev_slice_contours(self, planes, mode, half_width=2.0, truncate_center=True):
         """Returns dict(node_offsets=ptr, y=ptr, x=ptr, z=ptr, total_nodes, total_members); buffers are
         owned by the cloud and valid until the next call."""

@@ -241,6 +241,13 @@ int ppp_cloud_set_cell_hint(ppp_cloud* c, float cell) {
   return PPP_OK;
 }
 
+int ppp_dev_set_contour_buffers(ppp_cloud* c, double* y_dev, double* x_dev, double* z_dev, int64_t cap) {
+  REQUIRE(c, "cloud is NULL");
+  REQUIRE((y_dev && x_dev && z_dev && cap > 0) || (!y_dev && !x_dev && !z_dev), "give all three buffers or none");
+  c->ext_y = y_dev; c->ext_x = x_dev; c->ext_z = z_dev; c->ext_cap = y_dev ? cap : 0;
+  return PPP_OK;
+}
+
 const int32_t* ppp_dev_sorted_order(ppp_cloud* c) {
   if (!c || c->grids.empty()) return nullptr;
   return c->grids.back().order;
@@ -322,9 +329,9 @@ int ppp_dev_slice_contours(ppp_cloud* c, const float* plane_x_host, int S, float
   }
   if (st != PPP_OK) return st;
   if (node_offsets_dev) *node_offsets_dev = c->c_node_off;
-  if (y_dev) *y_dev = c->c_y;
-  if (x_dev) *x_dev = c->c_x;
-  if (z_dev) *z_dev = c->c_z;
+  if (y_dev) *y_dev = c->out_y;
+  if (x_dev) *x_dev = c->out_x;
+  if (z_dev) *z_dev = c->out_z;
   if (total_nodes) *total_nodes = total;
   if (total_members) *total_members = M;
   return PPP_OK;

@@ -122,6 +122,9 @@ struct ppp_cloud {
   double *c_y = nullptr, *c_x = nullptr, *c_z = nullptr;
   int64_t c_cap = 0;
   int c_S_cap = 0;
+  double *ext_y = nullptr, *ext_x = nullptr, *ext_z = nullptr;  // optional caller-owned node buffers
+  int64_t ext_cap = 0;
+  double *out_y = nullptr, *out_x = nullptr, *out_z = nullptr;  // where the last call wrote the nodes
 };
 
 // ---------------------------------------------------------------------------------------------

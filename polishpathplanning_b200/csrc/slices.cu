@@ -688,15 +688,21 @@ static int finish_nodes(ppp_cloud* c, int S, const int64_t* band_off_dev, const 
   int64_t total = 0;
   PPP_CUDA(cudaMemcpyAsync(&total, c->c_node_off + S, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   PPP_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (c->c_cap < total || !c->c_y) {
+  // caller-provided device buffers (ppp_dev_set_contour_buffers) take the nodes when they are large
+  // enough; otherwise the cloud-owned buffers are (re)allocated
+  const bool ext = c->ext_y && c->ext_cap >= total;
+  if (!ext && (c->c_cap < total || !c->c_y)) {
     dev_free(ctx, c->c_y); dev_free(ctx, c->c_x); dev_free(ctx, c->c_z);
     size_t cap = (size_t)std::max<int64_t>(total, 1);
     PPP_TRY(dev_alloc(ctx, &c->c_y, cap)); PPP_TRY(dev_alloc(ctx, &c->c_x, cap)); PPP_TRY(dev_alloc(ctx, &c->c_z, cap));
     c->c_cap = (int64_t)cap;
   }
+  c->out_y = ext ? c->ext_y : c->c_y;
+  c->out_x = ext ? c->ext_x : c->c_x;
+  c->out_z = ext ? c->ext_z : c->c_z;
   if (total > 0) {
     PPP_LAUNCH(ctx, "compact_nodes", k_compact_nodes, (unsigned)S, 256, 0, band_off_dev, (const int64_t*)c->c_node_off,
-               planes_dev, ty, tz, c->c_y, c->c_x, c->c_z);
+               planes_dev, ty, tz, c->out_y, c->out_x, c->out_z);
     PPP_CHECK_LAUNCH();
   }
   *total_nodes_out = total;
