@@ -128,6 +128,13 @@ int ppp_slice_contours(ppp_cloud* cloud, const float* plane_x, int S, float half
                        int pairing_mode, int64_t* node_offsets, double* y, double* x, double* z,
                        int64_t node_cap);
 
+/* insert_point(indices, PlanePoint) with the CALLER's index list instead of the band of the plane
+ * (same reference lines as above; every reference call site passes rangedX_index(PlanePoint[0]),
+ * for which ppp_slice_contours is the one-call equivalent).  indices: strictly ascending.
+ * *n_nodes = node count; y == NULL: count only; PPP_ERR_CAPACITY if node_cap is too small.       */
+int ppp_insert_point(ppp_cloud* cloud, const int32_t* indices, int64_t m, float plane_x, int pairing_mode,
+                     double* y, double* x, double* z, int64_t node_cap, int64_t* n_nodes);
+
 /* "next" row of SURVEY.md §8f: the device part of compute_transform (src/Path_Generation.cpp:362-400,
  * k = 10; src/Path_Alg/path_dynamic_alg.cpp:77-110, k = 50) for a batch of query points:
  * kdtree.nearestKSearch(point, k) + PrincipalCurvaturesEstimation::computePointPrincipalCurvatures
@@ -135,6 +142,17 @@ int ppp_slice_contours(ppp_cloud* cloud, const float* plane_x, int S, float half
  * (pcx, pcy, pcz, pc1, pc2); nn0 (nullable): nearest point index per query.                    */
 int ppp_principal_curvatures(ppp_cloud* cloud, const void* normals, size_t normal_stride_bytes, const float* q,
                              size_t nq, size_t q_stride_bytes, int k, float* out, int32_t* nn0);
+
+/* "next" row of SURVEY.md §8f-3: first pass of pcl::StatisticalOutlierRemoval as run by
+ * SectPath::remove_outlier (src/contour_alg.cpp:101-108; twins src/Path_Alg/path_slicing_alg.cpp:101-108):
+ * kNN(mean_k + 1) of every point, dist_out[i] = (float)(sum of the mean_k neighbour distances / mean_k),
+ * 0 for non-finite points; *n_valid = finite points.  The sequential mean/stddev/threshold pass over
+ * dist_out is the caller's (host adapters' remove_outlier()).  flags: PPP_SOR_SQRT_FLOAT evaluates
+ * sqrt(d2) in float (the overload a translation unit with <math.h> picks) instead of double.
+ * PPP_ERR_UNSUPPORTED if the cloud has no more than mean_k finite points (the reference reads past
+ * the neighbour list there).                                                                      */
+#define PPP_SOR_SQRT_FLOAT 1u
+int ppp_sor_mean_distances(ppp_cloud* cloud, int mean_k, unsigned flags, float* dist_out, int64_t* n_valid);
 
 /* "next" row of SURVEY.md §8f: compute_coverage (src/Path_Generation.cpp:483-496) for a batch of
  * path nodes.  flags: N bytes (host, in/out); flags[i] = 1 for every point i within `radius` of a

@@ -825,4 +825,61 @@ int ppo_principal_curvatures(void* h, const float* normals, int64_t nsf, const f
   return 0;
 }
 
+// pcl::StatisticalOutlierRemoval<PointT>::applyFilterIndices [upstream, recalled, PCL 1.10
+// filters/impl/statistical_outlier_removal.hpp] as run by SectPath::remove_outlier
+// (src/contour_alg.cpp:101-108: setMeanK(50), setStddevMulThresh(1.0); twins
+// src/Path_Alg/path_slicing_alg.cpp:101-108, commented out at src/Path_Generation.cpp:17-22).
+// First pass: per point, nearestKSearch(point, mean_k + 1); dist_sum (double) += sqrt(nn_dists[j]) for
+// j = 1..mean_k (entry 0 is the query itself); distances[i] = (float)(dist_sum / mean_k).  Non-finite
+// points get 0 and are not counted in n_valid.  `sqrt (nn_dists[k])` is an unqualified call on a float:
+// whether it resolves to the float overload depends on the headers of the translation unit, so both
+// are provided (sqrt_float = 0: double sqrt of the widened value; 1: float sqrt).
+int ppo_sor_mean_distances(void* h, int mean_k, int sqrt_float, float* dist, int64_t* n_valid, int threads) {
+  Cloud* C = (Cloud*)h;
+  const int k = mean_k + 1;
+  if (mean_k < 1 || C->P.n < k) return -1;   // the reference reads past the result list here
+  threads = clamp_threads(threads);
+  int64_t valid = 0;
+#pragma omp parallel num_threads(threads) reduction(+ : valid)
+  {
+    std::vector<Key> buf(k);
+#pragma omp for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < C->P.n; i++) {
+      dist[i] = 0.0f;
+      if (!finite3(C->P.at(i))) continue;
+      int m = C->tree.knn(C->P.at(i), k, buf.data());
+      if (m < k) continue;                   // fewer finite points than k: treated as a failed search
+      double dist_sum = 0.0;
+      for (int j = 1; j < k; j++) dist_sum += sqrt_float ? (double)std::sqrt(buf[j].d2) : std::sqrt((double)buf[j].d2);
+      dist[i] = (float)(dist_sum / mean_k);
+      valid++;
+    }
+  }
+  *n_valid = valid;
+  return 0;
+}
+
+// Second half of applyFilterIndices: sequential double sums over ALL distances (zeros of the invalid
+// points included), mean / variance over n_valid, threshold = mean + std_mul * stddev, inliers are
+// distances[i] <= threshold (negative = 0).  kept: ascending indices; returns their count.
+int64_t ppo_sor_select(const float* dist, int64_t n, int64_t n_valid, double std_mul, int negative, int32_t* kept,
+                       double* threshold_out) {
+  double sum = 0, sq_sum = 0;
+  for (int64_t i = 0; i < n; i++) {
+    sum += dist[i];
+    sq_sum += dist[i] * dist[i];             // float product, widened on accumulation
+  }
+  double mean = sum / (double)n_valid;
+  double variance = (sq_sum - sum * sum / (double)n_valid) / ((double)n_valid - 1);
+  double stddev = std::sqrt(variance);
+  double thr = mean + std_mul * stddev;
+  if (threshold_out) *threshold_out = thr;
+  int64_t o = 0;
+  for (int64_t i = 0; i < n; i++) {
+    bool outlier = (!negative && dist[i] > thr) || (negative && dist[i] <= thr);
+    if (!outlier) kept[o++] = (int32_t)i;
+  }
+  return o;
+}
+
 }  // extern "C"

@@ -56,6 +56,9 @@ def lib():
         L.ppo_num_threads.restype = C.c_int
         L.ppo_steffen_eval.argtypes = [_f64p, _f64p, C.c_int64, _f64p, C.c_int64, _f64p]
         L.ppo_principal_curvatures.argtypes = [C.c_void_p, _f32p, C.c_int64, _f32p, C.c_int64, C.c_int64, C.c_int, _f32p, _i32p]
+        L.ppo_sor_mean_distances.argtypes = [C.c_void_p, C.c_int, C.c_int, _f32p, C.POINTER(C.c_int64), C.c_int]
+        L.ppo_sor_select.argtypes = [_f32p, C.c_int64, C.c_int64, C.c_double, C.c_int, _i32p, C.POINTER(C.c_double)]
+        L.ppo_sor_select.restype = C.c_int64
         L.ppo_coverage_mark.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, C.c_double, C.POINTER(C.c_ubyte)]
         _lib = L
     return _lib
@@ -176,6 +179,24 @@ class OracleCloud:
         lib().ppo_principal_curvatures(self._h, _fp(normals), normals.shape[1], _fp(queries), queries.shape[0],
                                        queries.shape[1], int(k), _fp(out), _ip(nn0))
         return out, nn0
+
+    def sor_mean_distances(self, mean_k=50, sqrt_float=False, threads=0):
+        """First pass of StatisticalOutlierRemoval. Returns (distances float32[N], n_valid)."""
+        dist = np.empty(self.n, np.float32)
+        nv = C.c_int64(0)
+        rc = lib().ppo_sor_mean_distances(self._h, mean_k, int(sqrt_float), _fp(dist), C.byref(nv), threads)
+        if rc != 0:
+            raise ValueError("sor: cloud has no more than mean_k points")
+        return dist, nv.value
+
+    @staticmethod
+    def sor_select(dist, n_valid, std_mul=1.0, negative=False):
+        """Second pass: (kept indices, threshold)."""
+        dist = np.ascontiguousarray(dist, np.float32)
+        kept = np.empty(dist.shape[0], np.int32)
+        thr = C.c_double(0)
+        n = lib().ppo_sor_select(_fp(dist), dist.shape[0], n_valid, std_mul, int(negative), _ip(kept), C.byref(thr))
+        return kept[:n].copy(), thr.value
 
     def coverage_mark(self, queries, radius, flags=None):
         queries = np.ascontiguousarray(queries, np.float32)

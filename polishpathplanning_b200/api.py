@@ -215,6 +215,18 @@ class Cloud:
             t = int(off[-1])
             return off, y[:t], x[:t], z[:t]
 
+    def insert_point(self, indices, plane_x, mode):
+        """insert_point with an explicit (strictly ascending) index list. Returns (y, x, z)."""
+        if isinstance(mode, str):
+            mode = PPP_PAIR_GEN2 if mode.upper() == "A" else PPP_PAIR_SECT
+        indices = np.ascontiguousarray(indices, np.int32)
+        cap = max(indices.shape[0], 1)
+        y, x, z = (np.empty(cap, np.float64) for _ in range(3))
+        n = C.c_int64(0)
+        check(self.lib.ppp_insert_point(self._h, _ptr(indices), indices.shape[0], float(plane_x), mode, _ptr(y), _ptr(x),
+                                        _ptr(z), cap, C.byref(n)))
+        return y[:n.value], x[:n.value], z[:n.value]
+
     def normals_and_contours(self, planes, mode, k=0, radius=0.0, viewpoint=(0.0, 0.0, 0.0), flags=PPP_COV_PCL110,
                              half_width=2.0, truncate_center=True, normals_out=None, nodes_out=None, stride_floats=8):
         """estimate_normal + plane sweep in one call (normals D2H overlaps the slicing kernels).
@@ -250,6 +262,13 @@ class Cloud:
         check(self.lib.ppp_principal_curvatures(self._h, _ptr(normals), normals.shape[1] * 4, _ptr(queries),
                                                 queries.shape[0], queries.shape[1] * 4, int(k), _ptr(out), _ptr(nn0)))
         return out, nn0
+
+    def sor_mean_distances(self, mean_k=50, sqrt_float=False):
+        """First pass of StatisticalOutlierRemoval: (mean neighbour distance float32[N], n_valid)."""
+        dist = np.empty(self.n, np.float32)
+        nv = C.c_int64(0)
+        check(self.lib.ppp_sor_mean_distances(self._h, int(mean_k), 1 if sqrt_float else 0, _ptr(dist), C.byref(nv)))
+        return dist, nv.value
 
     def coverage_mark(self, queries, radius, flags=None):
         """compute_coverage for a batch of nodes; flags (uint8, N) is updated in place and returned."""

@@ -613,4 +613,76 @@ int ppp_principal_curvatures(ppp_cloud* c, const void* normals, size_t normal_st
   return PPP_OK;
 }
 
+// insert_point(std::vector<int> indices, Eigen::Vector3f PlanePoint) with the caller's own index
+// list (src/Path_Generation.cpp:107-206, src/contour_alg.cpp:165-237).  indices must be strictly
+// ascending and in range, as rangedX_index returns them.  y/x/z hold node_cap nodes; *n_nodes is the
+// node count (PPP_ERR_CAPACITY if it exceeds node_cap; y == NULL: count only).
+int ppp_insert_point(ppp_cloud* c, const int32_t* indices, int64_t m, float plane_x, int pairing_mode, double* y,
+                     double* x, double* z, int64_t node_cap, int64_t* n_nodes) {
+  REQUIRE(c && n_nodes && (m == 0 || indices), "NULL argument");
+  REQUIRE(m >= 0, "negative index count");
+  REQUIRE(pairing_mode == PPP_PAIR_GEN2 || pairing_mode == PPP_PAIR_SECT, "unknown pairing mode");
+  REQUIRE(!y || (x && z), "y, x, z must be given together");
+  for (int64_t i = 0; i < m; i++) {
+    REQUIRE(indices[i] >= 0 && indices[i] < c->n, "index out of range");
+    REQUIRE(i == 0 || indices[i] > indices[i - 1], "indices must be strictly ascending");
+  }
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  GridStore* g;
+  PPP_TRY(pick_any_grid(c, &g));
+  int64_t total = 0;
+  PPP_TRY(contours_from_indices_launch(c, *g, indices, m, plane_x, pairing_mode, &total));
+  *n_nodes = total;
+  int st = PPP_OK;
+  if (y) {
+    if (node_cap < total) {
+      ppp_set_error("ppp_insert_point: node_cap %lld < required %lld", (long long)node_cap, (long long)total);
+      st = PPP_ERR_CAPACITY;
+    } else if (total) {
+      PPP_CUDA(cudaMemcpyAsync(y, c->out_y, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      PPP_CUDA(cudaMemcpyAsync(x, c->out_x, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      PPP_CUDA(cudaMemcpyAsync(z, c->out_z, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+  }
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  return st;
+}
+
+// First pass of pcl::StatisticalOutlierRemoval as SectPath::remove_outlier runs it
+// (src/contour_alg.cpp:101-108, mean_k = 50): dist_out[i] = (float)(sum_j sqrt(d2_j) / mean_k) over the
+// mean_k nearest neighbours of point i (itself excluded), 0 for non-finite points; *n_valid = number of
+// finite points.  The reference's sequential mean / stddev / threshold pass over dist_out stays with
+// the caller (host adapters: remove_outlier).
+int ppp_sor_mean_distances(ppp_cloud* c, int mean_k, unsigned flags, float* dist_out, int64_t* n_valid) {
+  REQUIRE(c && n_valid && (dist_out || c->n == 0), "NULL argument");
+  REQUIRE(mean_k >= 1, "mean_k must be >= 1");
+  REQUIRE((flags & ~(unsigned)PPP_SOR_SQRT_FLOAT) == 0, "unknown flags");
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  if (c->n_finite <= mean_k) {
+    ppp_set_error("ppp_sor_mean_distances: %lld finite points, need more than mean_k = %d", (long long)c->n_finite, mean_k);
+    return PPP_ERR_UNSUPPORTED;
+  }
+  GridStore* g;
+  PPP_TRY(cloud_get_grid(c, cloud_cell_for_k(c, mean_k + 1), &g));
+  float* dist_d = nullptr; unsigned long long* nv_d = nullptr;
+  PPP_TRY(dev_alloc(ctx, &dist_d, (size_t)c->n));
+  PPP_TRY(dev_alloc(ctx, &nv_d, 1));
+  int st = sor_mean_distances_launch(c, *g, mean_k, (flags & PPP_SOR_SQRT_FLOAT) ? 1 : 0, dist_d, nv_d);
+  unsigned long long nv = 0;
+  if (st == PPP_OK) {
+    PPP_CUDA(cudaMemcpyAsync(dist_out, dist_d, (size_t)c->n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PPP_CUDA(cudaMemcpyAsync(&nv, nv_d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, dist_d); dev_free(ctx, nv_d);
+  if (st != PPP_OK) return st;
+  PPP_CUDA(e);
+  *n_valid = (int64_t)nv;
+  return PPP_OK;
+}
+
 }  // extern "C"

@@ -1032,6 +1032,33 @@ __global__ void __launch_bounds__(128) k_coverage_mark(SearchParams P, unsigned 
 }
 
 // counts for non-finite self points that are not in the sorted array: zero-fill first
+// StatisticalOutlierRemoval first pass (src/contour_alg.cpp:101-108): mean of the distances to the
+// mean_k nearest neighbours, from the sorted d2 rows of a (mean_k + 1)-NN search.  The additions run
+// in list order in double, exactly as the reference's scalar loop; entry 0 (the query itself) is skipped.
+__global__ void __launch_bounds__(256) k_sor_mean(const float4* __restrict__ xyz4, const float* __restrict__ d2, int64_t n,
+                                                  int k, int sqrt_float, float* __restrict__ dist,
+                                                  unsigned long long* __restrict__ n_valid) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool ok = false;
+  if (i < n) {
+    float4 p = __ldg(xyz4 + i);
+    ok = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+    float out = 0.0f;
+    if (ok) {
+      const float* row = d2 + i * k;
+      double sum = 0.0;
+      for (int j = 1; j < k; j++) {
+        float v = __ldg(row + j);
+        sum = __dadd_rn(sum, sqrt_float ? (double)__fsqrt_rn(v) : __dsqrt_rn((double)v));
+      }
+      out = (float)__ddiv_rn(sum, (double)(k - 1));
+    }
+    dist[i] = out;
+  }
+  unsigned cnt = __syncthreads_count(ok);
+  if (threadIdx.x == 0 && cnt) atomicAdd(n_valid, (unsigned long long)cnt);
+}
+
 __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -1302,6 +1329,30 @@ int coverage_mark_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, 
   PPP_LAUNCH(ctx, "coverage_mark", k_coverage_mark, blocks, 128, 0, P, flags_dev);
   PPP_CHECK_LAUNCH();
   return PPP_OK;
+}
+
+static int sor_mean_inner(ppp_cloud* c, const GridStore& gs, int k, int sqrt_float, int32_t* idx, float* d2,
+                          float* dist_dev, unsigned long long* n_valid_dev) {
+  ppp_ctx* ctx = c->ctx;
+  PPP_TRY(knn_launch(c, gs, nullptr, c->n_finite, 0, 0, k, idx, d2, false, nullptr, 0, nullptr, 0));
+  PPP_CUDA(cudaMemsetAsync(n_valid_dev, 0, 8, ctx->stream));
+  unsigned blocks = (unsigned)((c->n + 255) / 256);
+  PPP_LAUNCH(ctx, "sor_mean", k_sor_mean, blocks, 256, 0, (const float4*)c->xyz4, (const float*)d2, c->n, k, sqrt_float,
+             dist_dev, n_valid_dev);
+  PPP_CHECK_LAUNCH();
+  return PPP_OK;
+}
+
+int sor_mean_distances_launch(ppp_cloud* c, const GridStore& gs, int mean_k, int sqrt_float, float* dist_dev,
+                              unsigned long long* n_valid_dev) {
+  ppp_ctx* ctx = c->ctx;
+  const int k = mean_k + 1;
+  int32_t* idx = nullptr; float* d2 = nullptr;
+  PPP_TRY(dev_alloc(ctx, &idx, (size_t)c->n * k));
+  int st = dev_alloc(ctx, &d2, (size_t)c->n * k);
+  if (st == PPP_OK) st = sor_mean_inner(c, gs, k, sqrt_float, idx, d2, dist_dev, n_valid_dev);
+  dev_free(ctx, idx); dev_free(ctx, d2);
+  return st;
 }
 
 int principal_curvatures_launch(ppp_cloud* c, const int32_t* idx_dev, int64_t nq, int k, const float* normals_dev,

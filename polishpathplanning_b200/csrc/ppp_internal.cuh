@@ -199,6 +199,8 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& g, int64_t first, int64
 
 int principal_curvatures_launch(ppp_cloud* c, const int32_t* idx_dev, int64_t nq, int k, const float* normals_dev,
                                 int normal_stride_f, float* out_dev, int32_t* nn0_dev);
+int sor_mean_distances_launch(ppp_cloud* c, const GridStore& gs, int mean_k, int sqrt_float, float* dist_dev,
+                              unsigned long long* n_valid_dev);
 int coverage_mark_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq, int q_stride_f, float r2,
                          unsigned char* flags_dev);
 
@@ -208,4 +210,6 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
                  std::vector<int64_t>* offsets_host_out);
 int contours_launch(ppp_cloud* c, const GridStore& g, const float* planes_dev, int S, const int64_t* band_off_dev,
                     const int32_t* band_idx_dev, int64_t band_total, const std::vector<int64_t>& band_off_host, int mode,
-                    int64_t* total_nodes_out);
+                    int64_t* total_nodes_out, const uint32_t* member_bits = nullptr);
+int contours_from_indices_launch(ppp_cloud* c, const GridStore& gs, const int32_t* idx_host, int64_t m, float plane_x,
+                                 int mode, int64_t* total_nodes_out);

@@ -171,6 +171,7 @@ struct ContourParams {
   unsigned char *fl, *fr;
   double *ty, *tz;       // un-compacted nodes per slice
   int32_t* n_nodes;      // S
+  const uint32_t* member; // optional membership bitmap (explicit index lists)
 };
 
 __device__ __forceinline__ uint32_t f2ord_dev(float f) {
@@ -203,13 +204,17 @@ __device__ __forceinline__ int cta_flag_rank(bool flag, int* s_warp, int& runnin
 // metric 1: Eigen norm sqrtf(dx^2 + (dy^2 + dz^2)), ties -> highest index (std::map<float,int>
 //           overwrite in src/Path_Generation.cpp:143-150: equal keys keep the last j).
 // Searches the grid ring by ring; gives up after RMAX rings and scans the side's member list.
+template <bool MEMBER>
 __device__ int nn_side(const GridView& g, const float4* __restrict__ xyz4, float qx, float qy, float qz, float lo,
-                       float hi, float plane, bool want_left, int metric, const int32_t* list, int nlist) {
+                       float hi, float plane, bool want_left, int metric, const int32_t* list, int nlist,
+                       const uint32_t* __restrict__ member) {
   if (nlist <= 0) return -1;
   const int RMAX = 6;
   u64 best = PPP_KEY_INF;
+  // membership of the slice: the x-interval of the band, or (explicit index lists) a bitmap
   auto consider = [&](float cx, float cy, float cz, int idx) {
-    if (cx < lo || cx > hi) return;
+    if (MEMBER) { if (!((__ldg(member + (idx >> 5)) >> (idx & 31)) & 1u)) return; }
+    else if (cx < lo || cx > hi) return;
     if (want_left ? !(cx > plane) : !(cx < plane)) return;
     u64 key;
     if (metric == 0) {
@@ -226,7 +231,7 @@ __device__ int nn_side(const GridView& g, const float4* __restrict__ xyz4, float
   // when x is the fast grid axis only the cell columns that overlap the wanted x-interval can
   // hold members (cell coordinates are monotone in x)
   int ulo = -2147483647, uhi = 2147483647;
-  if (g.au == 0) {
+  if (g.au == 0 && !MEMBER) {
     ulo = cell_coord_raw(want_left ? plane : lo, g.min_u, g.inv_h);
     uhi = cell_coord_raw(want_left ? hi : plane, g.min_u, g.inv_h);
   }
@@ -285,6 +290,7 @@ __device__ __forceinline__ int lower_pos(const int32_t* a, int n, int v) {
 // and sort keys of a slice live in shared memory when they fit (9 bytes per band member), so the
 // order-dependent greedy flag pass — one thread replaying src/Path_Generation.cpp:137-179 — runs
 // at shared-memory latency; larger bands use the global scratch arrays with the same code.
+template <bool MEMBER>
 __global__ void __launch_bounds__(1024) k_contour(ContourParams P, int smem_cap) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ int s_warp[32];
@@ -347,13 +353,13 @@ __global__ void __launch_bounds__(1024) k_contour(ContourParams P, int smem_cap)
     // nearest right of every left, nearest left of every right (flag-independent) ...
     for (int i = threadIdx.x; i < nL; i += (int)blockDim.x) {
       float4 pl = __ldg(P.xyz4 + El[i]);
-      int r = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 1, Er, nR);
+      int r = nn_side<MEMBER>(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 1, Er, nR, P.member);
       posR[i] = lower_pos(Er, nR, r);
       fl[i] = 0;
     }
     for (int j = threadIdx.x; j < nR; j += (int)blockDim.x) {
       float4 pr = __ldg(P.xyz4 + Er[j]);
-      int l = nn_side(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 1, El, nL);
+      int l = nn_side<MEMBER>(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 1, El, nL, P.member);
       posL[j] = lower_pos(El, nL, l);
       fr[j] = 0;
     }
@@ -433,6 +439,7 @@ struct PairParams {
   u64* keys;
   float* ys;
   float* zs;
+  const uint32_t* member;   // optional membership bitmap (explicit index lists)
 };
 
 // Each warp takes PAIR_CHUNK consecutive members, keeps the left ones (about half) in a small
@@ -441,6 +448,7 @@ struct PairParams {
 constexpr int PAIR_CHUNK = 56;   // ~28 left members per chunk: usually one full round of 32 lanes
 constexpr int PAIR_WARPS = 4;
 
+template <bool MEMBER>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
   __shared__ int64_t s_m[PAIR_WARPS][64];
   __shared__ int s_s[PAIR_WARPS][64];
@@ -481,11 +489,11 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
     const float4 pl = __ldg(P.xyz4 + __ldg(P.band_idx + m));
     u64 key = PPP_KEY_INF;
     float y = 0.f, z = 0.f;
-    int ri = nn_side(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, band, B);
+    int ri = nn_side<MEMBER>(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, band, B, P.member);
     if (ri >= 0) {
       float4 pr = __ldg(P.xyz4 + ri);
       int rc = nn_full(P.g, pr.x, pr.y, pr.z, ri);
-      int li = nn_side(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, band, B);
+      int li = nn_side<MEMBER>(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, band, B, P.member);
       float4 pl2 = __ldg(P.xyz4 + li);
       int lc = nn_full(P.g, pl2.x, pl2.y, pl2.z, li);
       float4 a = __ldg(P.xyz4 + rc);  // index_right
@@ -555,6 +563,11 @@ __global__ void __launch_bounds__(SO_THREADS) k_slice_order(const int64_t* __res
     }
   }
   if (threadIdx.x == 0) n_nodes[s] = nodes;
+}
+
+__global__ void k_set_member_bits(const int32_t* __restrict__ idx, int64_t m, uint32_t* __restrict__ bits) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) atomicOr(bits + (idx[i] >> 5), 1u << (idx[i] & 31));
 }
 
 __global__ void __launch_bounds__(256) k_compact_nodes(const int64_t* __restrict__ band_off, const int64_t* __restrict__ node_off,
@@ -712,7 +725,7 @@ static int finish_nodes(ppp_cloud* c, int S, const int64_t* band_off_dev, const 
 // band_off_host: S+1 offsets (for sizing shared memory).  Variant A needs index-sorted bands.
 int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, int S, const int64_t* band_off_dev,
                     const int32_t* band_idx_dev, int64_t band_total, const std::vector<int64_t>& band_off_host, int mode,
-                    int64_t* total_nodes_out) {
+                    int64_t* total_nodes_out, const uint32_t* member_bits) {
   ppp_ctx* ctx = c->ctx;
   *total_nodes_out = 0;
   size_t M = (size_t)std::max<int64_t>(band_total, 1);
@@ -726,10 +739,12 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     P.g = gs.v; P.xyz4 = c->xyz4;
     P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
     P.band_off = band_off_dev; P.band_idx = band_idx_dev; P.S = S; P.M = band_total;
+    P.member = member_bits;
     PPP_TRY(dev_alloc(ctx, &P.keys, M)); PPP_TRY(dev_alloc(ctx, &P.ys, M)); PPP_TRY(dev_alloc(ctx, &P.zs, M));
     if (band_total > 0) {
       const int64_t per_block = (int64_t)PAIR_WARPS * PAIR_CHUNK;
-      PPP_LAUNCH(ctx, "pair_nodes", k_pair_nodes, (unsigned)((band_total + per_block - 1) / per_block), PAIR_WARPS * 32, 0, P);
+      auto kern = member_bits ? k_pair_nodes<true> : k_pair_nodes<false>;
+      PPP_LAUNCH(ctx, "pair_nodes", kern, (unsigned)((band_total + per_block - 1) / per_block), PAIR_WARPS * 32, 0, P);
       PPP_CHECK_LAUNCH();
     }
     int64_t maxB = 0;
@@ -752,6 +767,7 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
     P.band_off = band_off_dev; P.band_idx = band_idx_dev; P.mode = mode;
     P.ty = ty; P.tz = tz; P.n_nodes = n_nodes;
+    P.member = member_bits;
     PPP_TRY(dev_alloc(ctx, &P.El, M)); PPP_TRY(dev_alloc(ctx, &P.Er, M));
     PPP_TRY(dev_alloc(ctx, &P.keys, M));
     PPP_TRY(dev_alloc(ctx, &P.ys, M)); PPP_TRY(dev_alloc(ctx, &P.zs, M));
@@ -763,8 +779,9 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
       for (int s = 0; s < S; s++) maxB = std::max(maxB, band_off_host[s + 1] - band_off_host[s]);
       int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(maxB, 2), 22000);  // 9 bytes per member, <= 198 KB
       size_t smem = 9 * (size_t)((smem_cap + 1) & ~1) + 16;
-      if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(k_contour, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      PPP_LAUNCH(ctx, "contour_gen2", k_contour, (unsigned)S, 1024, smem, P, smem_cap);
+      auto kern = member_bits ? k_contour<true> : k_contour<false>;
+      if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PPP_LAUNCH(ctx, "contour_gen2", kern, (unsigned)S, 1024, smem, P, smem_cap);
       PPP_CHECK_LAUNCH();
     }
     st = finish_nodes(c, S, band_off_dev, planes_dev, n_nodes, ty, tz, total_nodes_out);
@@ -773,5 +790,33 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     dev_free(ctx, P.fr);
   }
   dev_free(ctx, ty); dev_free(ctx, tz); dev_free(ctx, n_nodes);
+  return st;
+}
+
+// insert_point(indices, PlanePoint) with an EXPLICIT index list (ascending, as rangedX_index
+// returns it): one slice whose members are exactly `indices`; membership tests use a bitmap
+// instead of the band's x-interval.
+int contours_from_indices_launch(ppp_cloud* c, const GridStore& gs, const int32_t* idx_host, int64_t m, float plane_x,
+                                 int mode, int64_t* total_nodes_out) {
+  ppp_ctx* ctx = c->ctx;
+  *total_nodes_out = 0;
+  float stage[3] = {plane_x, -INFINITY, INFINITY};
+  int64_t off_h[2] = {0, m};
+  float* planes = nullptr; int64_t* boff = nullptr; int32_t* bidx = nullptr; uint32_t* bits = nullptr;
+  size_t words = (size_t)(c->n + 31) / 32 + 1;
+  PPP_TRY(dev_alloc(ctx, &planes, 3)); PPP_TRY(dev_alloc(ctx, &boff, 2));
+  PPP_TRY(dev_alloc(ctx, &bidx, (size_t)std::max<int64_t>(m, 1))); PPP_TRY(dev_alloc(ctx, &bits, words));
+  PPP_CUDA(cudaMemcpyAsync(planes, stage, sizeof(stage), cudaMemcpyHostToDevice, ctx->stream));
+  PPP_CUDA(cudaMemcpyAsync(boff, off_h, sizeof(off_h), cudaMemcpyHostToDevice, ctx->stream));
+  if (m) PPP_CUDA(cudaMemcpyAsync(bidx, idx_host, (size_t)m * 4, cudaMemcpyHostToDevice, ctx->stream));
+  PPP_CUDA(cudaMemsetAsync(bits, 0, words * 4, ctx->stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));  // the small host arrays above live on this stack frame
+  if (m) {
+    PPP_LAUNCH(ctx, "set_member_bits", k_set_member_bits, (unsigned)((m + 255) / 256), 256, 0, (const int32_t*)bidx, m, bits);
+    PPP_CHECK_LAUNCH();
+  }
+  std::vector<int64_t> offv = {0, m};
+  int st = contours_launch(c, gs, planes, 1, boff, bidx, m, offv, mode, total_nodes_out, bits);
+  dev_free(ctx, planes); dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, bits);
   return st;
 }

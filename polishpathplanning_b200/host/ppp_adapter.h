@@ -126,6 +126,17 @@ inline Contours slice_contours(ppp_cloud* c, const std::vector<float>& planes, i
   return r;
 }
 
+// insert_point with the caller's index list (strictly ascending, as rangedX_index returns it)
+inline MAP insert_point(ppp_cloud* c, const std::vector<int>& indices, float plane_x, int mode) {
+  int64_t n = 0;
+  std::vector<double> y(indices.size() + 1), x(indices.size() + 1), z(indices.size() + 1);
+  check(ppp_insert_point(c, indices.data(), (int64_t)indices.size(), plane_x, mode, y.data(), x.data(), z.data(),
+                         (int64_t)y.size(), &n), "ppp_insert_point");
+  MAP m;
+  for (int64_t i = 0; i < n; i++) m[y[i]] = {x[i], z[i]};
+  return m;
+}
+
 inline MAP to_map(const Contours& c, int s) {
   MAP m;
   for (int64_t i = c.offsets[s]; i < c.offsets[s + 1]; i++) m[c.y[i]] = {c.x[i], c.z[i]};
@@ -175,12 +186,8 @@ public:
     return idx;
   }
 
-  // `indices` is rangedX_index(PlanePoint[0]) at every reference call site; the band is recomputed
-  // on the device from the plane, so the argument is accepted for signature compatibility.
   MAP insert_point(std::vector<int> indices, Eigen::Vector3f PlanePoint) {
-    (void)indices;
-    ppp_host::Contours c = ppp_host::slice_contours(dev_.get(*cloud), {PlanePoint[0]}, PPP_PAIR_GEN2);
-    return ppp_host::to_map(c, 0);
+    return ppp_host::insert_point(dev_.get(*cloud), indices, PlanePoint[0], PPP_PAIR_GEN2);
   }
 
   void slicing_method() {  // src/Path_Generation.cpp:282-321: all planes of the sweep in ONE device pass
@@ -252,6 +259,11 @@ public:
         if (ifChangeRange) { cloud->points[i].x *= 1000; cloud->points[i].y *= 1000; cloud->points[i].z *= 1000; }
       }
     }
+    // src/contour_alg.cpp:27-29.  smooth (MLS) and trans2center (PCA alignment) are outside the
+    // accelerated path (out of scope): say so instead of silently skipping them.
+    if (ifSmooth) fprintf(stderr, "SectPath: Smooth=true is not available in this build (MLS is out of scope)\n");
+    if (ifAlign) fprintf(stderr, "SectPath: Alignment=true is not available in this build (trans2center is out of scope)\n");
+    if (ifRemove && cloud->points.size() > 50) remove_outlier();
   }
   virtual ~SectPath() {}
 
@@ -260,6 +272,31 @@ public:
     normal_cloud->points.resize(cloud->points.size());
     ppp_host::check(ppp_normals_radius(dev_.get(*cloud), 2.5, vp, PPP_COV_PCL110, normal_cloud->points.data(), sizeof(pcl::Normal)),
                     "ppp_normals_radius");
+  }
+
+  // src/contour_alg.cpp:101-108: StatisticalOutlierRemoval, setMeanK(50), setStddevMulThresh(1.0),
+  // filter(*cloud).  The kNN pass runs on the device; the statistics are the reference's scalar loop.
+  void remove_outlier() {
+    const int mean_k = 50;
+    const double std_mul = 1.0;
+    std::vector<float> distances(cloud->points.size());
+    int64_t valid_distances = 0;
+    ppp_host::check(ppp_sor_mean_distances(dev_.get(*cloud), mean_k, 0, distances.data(), &valid_distances),
+                    "ppp_sor_mean_distances");
+    double sum = 0, sq_sum = 0;
+    for (const float& distance : distances) {
+      sum += distance;
+      sq_sum += distance * distance;
+    }
+    double mean = sum / static_cast<double>(valid_distances);
+    double variance = (sq_sum - sum * sum / static_cast<double>(valid_distances)) / (static_cast<double>(valid_distances) - 1);
+    double distance_threshold = mean + std_mul * std::sqrt(variance);
+    size_t o = 0;
+    for (size_t i = 0; i < distances.size(); i++)
+      if (!(distances[i] > distance_threshold)) cloud->points[o++] = cloud->points[i];
+    cloud->points.resize(o);
+    cloud->width = (uint32_t)o; cloud->height = 1;
+    dev_.invalidate();
   }
 
   virtual void GenPath() {  // src/contour_alg.cpp:287-339: centre-out sweep, all planes in one pass
@@ -320,8 +357,7 @@ protected:
     return idx;
   }
   MAP insert_point(std::vector<int> indices, Eigen::Vector3f PlanePoint) {
-    (void)indices;
-    return ppp_host::to_map(ppp_host::slice_contours(dev_.get(*cloud), {PlanePoint[0]}, PPP_PAIR_SECT), 0);
+    return ppp_host::insert_point(dev_.get(*cloud), indices, PlanePoint[0], PPP_PAIR_SECT);
   }
   Spline OnePath(Eigen::Vector3f plane_point) {
     return ppp_host::slice_contours(dev_.get(*cloud), {plane_point[0]}, PPP_PAIR_SECT).path(0);

@@ -241,14 +241,9 @@ class path_generater(_Base):
 
     def insert_point(self, indices, PlanePoint):
         """std::map<double, std::vector<double>> insert_point(indices, PlanePoint): returns the map
-        as (y, x, z) arrays in ascending y.  `indices` must be rangedX_index(PlanePoint[0]), as at
-        every reference call site (src/Path_Generation.cpp:300-301,665)."""
-        plane = _f32(PlanePoint[0])
-        band = self.rangedX_index(plane)
-        if not np.array_equal(np.asarray(indices, np.int32), band):
-            raise ValueError("insert_point: indices differ from rangedX_index(PlanePoint[0])")
-        off, y, x, z = self._contours([plane], api.PPP_PAIR_GEN2)
-        return y, x, z
+        as (y, x, z) arrays in ascending y.  `indices`: strictly ascending point indices (every reference
+        call site passes rangedX_index(PlanePoint[0]), src/Path_Generation.cpp:300-301,665)."""
+        return self._dev().insert_point(np.asarray(indices, np.int32), _f32(PlanePoint[0]), api.PPP_PAIR_GEN2)
 
     def path_track(self, plane_point):
         y, x, z = self.insert_point(self.rangedX_index(plane_point[0]), plane_point)
@@ -274,21 +269,45 @@ class path_generater(_Base):
         return planes
 
 
+def sor_select(distances, n_valid, stddev_mul=1.0, negative=False):
+    """Second pass of pcl::StatisticalOutlierRemoval::applyFilterIndices: running double sums in index
+    order over all distances (np.cumsum accumulates sequentially), variance over n_valid - 1, inliers
+    distance <= mean + stddev_mul * stddev.  Returns (kept indices ascending, threshold)."""
+    d = np.ascontiguousarray(distances, np.float32)
+    if d.shape[0] == 0 or n_valid < 1:
+        return np.zeros(0, np.int32), float("nan")
+    total = float(np.cumsum(d.astype(np.float64))[-1])
+    sq_total = float(np.cumsum((d * d).astype(np.float64))[-1])        # float32 products, widened when added
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean = np.float64(total) / np.float64(n_valid)
+        variance = (np.float64(sq_total) - np.float64(total) * np.float64(total) / np.float64(n_valid)) / (np.float64(n_valid) - 1.0)
+        thr = float(mean + np.float64(stddev_mul) * np.sqrt(variance))
+    outlier = (d <= thr) if negative else (d > thr)
+    return np.flatnonzero(~outlier).astype(np.int32), thr
+
+
 class SectPath(_Base):
     """SectPath (contour_alg.h): kd-tree pairing without flags (variant B), centre-out sweep."""
 
-    def __init__(self, cloud_name, Tool_Radius, ChangeRange=True, ctx=None, device=0):
+    def __init__(self, cloud_name, Tool_Radius, ChangeRange=True, RemoveOutlier=False, ctx=None, device=0):
         super().__init__(ctx, device)
         self.toolRadius = float(Tool_Radius)
         self._load(cloud_name, change_range=ChangeRange)
+        if RemoveOutlier and self.cloud.shape[0] > 50:      # src/contour_alg.cpp:29
+            self.remove_outlier()
 
     def insert_point(self, indices, PlanePoint):
-        plane = _f32(PlanePoint[0])
-        band = self.rangedX_index(plane)
-        if not np.array_equal(np.asarray(indices, np.int32), band):
-            raise ValueError("insert_point: indices differ from rangedX_index(PlanePoint[0])")
-        off, y, x, z = self._contours([plane], api.PPP_PAIR_SECT)
-        return y, x, z
+        return self._dev().insert_point(np.asarray(indices, np.int32), _f32(PlanePoint[0]), api.PPP_PAIR_SECT)
+
+    def remove_outlier(self, mean_k=50, stddev_mul=1.0):
+        """SectPath::remove_outlier (src/contour_alg.cpp:101-108): StatisticalOutlierRemoval with
+        setMeanK(50), setStddevMulThresh(1.0), filtered in place.  The kNN pass runs on the device; the
+        mean / stddev / threshold pass is the reference's sequential double arithmetic."""
+        dist, n_valid = self._dev().sor_mean_distances(mean_k)
+        keep, _ = sor_select(dist, n_valid, stddev_mul)
+        self.cloud = np.ascontiguousarray(self.cloud[keep])
+        self._invalidate()
+        return keep
 
     def OnePath(self, plane_point):
         return self.insert_point(self.rangedX_index(plane_point[0]), plane_point)

@@ -494,3 +494,71 @@ def test_cfg3_shape_10m_points_k32_1000_slices(ctx):
         assert np.array_equal(y[noff[s]:noff[s + 1]], o[1][o[0][j]:o[0][j + 1]])
         assert np.array_equal(z[noff[s]:noff[s + 1]], o[3][o[0][j]:o[0][j + 1]])
     gc.close()
+
+
+@pytest.mark.parametrize("mode", ["A", "B"])
+def test_insert_point_explicit_indices(ctx, mode):
+    """insert_point with the caller's own index list: the band itself, thinned bands, an
+    arbitrary ascending subset that ignores the band limits, one-sided and empty lists."""
+    pts = synth.panel(60000, 31)
+    oc = po.OracleCloud(pts)
+    gc = api.Cloud(ctx, pts)
+    rng = np.random.default_rng(5)
+    mn, mx = oc.minmax()
+    for px in (float(mn[0]) + 7.3, 0.5 * float(mn[0] + mx[0]), float(mx[0]) - 3.1):
+        band = oc.band(px)
+        wide = np.flatnonzero(np.abs(pts[:, 0] - np.float32(px)) < 6).astype(np.int32)   # wider than the band
+        left_only = band[pts[band, 0] < np.float32(px)]
+        cases = [band, band[::2], band[rng.random(band.shape[0]) < 0.3], wide, left_only, band[:1], band[:0]]
+        for idx in cases:
+            oy, ox, oz, _, _ = oc.insert_point(idx, px, mode)
+            y, x, z = gc.insert_point(idx, px, mode)
+            assert np.array_equal(y, oy) and np.array_equal(x, ox) and np.array_equal(z, oz)
+        off, y, x, z = gc.slice_contours([px], mode)
+        yb, xb, zb = gc.insert_point(band, px, mode)
+        assert np.array_equal(y, yb) and np.array_equal(z, zb)
+    with pytest.raises(api.PPPError):
+        gc.insert_point(np.array([5, 3], np.int32), 0.0, mode)      # not ascending
+    with pytest.raises(api.PPPError):
+        gc.insert_point(np.array([0, pts.shape[0]], np.int32), 0.0, mode)
+    gc.close()
+
+
+def test_sor_mean_distances_and_remove_outlier(ctx, tmp_path):
+    """StatisticalOutlierRemoval (SectPath::remove_outlier): device distances bit-exact with the
+    oracle for both sqrt overloads and several mean_k (k > 64 takes the generic search), kept set equal."""
+    pts = synth.panel(60000, 13)
+    rng = np.random.default_rng(3)
+    out_rows = rng.choice(pts.shape[0], 300, replace=False)
+    pts[out_rows, 2] += rng.uniform(15, 80, 300).astype(np.float32)     # outliers above the surface
+    pts[77, 1] = np.inf
+    pts[5000] = pts[5001]                                               # duplicate point
+    oc = po.OracleCloud(pts)
+    gc = api.Cloud(ctx, pts)
+    for mean_k in (50, 1, 8, 31, 63, 100):
+        for fl in (False, True):
+            od, onv = oc.sor_mean_distances(mean_k, fl)
+            gd, gnv = gc.sor_mean_distances(mean_k, fl)
+            assert gnv == onv
+            assert np.array_equal(gd.view(np.uint32), od.view(np.uint32)), (mean_k, fl)
+    gd, gnv = gc.sor_mean_distances(50)
+    keep, thr = ra.sor_select(gd, gnv, 1.0)
+    okeep, othr = po.OracleCloud.sor_select(*oc.sor_mean_distances(50), 1.0)
+    assert thr == othr and np.array_equal(keep, okeep)
+    assert not set(out_rows.tolist()) & set(keep.tolist())
+    gc.close()
+    # reference-shaped flow: SectPath with RemoveOutlier=true, then normals + sweep on the filtered cloud
+    pcd = str(tmp_path / "w.pcd")
+    synth.write_pcd(pcd, synth.to_pointxyzrgb(synth.panel_metres(60000, 13)))
+    sp = ra.SectPath(pcd, 12, ChangeRange=True, RemoveOutlier=True, ctx=ctx)
+    clean = synth.panel(60000, 13)
+    ock = po.OracleCloud(clean)
+    ok2, _ = po.OracleCloud.sor_select(*ock.sor_mean_distances(50), 1.0)
+    assert np.array_equal(sp.cloud, clean[ok2])
+    of = po.OracleCloud(sp.cloud)
+    _same_normals(sp.estimate_normal(), of.normals(radius=2.5)[0])
+    tiny = api.Cloud(ctx, synth.panel(40, 1))
+    with pytest.raises(api.PPPError) as e:
+        tiny.sor_mean_distances(50)
+    assert e.value.status == api._lib.PPP_ERR_UNSUPPORTED
+    tiny.close()

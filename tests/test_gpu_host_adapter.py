@@ -98,3 +98,30 @@ def test_slicing_method_flow(tmp_path):
     planes = po.planes("gen2_slicing", mn[0], mx[0], 15.0)
     ooff, oy, ox, oz = oc.slice_contours(planes, "A")
     assert np.array_equal(off, ooff) and np.array_equal(y, oy) and np.array_equal(z, oz)
+
+
+def test_sectpath_remove_outlier_flow(tmp_path):
+    """config.txt with RemoveOutlier = true: SOR(50, 1.0) in the constructor, then normals + sweep."""
+    _build()
+    pcd = str(tmp_path / "workpiece.pcd")
+    metres = synth.to_pointxyzrgb(synth.panel_metres(40000, 9))
+    metres[::400, 2] += np.float32(0.03)                      # 30 mm outliers
+    synth.write_pcd(pcd, metres)
+    cfg = str(tmp_path / "config.txt")
+    with open(cfg, "w") as f:
+        f.write("Tool_Radius = 12\nChangeRange = true\nRemoveOutlier = true\n")
+    out = str(tmp_path / "sect")
+    r = subprocess.run([EXE, "--sect", cfg, pcd, out], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert r.returncode == 0, r.stderr
+    off, y, x, z, nrm = _load(out)
+    cloud = metres.copy()
+    cloud[:, :3] = metres[:, :3] * np.float32(1000)
+    keep, _ = po.OracleCloud.sor_select(*po.OracleCloud(cloud).sor_mean_distances(50), 1.0)
+    assert 0 not in keep and keep.shape[0] < cloud.shape[0]
+    oc = po.OracleCloud(np.ascontiguousarray(cloud[keep]))
+    assert nrm.shape[0] == keep.shape[0]
+    _check_normals(nrm, oc.normals(radius=2.5)[0])
+    mn, mx = oc.minmax()
+    planes = po.planes("sectpath", mn[0], mx[0], 12.0)
+    ooff, oy, ox, oz = oc.slice_contours(planes, "B")
+    assert np.array_equal(off, ooff) and np.array_equal(y, oy) and np.array_equal(z, oz)

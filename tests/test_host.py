@@ -183,3 +183,19 @@ def test_steffen_spline_restatements_agree():
         ra.Spline(y[::-1], x, z)
     with pytest.raises(ValueError):
         po.steffen_eval(y[:2], z[:2], q)
+
+
+def test_sor_threshold_pass_restatements_agree():
+    """The host mirror of StatisticalOutlierRemoval's sequential statistics equals the oracle's loop."""
+    from polishpathplanning_b200 import reference_api as ra
+    rng = np.random.default_rng(11)
+    for n in (2, 7, 1000, 250000):
+        d = rng.gamma(9.0, 0.3, n).astype(np.float32)
+        d[rng.random(n) < 0.01] = 0.0
+        nv = int((d != 0).sum()) or 1
+        for mul in (1.0, 0.25, 3.0):
+            for neg in (False, True):
+                kept, thr = ra.sor_select(d, nv, mul, neg)
+                okept, othr = po.OracleCloud.sor_select(d, nv, mul, neg)
+                assert np.array_equal(kept, okept)
+                assert thr == othr or (np.isnan(thr) and np.isnan(othr))
