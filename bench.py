@@ -232,6 +232,9 @@ def run_ours(args):
 
     last = {}
     gat = {}
+    # how the normals reach rank 0: "peer" = direct NVLink stores from the search kernel (default),
+    # "nccl" = all-gather after the kernel, "none" = left on the owning GPU
+    gather_mode = os.environ.get("PPP_BENCH_GATHER", "none" if os.environ.get("PPP_BENCH_NOGATHER") else "peer")
     if world > 1:
         # static gather buffers: equal-sized NCCL gathers, no per-step size exchange
         # The whole local normal array (owned + halo rows) is gathered: rank 0 keeps the owned rows
@@ -240,12 +243,26 @@ def run_ours(args):
         t = torch.tensor([n_local], dtype=torch.int64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gat["own_cap"] = int(t.item())
-        with torch.cuda.stream(stream):
-            gat["own"] = torch.zeros((gat["own_cap"], 4), dtype=torch.float32, device=dev)
-            normals_d = gat["own"][:n_local]
-            # all-gather (NCCL ring / NVLS collective over NVSwitch) instead of a rooted gather: the
-            # rooted gather is a set of point-to-point send/recv pairs and measured ~8x slower here
-            gat["own_recv"] = torch.empty((world * gat["own_cap"], 4), dtype=torch.float32, device=dev)
+        if gather_mode == "peer":
+            # rank 0 owns the global result arrays; every rank's kernels store into them over NVLink
+            # as they finish (normals through the local->global row map, halo rows skipped; contour
+            # nodes + per-slice offsets into the rank's region) and a stream-ordered flag per rank
+            # closes the step: no collective on the data path (parallel.PeerSink).
+            t = torch.tensor([len(planes)], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            gat["sink"] = parallel.PeerSink(ctx, dist, dev, rank, world, n_total, node_cap=max(65536, gat["own_cap"] // 4),
+                                            S_cap=int(t.item()))
+            row_map = np.where(owned, local_idx, -1).astype(np.int32)
+            with torch.cuda.stream(stream):
+                gat["row_map"] = torch.from_numpy(row_map).to(dev)
+            gat["step"] = 0
+        else:
+            with torch.cuda.stream(stream):
+                gat["own"] = torch.zeros((gat["own_cap"], 4), dtype=torch.float32, device=dev)
+                normals_d = gat["own"][:n_local]
+                # all-gather (NCCL ring / NVLS collective over NVSwitch) instead of a rooted gather: the
+                # rooted gather is a set of point-to-point send/recv pairs and measured ~8x slower here
+                gat["own_recv"] = torch.empty((world * gat["own_cap"], 4), dtype=torch.float32, device=dev)
 
     def ensure_node_buffers(tn):
         if "nodes" in gat and gat["node_cap"] >= tn:
@@ -257,13 +274,28 @@ def run_ours(args):
             gat["nodes"] = torch.zeros((3, gat["node_cap"] + 1), dtype=torch.float64, device=dev)  # [:,0] = node count
             gat["nodes_recv"] = torch.empty((world * 3, gat["node_cap"] + 1), dtype=torch.float64, device=dev)
 
-    do_gather = not os.environ.get("PPP_BENCH_NOGATHER")
+    do_gather = gather_mode != "none"
 
     def dev_step(gather=True):
         gather = gather and do_gather
         c = api.Cloud(ctx, device_ptr=raw_d.data_ptr(), n=n_local, stride_bytes=32)
-        c.dev_normals_knn(K_NEIGH, normals_d.data_ptr(), nstride * 4, idx_ptr=idx_d.data_ptr())
-        if world > 1 and gather:
+        if world > 1 and gather_mode == "peer":
+            sink = gat["sink"]
+            c.dev_set_normal_row_map(gat["row_map"].data_ptr())
+            c.dev_normals_knn(K_NEIGH, sink.normals_ptr, 16, idx_ptr=idx_d.data_ptr())
+            sink.attach(c)
+            res = c.dev_slice_contours(planes, PAIRING, HALF_WIDTH, True)
+            if res["total_nodes"] > sink.node_cap:
+                raise SystemExit("bench.py: %d contour nodes exceed the peer region (%d)" % (res["total_nodes"], sink.node_cap))
+            gat["step"] += 1
+            sink.delivered(gat["step"])
+            last["nodes"] = res["total_nodes"]
+            last["members"] = res["total_members"]
+            c.close()
+            return
+        else:
+            c.dev_normals_knn(K_NEIGH, normals_d.data_ptr(), nstride * 4, idx_ptr=idx_d.data_ptr())
+        if world > 1 and gather and gather_mode == "nccl":
             # results to rank 0 (the reference's Spline / path connection run on the host of rank 0):
             # owned normals in original index order; issued before the slicing so the NVLink
             # transfer (NCCL's own stream) overlaps the band / contour kernels
@@ -327,6 +359,7 @@ def run_ours(args):
     launches = ctx.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     assert regions == args.steps
+    own_ms = total_ms
     if dist is not None:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -347,6 +380,10 @@ def run_ours(args):
     sync_all()
     prof = ctx.kernel_profile_read(reset=True)
     ctx.kernel_profile(False)
+    if os.environ.get("PPP_BENCH_VERBOSE"):
+        sys.stderr.write("[rank %d] own step %.4f ms; n_local %d; kernels %s\n" % (
+            rank, own_ms / args.steps, n_local,
+            {k: round(v[0] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:4]}))
 
     # ---- end to end through the host-pointer C ABI (pinned buffers) ----
     pin_cloud = ctx.pinned_empty(cloud.shape, np.float32)
@@ -382,6 +419,40 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = units * args.steps / e2e_s
+
+    # ---- untimed check of the peer-store delivery: rank 0's global arrays vs every rank's own results ----
+    sink_mismatch = None
+    if world > 1 and gather_mode == "peer":
+        sync_all()
+        sink = gat["sink"]
+        S_list = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(S_list, torch.tensor([len(planes)], dtype=torch.int64, device=dev))
+        full = torch.empty((n_total, 4), dtype=torch.float32, device=dev)
+        node_sum = torch.zeros((world, 4), dtype=torch.float64, device=dev)    # per rank: count, sum y, sum x, sum z
+        if rank == 0:
+            normals_g, per_rank = sink.read([int(v.item()) for v in S_list])
+            full.copy_(torch.from_numpy(normals_g))
+            for r, (off, yy, xx, zz) in enumerate(per_rank):
+                node_sum[r] = torch.tensor([float(off[-1]), yy.sum(), xx.sum(), zz.sum()], dtype=torch.float64)
+        dist.broadcast(full, 0)
+        dist.broadcast(node_sum, 0)
+        c = api.Cloud(ctx, device_ptr=raw_d.data_ptr(), n=n_local, stride_bytes=32)
+        with torch.cuda.stream(stream):
+            mine = torch.empty((n_local, 4), dtype=torch.float32, device=dev)
+        stream.synchronize()
+        c.dev_normals_knn(K_NEIGH, mine.data_ptr(), 16, idx_ptr=idx_d.data_ptr())
+        res = c.dev_slice_contours(planes, PAIRING, HALF_WIDTH, True)
+        stream.synchronize()
+        tn = res["total_nodes"]
+        loc = [float(tn)] + [float(ctx.download(res[k], (tn,), np.float64).sum()) for k in ("y", "x", "z")]
+        c.close()
+        got = full[torch.from_numpy(local_idx[owned]).to(dev)].view(torch.int32)
+        bad = (got != mine[owned_d].view(torch.int32)).sum().to(torch.int64)
+        bad += int(not np.array_equal(np.asarray(loc), node_sum[rank].cpu().numpy()))
+        dist.all_reduce(bad)
+        sink_mismatch = int(bad.item())
+        del full, mine, got
+        sink.close()
 
     if rank == 0:
         peak, peak_src = read_peaks()
@@ -431,6 +502,11 @@ def run_ours(args):
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "points_local": n_local, "band_members": last.get("members"), "contour_nodes": last.get("nodes"),
         }
+        if world > 1:
+            line["config"]["normals_to_rank0"] = {"peer": "NVLink stores from the search kernel into rank 0's array",
+                                                  "nccl": "all_gather after the kernel", "none": "not gathered"}[gather_mode]
+            if sink_mismatch is not None:
+                line["peer_store_mismatches"] = sink_mismatch
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

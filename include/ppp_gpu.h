@@ -191,6 +191,32 @@ int ppp_dev_slice_contours(ppp_cloud* cloud, const float* plane_x_host, int S, f
 /* Optional: caller-owned device buffers (cap doubles each) that ppp_dev_slice_contours fills
  * instead of the cloud-owned ones whenever the node total fits (e.g. an NCCL gather buffer). */
 int ppp_dev_set_contour_buffers(ppp_cloud* cloud, double* y_dev, double* x_dev, double* z_dev, int64_t cap);
+/* Optional: device buffer (cap_entries int64) that also receives the S+1 per-slice node offsets
+ * of every ppp_dev_slice_contours call (entry S = node total), e.g. inside a peer buffer.       */
+int ppp_dev_set_contour_offsets_buffer(ppp_cloud* cloud, int64_t* offsets_dev, int64_t cap_entries);
+/* Stream-ordered 32-bit flags (stream memory operations, no kernel launch).  signal: *flag = value
+ * once all earlier work of the context's stream has finished; wait: later work of the stream is
+ * held until *flag >= value.  With the flag in a peer buffer the pair is the completion signal for
+ * results delivered to another GPU by plain NVLink stores.                                        */
+int ppp_dev_signal(ppp_ctx* ctx, uint32_t* flag_dev, uint32_t value);
+int ppp_dev_wait(ppp_ctx* ctx, const uint32_t* flag_dev, uint32_t value);
+/* Optional: where the normal record of local row i goes: record row_map_dev[i] of the normals buffer
+ * (negative: not stored).  With a buffer obtained from ppp_peer_buffer_open the search kernel
+ * stores each finished normal straight into another GPU's memory over NVLink, so a slab's owned
+ * rows land in rank 0's global array while the kernel runs and no gather collective follows
+ * (SURVEY.md §8e "Gather").  NULL restores the identity.  The map must stay valid while in use.  */
+int ppp_dev_set_normal_row_map(ppp_cloud* cloud, const int32_t* row_map_dev);
+/* Device buffers that the GPUs of OTHER processes on this node can write (CUDA IPC over
+ * NVLink/NVSwitch).  alloc: owner side, returns the pointer and a 64-byte handle to ship to the peers
+ * (any transport, e.g. a torch.distributed broadcast); the memory is zero-filled.  open/close: peer
+ * side; free: owner side.                                                                         */
+#define PPP_PEER_HANDLE_BYTES 64
+int ppp_peer_buffer_alloc(ppp_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char handle[PPP_PEER_HANDLE_BYTES]);
+int ppp_peer_buffer_open(ppp_ctx* ctx, const unsigned char handle[PPP_PEER_HANDLE_BYTES], void** dev_ptr);
+int ppp_peer_buffer_close(ppp_ctx* ctx, void* dev_ptr);
+int ppp_peer_buffer_free(ppp_ctx* ctx, void* dev_ptr);
+/* stream-ordered device -> host copy of a raw device range, then synchronise */
+int ppp_dev_download(ppp_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
 /* original index of the point at sorted position p (device array of n int32) */
 const int32_t* ppp_dev_sorted_order(ppp_cloud* cloud);
 

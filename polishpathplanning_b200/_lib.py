@@ -64,6 +64,15 @@ SIGNATURES = {
     "ppp_dev_slice_contours": (C.c_int, [_vp, _vp, C.c_int, C.c_float, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp),
                                          C.POINTER(_vp), C.POINTER(_vp), _i64p, _i64p]),
     "ppp_dev_set_contour_buffers": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int64]),
+    "ppp_dev_set_contour_offsets_buffer": (C.c_int, [_vp, _vp, C.c_int64]),
+    "ppp_dev_signal": (C.c_int, [_vp, _vp, C.c_uint32]),
+    "ppp_dev_wait": (C.c_int, [_vp, _vp, C.c_uint32]),
+    "ppp_dev_set_normal_row_map": (C.c_int, [_vp, _vp]),
+    "ppp_peer_buffer_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(C.c_void_p), _vp]),
+    "ppp_peer_buffer_open": (C.c_int, [_vp, _vp, C.POINTER(C.c_void_p)]),
+    "ppp_peer_buffer_close": (C.c_int, [_vp, _vp]),
+    "ppp_peer_buffer_free": (C.c_int, [_vp, _vp]),
+    "ppp_dev_download": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "ppp_dev_sorted_order": (_vp, [_vp]),
 }
 

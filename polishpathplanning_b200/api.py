@@ -77,6 +77,40 @@ class Context:
             out[name] = (float(ms), int(cnt))
         return out
 
+    # -- buffers the GPUs of other processes can write (CUDA IPC over NVLink / NVSwitch) ------------
+    def peer_buffer_alloc(self, nbytes):
+        """Owner side: returns (device pointer, 64-byte handle as bytes)."""
+        p = C.c_void_p(0)
+        h = (C.c_ubyte * 64)()
+        check(self.lib.ppp_peer_buffer_alloc(self._h, int(nbytes), C.byref(p), h))
+        return p.value, bytes(h)
+
+    def peer_buffer_open(self, handle):
+        p = C.c_void_p(0)
+        h = (C.c_ubyte * 64).from_buffer_copy(bytes(handle))
+        check(self.lib.ppp_peer_buffer_open(self._h, h, C.byref(p)))
+        return p.value
+
+    def peer_buffer_close(self, ptr):
+        check(self.lib.ppp_peer_buffer_close(self._h, _vp(ptr)))
+
+    def peer_buffer_free(self, ptr):
+        check(self.lib.ppp_peer_buffer_free(self._h, _vp(ptr)))
+
+    def signal(self, flag_ptr, value):
+        """*flag = value after all earlier work of the context's stream (no kernel launch)."""
+        check(self.lib.ppp_dev_signal(self._h, _vp(flag_ptr), int(value)))
+
+    def wait(self, flag_ptr, value):
+        """Later work of the context's stream waits until *flag >= value."""
+        check(self.lib.ppp_dev_wait(self._h, _vp(flag_ptr), int(value)))
+
+    def download(self, dev_ptr, shape, dtype):
+        """Device range -> new numpy array (synchronises)."""
+        out = np.empty(shape, dtype)
+        check(self.lib.ppp_dev_download(self._h, _ptr(out), _vp(dev_ptr), out.nbytes))
+        return out
+
     def pinned_empty(self, shape, dtype):
         """numpy array over pinned host memory from ppp_host_alloc (freed with the array)."""
         dtype = np.dtype(dtype)
@@ -295,6 +329,13 @@ class Cloud:
         vp = np.asarray(viewpoint, np.float32)
         check(self.lib.ppp_dev_normals_radius(self._h, float(r), vp.ctypes.data_as(_lib._f32p), flags, int(first),
                                               int(count), _vp(normals_ptr), int(normal_stride_bytes)))
+
+    def dev_set_normal_row_map(self, map_ptr):
+        """Device int32 map row -> record of the normals buffer (negative: skip); None = identity."""
+        check(self.lib.ppp_dev_set_normal_row_map(self._h, _vp(map_ptr) if map_ptr else None))
+
+    def dev_set_contour_offsets_buffer(self, off_ptr, cap_entries):
+        check(self.lib.ppp_dev_set_contour_offsets_buffer(self._h, _vp(off_ptr) if off_ptr else None, int(cap_entries)))
 
     def dev_set_contour_buffers(self, y_ptr, x_ptr, z_ptr, cap):
         check(self.lib.ppp_dev_set_contour_buffers(self._h, _vp(y_ptr) if y_ptr else None, _vp(x_ptr) if x_ptr else None,

@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "ppp_internal.cuh"
+#include <cstring>
+#include <cuda.h>
 
 static thread_local char g_err[1024] = "";
 
@@ -245,6 +247,115 @@ int ppp_dev_set_contour_buffers(ppp_cloud* c, double* y_dev, double* x_dev, doub
   REQUIRE(c, "cloud is NULL");
   REQUIRE((y_dev && x_dev && z_dev && cap > 0) || (!y_dev && !x_dev && !z_dev), "give all three buffers or none");
   c->ext_y = y_dev; c->ext_x = x_dev; c->ext_z = z_dev; c->ext_cap = y_dev ? cap : 0;
+  return PPP_OK;
+}
+
+int ppp_dev_set_contour_offsets_buffer(ppp_cloud* c, int64_t* offsets_dev, int64_t cap_entries) {
+  REQUIRE(c, "cloud is NULL");
+  REQUIRE((offsets_dev && cap_entries > 0) || (!offsets_dev && cap_entries == 0), "give a buffer and its capacity, or neither");
+  c->ext_off = offsets_dev; c->ext_off_cap = cap_entries;
+  return PPP_OK;
+}
+
+// Stream-ordered 32-bit flags (stream memory operations, no kernel): signal = write `value` once all
+// earlier work of the context's stream has finished; wait = hold later work of the stream until
+// *flag >= value.  The flag may live in a peer buffer, which makes the pair a cross-GPU completion
+// signal for data delivered with plain NVLink stores.
+typedef CUresult (*stream_write32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*stream_wait32_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static int driver_entry(const char* name, void** fn) {
+  cudaDriverEntryPointQueryResult qr;
+  cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &qr);
+  if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !*fn) {
+    ppp_set_error("driver entry point %s unavailable", name);
+    return PPP_ERR_UNSUPPORTED;
+  }
+  return PPP_OK;
+}
+
+int ppp_dev_signal(ppp_ctx* ctx, uint32_t* flag_dev, uint32_t value) {
+  REQUIRE(ctx && flag_dev, "NULL argument");
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  static stream_write32_fn fn = nullptr;
+  if (!fn) PPP_TRY(driver_entry("cuStreamWriteValue32", (void**)&fn));
+  CUresult r = fn((CUstream)ctx->stream, (CUdeviceptr)(uintptr_t)flag_dev, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+  if (r != CUDA_SUCCESS) { ppp_set_error("cuStreamWriteValue32 failed (%d)", (int)r); return PPP_ERR_CUDA; }
+  return PPP_OK;
+}
+
+int ppp_dev_wait(ppp_ctx* ctx, const uint32_t* flag_dev, uint32_t value) {
+  REQUIRE(ctx && flag_dev, "NULL argument");
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  static stream_wait32_fn fn = nullptr;
+  if (!fn) PPP_TRY(driver_entry("cuStreamWaitValue32", (void**)&fn));
+  CUresult r = fn((CUstream)ctx->stream, (CUdeviceptr)(uintptr_t)flag_dev, value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) { ppp_set_error("cuStreamWaitValue32 failed (%d)", (int)r); return PPP_ERR_CUDA; }
+  return PPP_OK;
+}
+
+int ppp_dev_set_normal_row_map(ppp_cloud* c, const int32_t* row_map_dev) {
+  REQUIRE(c, "cloud is NULL");
+  c->nmap = row_map_dev;
+  return PPP_OK;
+}
+
+// Buffers other processes' GPUs can write: plain cudaMalloc memory exported as a CUDA IPC handle.
+int ppp_peer_buffer_alloc(ppp_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char handle[PPP_PEER_HANDLE_BYTES]) {
+  REQUIRE(ctx && dev_ptr && handle && bytes > 0, "bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == PPP_PEER_HANDLE_BYTES, "handle size");
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  PPP_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    ppp_set_error("peer buffer (memset / cudaIpcGetMemHandle): %s", cudaGetErrorString(e));
+    return PPP_ERR_CUDA;
+  }
+  memcpy(handle, &h, sizeof(h));
+  *dev_ptr = p;
+  return PPP_OK;
+}
+
+int ppp_peer_buffer_open(ppp_ctx* ctx, const unsigned char handle[PPP_PEER_HANDLE_BYTES], void** dev_ptr) {
+  REQUIRE(ctx && dev_ptr && handle, "bad argument");
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  PPP_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return PPP_OK;
+}
+
+int ppp_peer_buffer_close(ppp_ctx* ctx, void* dev_ptr) {
+  REQUIRE(ctx, "context is NULL");
+  if (!dev_ptr) return PPP_OK;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  PPP_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return PPP_OK;
+}
+
+int ppp_peer_buffer_free(ppp_ctx* ctx, void* dev_ptr) {
+  REQUIRE(ctx, "context is NULL");
+  if (!dev_ptr) return PPP_OK;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  PPP_CUDA(cudaFree(dev_ptr));
+  return PPP_OK;
+}
+
+int ppp_dev_download(ppp_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes) {
+  REQUIRE(ctx && (bytes == 0 || (host_dst && dev_src)), "bad argument");
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  if (bytes) PPP_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
   return PPP_OK;
 }
 

@@ -34,6 +34,7 @@ struct SearchParams {
   float* d2_out;
   const int64_t* offsets;
   float* normals;
+  const int32_t* nmap;  // optional row map for the normal records (row -> record, < 0: not stored)
   int nsf;
   float vpx, vpy, vpz;
   unsigned flags;
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
       }
       normal_from_accumulators(acc, cnt, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
     }
-    store_normal(P.normals, row, P.nsf, o);
+    store_normal(P.normals, P.nmap, row, P.nsf, o);
   }
 }
 
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
         }
         normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
       }
-      store_normal(P.normals, row, P.nsf, o);
+      store_normal(P.normals, P.nmap, row, P.nsf, o);
     }
   } else {
     // long lists: park the sorted keys in this thread's shared-memory column (K slots) and walk
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
         }
         normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
       }
-      store_normal(P.normals, row, P.nsf, o);
+      store_normal(P.normals, P.nmap, row, P.nsf, o);
     }
   }
 }
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
       }
       normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
     }
-    store_normal(P.normals, row, P.nsf, o);
+    store_normal(P.normals, P.nmap, row, P.nsf, o);
   }
 }
 
@@ -693,7 +694,7 @@ __global__ void __launch_bounds__(128, 6) k_radius_normals32(SearchParams P) {
     }
     normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
   }
-  store_normal(P.normals, row, P.nsf, o);
+  store_normal(P.normals, P.nmap, row, P.nsf, o);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -817,7 +818,7 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
       }
       normal_from_accumulators(acc, have, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
     }
-    if (lane == 0) store_normal(P.normals, row, P.nsf, o);
+    if (lane == 0) store_normal(P.normals, P.nmap, row, P.nsf, o);
   }
   __syncwarp();
   }  // slot loop
@@ -890,7 +891,7 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_radius_warp(SearchParams P
     float o[4];
     if (m < 3) o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
     else normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
-    if (lane == 0) store_normal(P.normals, row, P.nsf, o);
+    if (lane == 0) store_normal(P.normals, P.nmap, row, P.nsf, o);
     __syncwarp();
   }
 }
@@ -1067,7 +1068,7 @@ __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
 // Self-mode outputs are written by original index of the *indexed* points only; rows of
 // non-finite points get their defaults here (idx -1 / d2 inf / NaN normals).
 __global__ void k_default_rows(const float4* __restrict__ xyz4, int64_t n, int cap, int32_t* idx_out, float* d2_out,
-                               float* normals, int nsf) {
+                               float* normals, int nsf, const int32_t* __restrict__ nmap) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = __ldg(xyz4 + i);
@@ -1079,7 +1080,7 @@ __global__ void k_default_rows(const float4* __restrict__ xyz4, int64_t n, int c
     }
   if (normals) {
     float o[4] = {CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F};
-    store_normal(normals, i, nsf, o);
+    store_normal(normals, nmap, i, nsf, o);
   }
 }
 
@@ -1195,12 +1196,12 @@ int knn_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq
   P.g = gs.v; P.xyz4 = c->xyz4; P.q = q_dev; P.q_sf = q_stride_f; P.nq = nq; P.first = first;
   P.cap = k; P.kk = (int)std::min<int64_t>(k, c->n_finite); P.mode = 0; P.R0 = 2; P.r2 = 0;
   P.idx_out = idx_dev; P.d2_out = d2_dev; P.offsets = nullptr;
-  P.normals = with_normals ? normals_dev : nullptr; P.nsf = normal_stride_f;
+  P.normals = with_normals ? normals_dev : nullptr; P.nsf = normal_stride_f; P.nmap = c->nmap;
   P.vpx = vp ? vp[0] : 0; P.vpy = vp ? vp[1] : 0; P.vpz = vp ? vp[2] : 0; P.flags = flags;
   if (!q_dev && c->n_finite < c->n && first == 0) {
     unsigned blocks = (unsigned)((c->n + 255) / 256);
     PPP_LAUNCH(ctx, "default_rows", k_default_rows, blocks, 256, 0, (const float4*)c->xyz4, c->n, k, idx_dev, d2_dev,
-               P.normals, normal_stride_f);
+               P.normals, normal_stride_f, c->nmap);
     PPP_CHECK_LAUNCH();
   }
   if (k <= 64 && nq > 0 && !getenv("PPP_KNN_GENERIC")) return launch_knn_fast(c, P);
@@ -1252,12 +1253,12 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int6
   SearchParams P{};
   P.g = gs.v; P.xyz4 = c->xyz4; P.q = nullptr; P.nq = count; P.first = first;
   P.mode = 1; P.r2 = r2; P.R0 = radius_rings(gs.v, std::sqrt((double)r2));
-  P.normals = normals_dev; P.nsf = normal_stride_f;
+  P.normals = normals_dev; P.nsf = normal_stride_f; P.nmap = c->nmap;
   P.vpx = vp ? vp[0] : 0; P.vpy = vp ? vp[1] : 0; P.vpz = vp ? vp[2] : 0; P.flags = flags;
   if (c->n_finite < c->n && first == 0) {
     unsigned blocks = (unsigned)((c->n + 255) / 256);
     PPP_LAUNCH(ctx, "default_rows", k_default_rows, blocks, 256, 0, (const float4*)c->xyz4, c->n, 0, (int32_t*)nullptr,
-               (float*)nullptr, normals_dev, normal_stride_f);
+               (float*)nullptr, normals_dev, normal_stride_f, c->nmap);
     PPP_CHECK_LAUNCH();
   }
   if (count <= 0) return PPP_OK;

@@ -184,8 +184,15 @@ __device__ __forceinline__ void accumulate_point(float acc[9], float x, float y,
 }
 
 // Store one normal record. stride_f == 4: {nx,ny,nz,curv}; stride_f >= 8: pcl::Normal layout
-// {nx,ny,nz,0, curv,0,0,0}; other strides: nx,ny,nz at 0..2, curvature at 3.
-__device__ __forceinline__ void store_normal(float* base, int64_t row, int stride_f, const float o[4]) {
+// {nx,ny,nz,0, curv,0,0,0}; other strides: nx,ny,nz at 0..2, curvature at 3.  map (optional): record
+// number of each row, negative = the row is not stored (halo rows of a slab whose records go to
+// another GPU's buffer over NVLink).
+__device__ __forceinline__ void store_normal(float* base, const int32_t* __restrict__ map, int64_t row, int stride_f,
+                                             const float o[4]) {
+  if (map) {
+    row = __ldg(map + row);
+    if (row < 0) return;
+  }
   float* p = base + row * (int64_t)stride_f;
   if (stride_f == 8) {
     reinterpret_cast<float4*>(p)[0] = make_float4(o[0], o[1], o[2], 0.0f);

@@ -124,6 +124,9 @@ struct ppp_cloud {
   int c_S_cap = 0;
   double *ext_y = nullptr, *ext_x = nullptr, *ext_z = nullptr;  // optional caller-owned node buffers
   int64_t ext_cap = 0;
+  const int32_t* nmap = nullptr;   // ppp_dev_set_normal_row_map
+  int64_t* ext_off = nullptr;      // ppp_dev_set_contour_offsets_buffer
+  int64_t ext_off_cap = 0;
   double *out_y = nullptr, *out_x = nullptr, *out_z = nullptr;  // where the last call wrote the nodes
 };
 

@@ -710,6 +710,8 @@ static int finish_nodes(ppp_cloud* c, int S, const int64_t* band_off_dev, const 
     PPP_TRY(dev_alloc(ctx, &c->c_y, cap)); PPP_TRY(dev_alloc(ctx, &c->c_x, cap)); PPP_TRY(dev_alloc(ctx, &c->c_z, cap));
     c->c_cap = (int64_t)cap;
   }
+  if (c->ext_off && c->ext_off_cap >= (int64_t)S + 1)   // per-slice node offsets for a remote consumer
+    PPP_CUDA(cudaMemcpyAsync(c->ext_off, c->c_node_off, ((size_t)S + 1) * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
   c->out_y = ext ? c->ext_y : c->c_y;
   c->out_x = ext ? c->ext_x : c->c_x;
   c->out_z = ext ? c->ext_z : c->c_z;

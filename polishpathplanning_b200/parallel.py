@@ -183,3 +183,91 @@ def redistribute(dist, chunk, global_start, rank, world, halo, bins=4096):
     local[:, IDX_COL] = 0.0
     local[:, OWNED_COL] = 0.0
     return local, g, owned, cuts
+
+
+# -------------------------------------------------------------------------------------------------
+# Result delivery without a collective: rank 0 owns the global result arrays, every rank's kernels
+# store into them over NVLink (CUDA IPC mapping), and a stream-ordered flag per rank tells rank 0
+# when a step's results have landed.
+# -------------------------------------------------------------------------------------------------
+class PeerSink:
+    """Global result arrays on rank 0, written in place by all ranks.
+
+    Layout of the one peer buffer (rank 0's HBM):
+      normals   n_total x 16 B   {nx, ny, nz, curvature} in ORIGINAL index order
+      per rank  offsets (S_cap + 1) int64, then y / x / z: node_cap doubles each
+      flags     world x 128 B    flag r = number of the last step rank r has delivered
+
+    Every rank passes `normals_ptr` with its local->global row map to the search
+    (Cloud.dev_set_normal_row_map + dev_normals_*), calls attach(cloud) before dev_slice_contours and
+    delivered(step) after it.  On rank 0, delivered() also makes the stream wait for every peer's flag,
+    so work queued behind it (and a host sync) sees all ranks' results of that step.  There is no ack
+    back to the writers: a consumer that reads while the next step runs must double-buffer.
+    """
+
+    def __init__(self, ctx, dist, device, rank, world, n_total, node_cap, S_cap):
+        import torch
+        self.ctx, self.rank, self.world = ctx, rank, world
+        # one layout for all ranks: capacities are the maxima over the ranks' requests
+        caps = torch.tensor([int(n_total), int(node_cap), int(S_cap)], dtype=torch.int64, device=device)
+        dist.all_reduce(caps, op=dist.ReduceOp.MAX)
+        self.n_total, self.node_cap, self.S_cap = (int(v) for v in caps.tolist())
+        a256 = lambda v: (int(v) + 255) // 256 * 256
+        self._normals_bytes = a256(self.n_total * 16)
+        self._off_bytes = a256((self.S_cap + 1) * 8)
+        self._arr_bytes = a256(self.node_cap * 8)
+        self._region_bytes = self._off_bytes + 3 * self._arr_bytes
+        self._flags_at = self._normals_bytes + world * self._region_bytes
+        total = self._flags_at + world * 128
+        hbuf = torch.zeros(64, dtype=torch.uint8, device=device)
+        if rank == 0:
+            self.base, handle = ctx.peer_buffer_alloc(total)      # zero-filled
+            hbuf.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+        dist.broadcast(hbuf, 0)
+        if rank != 0:
+            self.base = ctx.peer_buffer_open(hbuf.cpu().numpy().tobytes())
+        self.normals_ptr = self.base
+        self._dist = dist
+
+    def region(self, r):
+        at = self.base + self._normals_bytes + r * self._region_bytes
+        return {"off": at, "y": at + self._off_bytes, "x": at + self._off_bytes + self._arr_bytes,
+                "z": at + self._off_bytes + 2 * self._arr_bytes}
+
+    def flag(self, r):
+        return self.base + self._flags_at + 128 * r
+
+    def attach(self, cloud):
+        """Route the contour nodes + per-slice offsets of `cloud` into this rank's region."""
+        g = self.region(self.rank)
+        cloud.dev_set_contour_buffers(g["y"], g["x"], g["z"], self.node_cap)
+        cloud.dev_set_contour_offsets_buffer(g["off"], self.S_cap + 1)
+
+    def delivered(self, step):
+        """Stream-ordered: this rank's results of `step` (1, 2, ...) are in place."""
+        self.ctx.signal(self.flag(self.rank), step)
+        if self.rank == 0:
+            for r in range(1, self.world):
+                self.ctx.wait(self.flag(r), step)
+
+    def read(self, S_per_rank):
+        """Rank 0, after a host sync: (normals (n_total, 4), [(offsets, y, x, z) per rank])."""
+        assert self.rank == 0
+        normals = self.ctx.download(self.normals_ptr, (self.n_total, 4), np.float32)
+        out = []
+        for r in range(self.world):
+            g = self.region(r)
+            off = self.ctx.download(g["off"], (S_per_rank[r] + 1,), np.int64)
+            n = int(off[-1])
+            out.append((off, self.ctx.download(g["y"], (n,), np.float64), self.ctx.download(g["x"], (n,), np.float64),
+                        self.ctx.download(g["z"], (n,), np.float64)))
+        return normals, out
+
+    def close(self):
+        """Collective: peers unmap, then rank 0 frees."""
+        if self.rank != 0:
+            self.ctx.peer_buffer_close(self.base)
+        self._dist.barrier()
+        if self.rank == 0:
+            self.ctx.peer_buffer_free(self.base)
+        self.base = None

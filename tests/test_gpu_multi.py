@@ -19,3 +19,4 @@ def test_two_rank_nccl_redistribution_matches_single_gpu():
                        capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "normals_bitexact=True knn_ids=True contours=True" in r.stdout
+    assert "peer_normals=True peer_contours=True" in r.stdout      # NVLink-store delivery (parallel.PeerSink)

@@ -48,8 +48,29 @@ def main():
     counts = np.diff(off)
     node_plane = np.repeat(pos, counts).astype(np.int64)
     res2 = parallel.gather_to_rank0(dist, [node_plane, y, x, z], rank, world, device=dev)
+    # second delivery path: no collective; every rank's kernels store into rank 0's global arrays over
+    # NVLink (parallel.PeerSink), two steps to exercise the per-step flags
+    smax = torch.tensor([len(pos)], dtype=torch.int64, device=dev)
+    dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+    sink = parallel.PeerSink(ctx, dist, dev, rank, world, n, node_cap=max(4096, nl // 2), S_cap=int(smax.item()))
+    row_map = torch.where(owned, g, torch.full_like(g, -1)).to(torch.int32).contiguous()
+    torch.cuda.synchronize()
+    c.dev_set_normal_row_map(row_map.data_ptr())
+    for step in (1, 2):
+        c.dev_normals_knn(k, sink.normals_ptr, 16, idx_ptr=idx.data_ptr())
+        sink.attach(c)
+        r_dev = c.dev_slice_contours(planes[pos], "B")
+        assert r_dev["total_nodes"] <= sink.node_cap
+        sink.delivered(step)
+    c.dev_set_normal_row_map(None)
+    c.dev_set_contour_buffers(None, None, None, 0)
+    c.dev_set_contour_offsets_buffer(None, 0)
+    ctx.sync()
+    all_pos = [None] * world
+    dist.all_gather_object(all_pos, pos.tolist())
     ok = True
     if rank == 0:
+        peer_n, peer_nodes = sink.read([len(p_) for p_ in all_pos])
         full = api.Cloud(ctx, cloud)
         ref_n, ref_i = full.normals_knn(k, stride_floats=4, return_idx=True)
         got_n = parallel.assemble_normals(n, 4, [(r[0], r[1]) for r in res])
@@ -64,13 +85,19 @@ def main():
             o = np.concatenate([[0], np.cumsum([(pl == s).sum() for s in ppos])]).astype(np.int64)
             per_rank.append((ppos.astype(np.int64), o, yy, xx, zz))
         goff, gy, gx, gz = parallel.assemble_contours(S, per_rank)
+        poff, py, px, pz = parallel.assemble_contours(
+            S, [(np.asarray(all_pos[r], np.int64),) + peer_nodes[r] for r in range(world)])
+        peer_ok_n = np.array_equal(peer_n.view(np.uint32), ref_n.view(np.uint32))
+        peer_ok_c = np.array_equal(poff, ro) and np.array_equal(py, ry) and np.array_equal(px, rx) and np.array_equal(pz, rz)
+        print("MULTI_GPU_CHECK peer_normals=%s peer_contours=%s" % (peer_ok_n, peer_ok_c), flush=True)
         ok = (np.array_equal(got_n.view(np.uint32), ref_n.view(np.uint32)) and np.array_equal(got_i, ref_i.astype(np.int64))
-              and np.array_equal(goff, ro) and np.array_equal(gy, ry) and np.array_equal(gz, rz))
+              and np.array_equal(goff, ro) and np.array_equal(gy, ry) and np.array_equal(gz, rz) and peer_ok_n and peer_ok_c)
         print("MULTI_GPU_CHECK world=%d n=%d normals_bitexact=%s knn_ids=%s contours=%s" % (
             world, n, np.array_equal(got_n.view(np.uint32), ref_n.view(np.uint32)), np.array_equal(got_i, ref_i.astype(np.int64)),
             np.array_equal(goff, ro) and np.array_equal(gy, ry) and np.array_equal(gz, rz)), flush=True)
         full.close()
     c.close()
+    sink.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()
