@@ -65,6 +65,7 @@ int ppp_create(int device, ppp_ctx** out) {
   PPP_CUDA(cudaStreamCreateWithPriority(&ctx->main_stream, cudaStreamNonBlocking, prio_lo));
   PPP_CUDA(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi));
   PPP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  PPP_CUDA(cudaHostAlloc(&ctx->fetch_host, FETCH_BYTES, cudaHostAllocMapped));
   ctx->stream = ctx->main_stream;
   cudaMemPool_t pool;
   PPP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -86,6 +87,7 @@ void ppp_destroy(ppp_ctx* ctx) {
   cudaStreamDestroy(ctx->main_stream);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->fetch_host) cudaFreeHost(ctx->fetch_host);
   delete ctx;
 }
 
@@ -646,6 +648,10 @@ int ppp_normals_and_contours(ppp_cloud* c, int k, double radius, const float vp[
       PPP_CUDA(cudaEventRecord(ev, ctx->stream));
       PPP_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
       PPP_CUDA(cudaMemcpyAsync(normals_out, n_d, nbytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+      // Host-pointer path: the long pole after the search is the normals' device->host copy, so the
+      // search must finish as early as possible.  Hold the slicing chain (auxiliary stream) until the
+      // search is done; it then runs in the shadow of the copy instead of competing for the SMs.
+      PPP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ev, 0));
     }
   }
   if (st == PPP_OK) st = ppp_slice_contours(c, plane_x, S, half_width, truncate_center, pairing_mode, node_offsets, y, x, z, node_cap);

@@ -159,8 +159,7 @@ int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes) {
     PPP_CHECK_LAUNCH();
   }
   BBoxAcc h;
-  PPP_CUDA(cudaMemcpyAsync(&h, acc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  PPP_TRY(fetch_small(ctx, acc, sizeof(h), &h));
   dev_free(ctx, acc);
   c->n_finite = (int64_t)h.n_finite;
   for (int d = 0; d < 3; d++) {
@@ -245,5 +244,24 @@ int cloud_get_grid(ppp_cloud* c, double h, GridStore** out) {
   PPP_CUDA(cudaEventRecord(gs.ready, ctx->stream));
   c->grids.push_back(gs);
   *out = &c->grids.back();
+  return PPP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_fetch_small(const unsigned* __restrict__ src, unsigned* __restrict__ dst, int words) {
+  for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+}
+
+int fetch_small(ppp_ctx* ctx, const void* dev_src, size_t bytes, void* host_dst) {
+  if (bytes == 0) { PPP_CUDA(cudaStreamSynchronize(ctx->stream)); return PPP_OK; }
+  if (bytes > FETCH_BYTES || (bytes & 3) || ((uintptr_t)dev_src & 3) || !ctx->fetch_host) {
+    PPP_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PPP_OK;
+  }
+  PPP_LAUNCH(ctx, "fetch_small", k_fetch_small, 1, 256, 0, (const unsigned*)dev_src, (unsigned*)ctx->fetch_host, (int)(bytes / 4));
+  PPP_CHECK_LAUNCH();
+  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(host_dst, ctx->fetch_host, bytes);
   return PPP_OK;
 }

@@ -1179,8 +1179,7 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
   }
   if (st == PPP_OK && getenv("PPP_DEBUG")) {
     int32_t n_redo = 0;
-    cudaMemcpyAsync(&n_redo, redo, 4, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
+    fetch_small(ctx, redo, 4, &n_redo);
     fprintf(stderr, "[ppp] knn fast path: %lld queries, %d handed to the ring-expanding kernel (h=%g, R0=%d)\n",
             (long long)P.nq, n_redo, (double)P.g.h, P.R0);
   }
@@ -1228,8 +1227,7 @@ int radius_count_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, i
     PPP_CHECK_LAUNCH();
   }
   int hmx = 0;
-  PPP_CUDA(cudaMemcpyAsync(&hmx, mx, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  PPP_TRY(fetch_small(ctx, mx, 4, &hmx));
   dev_free(ctx, mx);
   return hmx;  // >= 0: maximum neighbour count (used to size the fill pass)
 }
@@ -1288,8 +1286,7 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int6
       PPP_LAUNCH(ctx, "radius_redo", k_radius_warp, blocks, WARPQ_WARPS * 32, 0, P, redo2, redo2 + 1);
       PPP_CHECK_LAUNCH();
     }
-    PPP_CUDA(cudaMemcpyAsync(&n_redo, redo2, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+    PPP_TRY(fetch_small(ctx, redo2, 4, &n_redo));
     dev_free(ctx, redo);
     redo = redo2;
     if (n_redo == 0) { dev_free(ctx, redo); return PPP_OK; }
@@ -1310,8 +1307,7 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int6
     PPP_CHECK_LAUNCH();
   }
   int hmx = 0;
-  PPP_CUDA(cudaMemcpyAsync(&hmx, mx, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  PPP_TRY(fetch_small(ctx, mx, 4, &hmx));
   dev_free(ctx, mx);
   C.cap = std::max(hmx, 1);
   int st = launch_search(c, C);

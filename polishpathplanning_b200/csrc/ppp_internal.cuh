@@ -48,6 +48,7 @@ struct ppp_ctx {
   cudaStream_t main_stream = nullptr;  // what ppp_stream() returns; timers and ppp_sync refer to it
   cudaStream_t aux_stream = nullptr;   // high priority: the slicing chain runs here, concurrently with the kNN kernel
   cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap later kernels
+  void* fetch_host = nullptr;          // mapped pinned scratch for fetch_small (FETCH_BYTES)
   std::recursive_mutex mu;
   int64_t launches = 0;
   bool profile = false;
@@ -161,6 +162,13 @@ struct LaunchScope {
   } while (0)
 
 #define PPP_CHECK_LAUNCH() PPP_CUDA(cudaGetLastError())
+
+// A few bytes of device memory to the host in stream order, then synchronise: a tiny kernel stores
+// them into mapped pinned memory.  Unlike a cudaMemcpyAsync this does not queue behind a large
+// device->host copy another stream has in flight on the copy engine (the mid-chain size fetches of
+// the slicing path otherwise stall until the normals' 32 MB copy has drained).
+constexpr size_t FETCH_BYTES = 64 * 1024;
+int fetch_small(ppp_ctx* ctx, const void* dev_src, size_t bytes, void* host_dst);
 
 template <typename T>
 int dev_alloc(ppp_ctx* ctx, T** p, size_t count) {

@@ -657,8 +657,7 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
   }
   PPP_TRY(scan_exclusive_i32_to_i64(ctx, counts, offsets, S));
   std::vector<int64_t> off_h((size_t)S + 1, 0);
-  PPP_CUDA(cudaMemcpyAsync(off_h.data(), offsets, ((size_t)S + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));  // also covers the pageable staging vectors above
+  PPP_TRY(fetch_small(ctx, offsets, ((size_t)S + 1) * sizeof(int64_t), off_h.data()));  // sync: also covers the pageable staging vectors above
   int64_t total = off_h[S];
   int32_t* idx = nullptr;
   PPP_TRY(dev_alloc(ctx, &idx, (size_t)std::max<int64_t>(total, 1)));
@@ -699,8 +698,7 @@ static int finish_nodes(ppp_cloud* c, int S, const int64_t* band_off_dev, const 
   }
   PPP_TRY(scan_exclusive_i32_to_i64(ctx, n_nodes, c->c_node_off, S));
   int64_t total = 0;
-  PPP_CUDA(cudaMemcpyAsync(&total, c->c_node_off + S, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  PPP_TRY(fetch_small(ctx, c->c_node_off + S, sizeof(int64_t), &total));
   // caller-provided device buffers (ppp_dev_set_contour_buffers) take the nodes when they are large
   // enough; otherwise the cloud-owned buffers are (re)allocated
   const bool ext = c->ext_y && c->ext_cap >= total;
