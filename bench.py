@@ -38,6 +38,8 @@ UNIT = "points/s"
 N_PER_GPU = 1_000_000
 K_NEIGH = 16
 S_PER_MILLION = 200       # 5 mm plane spacing on the 1000 mm panel
+S_FIXED_TOTAL = None      # --config cfg3: fixed plane count instead
+CONFIG_NAME, SCALING = "cfg2", "weak"
 HALF_WIDTH = 2.0
 HALO_MM = 12.0
 PAIRING = "B"             # SectPath::insert_point (src/contour_alg.cpp:165-237)
@@ -168,10 +170,19 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def total_slices(gpus):
+    return S_FIXED_TOTAL if S_FIXED_TOTAL else int(round(S_PER_MILLION * np.sqrt(gpus)))
+
+
 def workload_config(gpus):
-    return {"workload": "cfg2: %d-point synthetic freeform panel per GPU (seed 0, 1 pt/mm^2), k=%d normals + %d slices "
-                        "per million points (5 mm spacing, +-2 mm bands, SectPath pairing)" % (N_PER_GPU, K_NEIGH, S_PER_MILLION),
-            "points_per_gpu": N_PER_GPU, "k": K_NEIGH, "slices_total": int(round(S_PER_MILLION * np.sqrt(gpus))),
+    if CONFIG_NAME == "cfg3":
+        text = ("cfg3: %d-point synthetic freeform panel in total (%d per GPU, seed 0, 1 pt/mm^2), k=%d normals + %d evenly "
+                "spaced slices (+-2 mm bands, SectPath pairing)" % (N_PER_GPU * gpus, N_PER_GPU, K_NEIGH, S_FIXED_TOTAL))
+    else:
+        text = ("cfg2: %d-point synthetic freeform panel per GPU (seed 0, 1 pt/mm^2), k=%d normals + %d slices "
+                "per million points (5 mm spacing, +-2 mm bands, SectPath pairing)" % (N_PER_GPU, K_NEIGH, S_PER_MILLION))
+    return {"workload": text,
+            "points_per_gpu": N_PER_GPU, "k": K_NEIGH, "slices_total": total_slices(gpus),
             "pairing": "B(SectPath)", "partition": "x-slabs+%gmm halo" % HALO_MM if gpus > 1 else "single GPU",
             "l2": "flushed between timed steps (256 MiB write + 256 MiB read)"}
 
@@ -204,7 +215,7 @@ def run_ours(args):
 
     # ---- data (host prep is untimed: it stands for loading the PCD) ----
     n_total = N_PER_GPU * world
-    S_total = int(round(S_PER_MILLION * np.sqrt(world)))
+    S_total = total_slices(world)
     cloud_g = synth.panel(n_total, seed=0)
     planes_g = make_planes(cloud_g[:, 0].min(), cloud_g[:, 0].max(), S_total)
     if world > 1:
@@ -482,7 +493,7 @@ def run_ours(args):
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": dom_ms / dom_launches,
                     "kernel_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
         cpu = None
-        if world == 1:
+        if world == 1 and CONFIG_NAME == "cfg2":
             v_all, cores, secs = cpu_baseline(True)
             v_one, _, secs1 = cpu_baseline(False)
             cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
@@ -492,7 +503,7 @@ def run_ours(args):
                    "single_thread_value": v_one}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(e2e_bytes.get("h2d", 0)),
@@ -529,7 +540,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3"],
+                    help="cfg2 (default, the driver's contract): 1M points per GPU, k=16, 200*sqrt(N) planes, weak scaling. "
+                         "cfg3 (extra, SURVEY 8d): 10M points in TOTAL split over the GPUs, k=32, 1000 planes.")
     args = ap.parse_args()
+    if args.config == "cfg3":
+        global N_PER_GPU, K_NEIGH, S_PER_MILLION, CONFIG_NAME, SCALING, S_FIXED_TOTAL
+        N_PER_GPU = 10_000_000 // max(args.gpus, 1)
+        K_NEIGH = 32
+        S_FIXED_TOTAL = 1000
+        CONFIG_NAME, SCALING = "cfg3", "strong"
     if args.impl == "reference":
         run_reference(args)
     else:
