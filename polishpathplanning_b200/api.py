@@ -232,8 +232,8 @@ class Cloud:
         off = np.zeros(S + 1, np.int64)
         cap = int(node_cap) if node_cap else max(self.n // 4, 1024)
         while True:
-            if out is not None and out[0].shape[0] >= cap:
-                y, x, z = out
+            if out is not None and (node_cap is None or out[0].shape[0] >= cap):
+                y, x, z = out                      # caller's buffers (e.g. pinned): filled in place if large enough
                 cap = y.shape[0]
             else:
                 y = np.empty(cap, np.float64)

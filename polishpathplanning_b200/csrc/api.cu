@@ -433,12 +433,18 @@ int ppp_dev_slice_contours(ppp_cloud* c, const float* plane_x_host, int S, float
     // search: it runs on the high-priority auxiliary stream, concurrently with a kNN / normals
     // kernel still executing on the main stream; the main stream waits for it on scope exit.
     AuxScope aux(ctx, g->ready);
-    int64_t* boff = nullptr; int32_t* bidx = nullptr; float* planes = nullptr;
-    std::vector<int64_t> off_h;
-    st = bands_launch(c, plane_x_host, S, half_width, truncate_center, pairing_mode == PPP_PAIR_GEN2, &boff, &bidx, &M,
-                      &planes, &off_h);
-    if (st == PPP_OK) st = contours_launch(c, *g, planes, S, boff, bidx, M, off_h, pairing_mode, &total);
-    dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, planes);
+    // SectPath pairing: the chain without mid-way host round trips, unless its allocation bound is too large
+    st = pairing_mode == PPP_PAIR_SECT && !getenv("PPP_SLICE_SYNC")
+             ? slice_contours_sect_async(c, *g, plane_x_host, S, half_width, truncate_center, &total, &M)
+             : PPP_ERR_UNSUPPORTED;
+    if (st == PPP_ERR_UNSUPPORTED) {
+      int64_t* boff = nullptr; int32_t* bidx = nullptr; float* planes = nullptr;
+      std::vector<int64_t> off_h;
+      st = bands_launch(c, plane_x_host, S, half_width, truncate_center, pairing_mode == PPP_PAIR_GEN2, &boff, &bidx, &M,
+                        &planes, &off_h);
+      if (st == PPP_OK) st = contours_launch(c, *g, planes, S, boff, bidx, M, off_h, pairing_mode, &total);
+      dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, planes);
+    }
   }
   if (st != PPP_OK) return st;
   if (node_offsets_dev) *node_offsets_dev = c->c_node_off;
@@ -596,6 +602,15 @@ int ppp_slice_bands(ppp_cloud* c, const float* plane_x, int S, float half_width,
   return st;
 }
 
+// Is p ordinary page-locked host memory (cudaHostAlloc / cudaHostRegister)?  Under UVA such memory is
+// addressable from kernels with the same pointer value.
+static bool host_ptr_is_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost && at.devicePointer == p;
+}
+
 int ppp_slice_contours(ppp_cloud* c, const float* plane_x, int S, float half_width, int truncate_center, int pairing_mode,
                        int64_t* node_offsets, double* y, double* x, double* z, int64_t node_cap) {
   REQUIRE(c && node_offsets, "NULL argument");
@@ -603,21 +618,29 @@ int ppp_slice_contours(ppp_cloud* c, const float* plane_x, int S, float half_wid
   ppp_ctx* ctx = c->ctx;
   LOCK(ctx);
   const int64_t* off_d; const double *y_d, *x_d, *z_d; int64_t total = 0, M = 0;
-  PPP_TRY(ppp_dev_slice_contours(c, plane_x, S, half_width, truncate_center, pairing_mode, &off_d, &y_d, &x_d, &z_d, &total, &M));
-  PPP_CUDA(cudaMemcpyAsync(node_offsets, off_d, ((size_t)S + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  int st = PPP_OK;
+  // Page-locked result arrays are filled by the compaction kernel itself (coalesced stores over PCIe
+  // while the chain runs): three separate ~1 MB device->host copies measured ~80 us EACH here.
+  const bool direct = y && node_cap > 0 && host_ptr_is_pinned(y) && host_ptr_is_pinned(x) && host_ptr_is_pinned(z);
+  double *sy = c->ext_y, *sx = c->ext_x, *sz = c->ext_z;
+  const int64_t scap = c->ext_cap;
+  if (direct) { c->ext_y = y; c->ext_x = x; c->ext_z = z; c->ext_cap = node_cap; }
+  int st = ppp_dev_slice_contours(c, plane_x, S, half_width, truncate_center, pairing_mode, &off_d, &y_d, &x_d, &z_d, &total, &M);
+  if (direct) { c->ext_y = sy; c->ext_x = sx; c->ext_z = sz; c->ext_cap = scap; }
+  if (st != PPP_OK) return st;
+  PPP_TRY(fetch_small(ctx, off_d, ((size_t)S + 1) * 8, node_offsets));   // synchronises the stream
   if (y) {
     if (node_cap < total) {
       ppp_set_error("ppp_slice_contours: node_cap %lld < required %lld", (long long)node_cap, (long long)total);
-      st = PPP_ERR_CAPACITY;
-    } else if (total) {
+      return PPP_ERR_CAPACITY;
+    }
+    if (total && y_d != y) {
       PPP_CUDA(cudaMemcpyAsync(y, y_d, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
       PPP_CUDA(cudaMemcpyAsync(x, x_d, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
       PPP_CUDA(cudaMemcpyAsync(z, z_d, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      PPP_CUDA(cudaStreamSynchronize(ctx->stream));
     }
   }
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
-  return st;
+  return PPP_OK;
 }
 
 // estimate_normal() + the whole plane sweep in one call (the gen-3 GenPath does exactly this

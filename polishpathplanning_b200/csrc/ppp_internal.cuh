@@ -126,6 +126,7 @@ struct ppp_cloud {
   double *ext_y = nullptr, *ext_x = nullptr, *ext_z = nullptr;  // optional caller-owned node buffers
   int64_t ext_cap = 0;
   const int32_t* nmap = nullptr;   // ppp_dev_set_normal_row_map
+  int64_t max_band_hint = 0;       // largest band of the last sync-free slicing call (sizes its shared memory)
   int64_t* ext_off = nullptr;      // ppp_dev_set_contour_offsets_buffer
   int64_t ext_off_cap = 0;
   double *out_y = nullptr, *out_x = nullptr, *out_z = nullptr;  // where the last call wrote the nodes
@@ -162,6 +163,7 @@ struct LaunchScope {
   } while (0)
 
 #define PPP_CHECK_LAUNCH() PPP_CUDA(cudaGetLastError())
+
 
 // A few bytes of device memory to the host in stream order, then synchronise: a tiny kernel stores
 // them into mapped pinned memory.  Unlike a cudaMemcpyAsync this does not queue behind a large
@@ -222,5 +224,7 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
 int contours_launch(ppp_cloud* c, const GridStore& g, const float* planes_dev, int S, const int64_t* band_off_dev,
                     const int32_t* band_idx_dev, int64_t band_total, const std::vector<int64_t>& band_off_host, int mode,
                     int64_t* total_nodes_out, const uint32_t* member_bits = nullptr);
+int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* plane_x_host, int S, float half_width,
+                              int truncate_center, int64_t* total_nodes_out, int64_t* total_members_out);
 int contours_from_indices_launch(ppp_cloud* c, const GridStore& gs, const int32_t* idx_host, int64_t m, float plane_x,
                                  int mode, int64_t* total_nodes_out);

@@ -5,6 +5,7 @@
 // insert_point (src/Path_Generation.cpp:107-206; src/contour_alg.cpp:165-237) and the map ->
 // array flattening in path_track / OnePath (src/Path_Generation.cpp:659-676; src/contour_alg.cpp:240-257).
 #include <algorithm>
+#include <functional>
 #include <cmath>
 #include <vector>
 
@@ -454,14 +455,15 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
   __shared__ int s_s[PAIR_WARPS][64];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t base = ((int64_t)blockIdx.x * PAIR_WARPS + w) * PAIR_CHUNK;
-  if (base >= P.M) return;
+  const int64_t M = __ldg(P.band_off + P.S);   // the launch may be sized from a host-side bound
+  if (base >= M) return;
   int cnt = 0;
   for (int half = 0; half < 2; half++) {
     const int off = half * 32 + lane;
     const int64_t m = base + off;
     bool isL = false;
     int s = 0;
-    if (off < PAIR_CHUNK && m < P.M) {
+    if (off < PAIR_CHUNK && m < M) {
       // slice of member m: last s with band_off[s] <= m
       int l = 0, r = P.S;
       while (l < r) { int mid = (l + r) >> 1; if (__ldg(P.band_off + mid + 1) <= m) l = mid + 1; else r = mid; }
@@ -585,6 +587,40 @@ __global__ void __launch_bounds__(256) k_compact_nodes(const int64_t* __restrict
   }
 }
 
+// Sync-free variant: the host does not know the node total when it launches this, so the kernel
+// itself picks the destination (caller's buffers if the total fits, else the cloud's) and leaves
+// {node total, band members, largest band, used caller's buffers} for one fetch at the very end.
+struct NodeDest {
+  double *ey, *ex, *ez; int64_t ecap;   // caller-owned (may be page-locked host memory), optional
+  double *oy, *ox, *oz;                 // cloud-owned, large enough for any total
+  int64_t* ext_off; int64_t ext_off_cap;
+};
+
+__global__ void __launch_bounds__(256) k_compact_nodes_auto(const int64_t* __restrict__ band_off, const int64_t* __restrict__ node_off,
+                                                           int S, const float* __restrict__ planes, const double* __restrict__ ty,
+                                                           const double* __restrict__ tz, NodeDest D, int64_t* __restrict__ summary) {
+  const int s = blockIdx.x;
+  const int64_t total = node_off[S];
+  const bool ext = D.ey && total <= D.ecap;
+  double* y = ext ? D.ey : D.oy; double* x = ext ? D.ex : D.ox; double* z = ext ? D.ez : D.oz;
+  const int64_t so = band_off[s], d = node_off[s];
+  const int n = (int)(node_off[s + 1] - d);
+  const double px = (double)planes[s];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    y[d + i] = ty[so + i];
+    x[d + i] = px;
+    z[d + i] = tz[so + i];
+  }
+  if (D.ext_off && D.ext_off_cap >= (int64_t)S + 1) {
+    if (threadIdx.x == 0) D.ext_off[s] = d;
+    if (threadIdx.x == 1 && s == S - 1) D.ext_off[S] = total;
+  }
+  if (threadIdx.x == 0) {
+    atomicMax((unsigned long long*)(summary + 2), (unsigned long long)(band_off[s + 1] - so));
+    if (s == 0) { summary[0] = total; summary[1] = band_off[S]; summary[3] = ext ? 1 : 0; }
+  }
+}
+
 }  // namespace
 
 static void band_limits_host(float plane_x, float half_width, int truncate_center, float* lo, float* hi) {
@@ -599,13 +635,22 @@ static void band_limits_host(float plane_x, float half_width, int truncate_cente
   }
 }
 
-// Device arrays produced: offsets (S+1, int64), idx (total), planes/lo/hi (3*S floats, original
-// order).  sort_bands != 0: every band in ascending point index (PassThrough order).
-int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center, int sort_bands,
-                 int64_t** offsets_dev_out, int32_t** idx_dev_out, int64_t* total_out, float** planes_dev_out,
-                 std::vector<int64_t>* offsets_host_out) {
+// Host staging + counting pass shared by the two band builders: limits per plane, planes sorted by
+// lower limit, upload, k_band_count, exclusive scan.  Leaves counts zeroed for the fill pass.
+struct BandPrep {
+  float* fdev = nullptr;      // [planes S][lo S][hi S][lo_sorted S][hi_sorted S]
+  int32_t* pdev = nullptr;    // sorted position -> plane
+  int32_t* counts = nullptr;  // S
+  int64_t* offsets = nullptr; // S + 1
+  BandSet b{};
+  int Sv = 0, use_smem = 0;
+  unsigned blocks = 1;
+  int64_t chunk = 0;
+  int max_depth = 0;          // most bands any single x can belong to
+};
+
+static int bands_prepare(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center, BandPrep* bp) {
   ppp_ctx* ctx = c->ctx;
-  *offsets_dev_out = nullptr; *idx_dev_out = nullptr; *planes_dev_out = nullptr; *total_out = 0;
   std::vector<float> lo(S), hi(S);
   std::vector<int32_t> perm(S);
   for (int s = 0; s < S; s++) {
@@ -633,40 +678,69 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
     stage[3 * S + t] = lo[s];
     stage[4 * S + t] = hi[s];
   }
-  float* fdev = nullptr;
-  int32_t* pdev = nullptr;
-  PPP_TRY(dev_alloc(ctx, &fdev, 5 * (size_t)std::max(S, 1)));
-  PPP_TRY(dev_alloc(ctx, &pdev, (size_t)std::max(S, 1)));
-  int32_t* counts = nullptr;
-  int64_t* offsets = nullptr;
-  PPP_TRY(dev_alloc(ctx, &counts, (size_t)std::max(S, 1)));
-  PPP_TRY(dev_alloc(ctx, &offsets, (size_t)S + 1));
-  PPP_CUDA(cudaMemsetAsync(counts, 0, (size_t)std::max(S, 1) * sizeof(int32_t), ctx->stream));
-  if (S > 0) {
-    PPP_CUDA(cudaMemcpyAsync(fdev, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    PPP_CUDA(cudaMemcpyAsync(pdev, perm.data(), (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  {  // overlap depth of the closed intervals [lo, hi], taken in ascending lo
+    std::vector<float> ends;  // min-heap of the upper limits still open
+    int depth = 0;
+    for (int t = 0; t < Sv; t++) {
+      const float l = stage[3 * S + t], h = stage[4 * S + t];
+      while (!ends.empty() && ends.front() < l) { std::pop_heap(ends.begin(), ends.end(), std::greater<float>()); ends.pop_back(); }
+      ends.push_back(h); std::push_heap(ends.begin(), ends.end(), std::greater<float>());
+      depth = std::max(depth, (int)ends.size());
+    }
+    bp->max_depth = depth;
   }
-  BandSet b{fdev + 3 * (size_t)S, fdev + 4 * (size_t)S, pdev, Sv};
-  const int use_smem = Sv <= BAND_SMEM_BINS / 2;  // fill needs two arrays
-  unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((c->n + 1023) / 1024, (int64_t)ctx->sm_count * 8));
-  int64_t chunk = (c->n + blocks - 1) / blocks;
+  PPP_TRY(dev_alloc(ctx, &bp->fdev, 5 * (size_t)std::max(S, 1)));
+  PPP_TRY(dev_alloc(ctx, &bp->pdev, (size_t)std::max(S, 1)));
+  PPP_TRY(dev_alloc(ctx, &bp->counts, (size_t)std::max(S, 1)));
+  PPP_TRY(dev_alloc(ctx, &bp->offsets, (size_t)S + 1));
+  PPP_CUDA(cudaMemsetAsync(bp->counts, 0, (size_t)std::max(S, 1) * sizeof(int32_t), ctx->stream));
+  if (S > 0) {
+    // pageable sources: the runtime stages them before returning, so the vectors may go out of scope
+    PPP_CUDA(cudaMemcpyAsync(bp->fdev, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    PPP_CUDA(cudaMemcpyAsync(bp->pdev, perm.data(), (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  bp->b = BandSet{bp->fdev + 3 * (size_t)S, bp->fdev + 4 * (size_t)S, bp->pdev, Sv};
+  bp->Sv = Sv;
+  bp->use_smem = Sv <= BAND_SMEM_BINS / 2;  // fill needs two arrays
+  bp->blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((c->n + 1023) / 1024, (int64_t)ctx->sm_count * 8));
+  bp->chunk = (c->n + bp->blocks - 1) / bp->blocks;
   if (c->n > 0 && Sv > 0) {
-    PPP_LAUNCH(ctx, "band_count", k_band_count, blocks, 256, use_smem ? (size_t)Sv * 4 : 0, b, (const float4*)c->xyz4, c->n,
-               chunk, use_smem, counts);
+    PPP_LAUNCH(ctx, "band_count", k_band_count, bp->blocks, 256, bp->use_smem ? (size_t)Sv * 4 : 0, bp->b, (const float4*)c->xyz4,
+               c->n, bp->chunk, bp->use_smem, bp->counts);
     PPP_CHECK_LAUNCH();
   }
-  PPP_TRY(scan_exclusive_i32_to_i64(ctx, counts, offsets, S));
+  PPP_TRY(scan_exclusive_i32_to_i64(ctx, bp->counts, bp->offsets, S));
+  PPP_CUDA(cudaMemsetAsync(bp->counts, 0, (size_t)std::max(S, 1) * sizeof(int32_t), ctx->stream));
+  return PPP_OK;
+}
+
+static int bands_fill(ppp_cloud* c, const BandPrep& bp, int32_t* idx) {
+  ppp_ctx* ctx = c->ctx;
+  if (c->n <= 0 || bp.Sv <= 0) return PPP_OK;
+  if (bp.use_smem) PPP_CUDA(cudaFuncSetAttribute(k_band_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_SMEM_BINS * 4));
+  PPP_LAUNCH(ctx, "band_fill", k_band_fill, bp.blocks, 256, bp.use_smem ? (size_t)bp.Sv * 8 : 0, bp.b, (const float4*)c->xyz4, c->n,
+             bp.chunk, bp.use_smem, bp.counts, (const int64_t*)bp.offsets, idx);
+  PPP_CHECK_LAUNCH();
+  return PPP_OK;
+}
+
+// Device arrays produced: offsets (S+1, int64), idx (total), planes/lo/hi (3*S floats, original
+// order).  sort_bands != 0: every band in ascending point index (PassThrough order).
+int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center, int sort_bands,
+                 int64_t** offsets_dev_out, int32_t** idx_dev_out, int64_t* total_out, float** planes_dev_out,
+                 std::vector<int64_t>* offsets_host_out) {
+  ppp_ctx* ctx = c->ctx;
+  *offsets_dev_out = nullptr; *idx_dev_out = nullptr; *planes_dev_out = nullptr; *total_out = 0;
+  BandPrep bp;
+  PPP_TRY(bands_prepare(c, plane_x_host, S, half_width, truncate_center, &bp));
+  int64_t* offsets = bp.offsets;
   std::vector<int64_t> off_h((size_t)S + 1, 0);
-  PPP_TRY(fetch_small(ctx, offsets, ((size_t)S + 1) * sizeof(int64_t), off_h.data()));  // sync: also covers the pageable staging vectors above
+  PPP_TRY(fetch_small(ctx, offsets, ((size_t)S + 1) * sizeof(int64_t), off_h.data()));
   int64_t total = off_h[S];
   int32_t* idx = nullptr;
   PPP_TRY(dev_alloc(ctx, &idx, (size_t)std::max<int64_t>(total, 1)));
   if (total > 0) {
-    PPP_CUDA(cudaMemsetAsync(counts, 0, (size_t)S * sizeof(int32_t), ctx->stream));
-    if (use_smem) PPP_CUDA(cudaFuncSetAttribute(k_band_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_SMEM_BINS * 4));
-    PPP_LAUNCH(ctx, "band_fill", k_band_fill, blocks, 256, use_smem ? (size_t)Sv * 8 : 0, b, (const float4*)c->xyz4, c->n, chunk,
-               use_smem, counts, (const int64_t*)offsets, idx);
-    PPP_CHECK_LAUNCH();
+    PPP_TRY(bands_fill(c, bp, idx));
     if (sort_bands) {
       int64_t maxB = 0;
       for (int s = 0; s < S; s++) maxB = std::max(maxB, off_h[s + 1] - off_h[s]);
@@ -678,11 +752,11 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
       PPP_CHECK_LAUNCH();
     }
   }
-  dev_free(ctx, counts);
-  dev_free(ctx, pdev);
+  dev_free(ctx, bp.counts);
+  dev_free(ctx, bp.pdev);
   *offsets_dev_out = offsets;
   *idx_dev_out = idx;
-  *planes_dev_out = fdev;  // [planes][lo][hi] in original order (+ sorted copies behind)
+  *planes_dev_out = bp.fdev;  // [planes][lo][hi] in original order (+ sorted copies behind)
   *total_out = total;
   if (offsets_host_out) *offsets_host_out = std::move(off_h);
   return PPP_OK;
@@ -818,5 +892,94 @@ int contours_from_indices_launch(ppp_cloud* c, const GridStore& gs, const int32_
   std::vector<int64_t> offv = {0, m};
   int st = contours_launch(c, gs, planes, 1, boff, bidx, m, offv, mode, total_nodes_out, bits);
   dev_free(ctx, planes); dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, bits);
+  return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SectPath pairing without a mid-chain host synchronisation.  bands_launch / contours_launch fetch two
+// sizes on the way (band members, node total) to size their allocations; each fetch is a device->host
+// round trip, and in the host-pointer path those round trips queue behind the 32 MB copy of the
+// normals (measured: the chain took 690 us under the copy against 320 us alone).  Here every buffer is
+// sized from a HOST-side bound instead -- a point belongs to at most `max_depth` bands, a band yields
+// at most one node per member -- the kernels read the real sizes from device memory, and one fetch
+// at the end returns {node total, band members, largest band, destination used}.
+// Returns PPP_ERR_UNSUPPORTED (nothing launched) when the bound is too large to allocate blindly.
+// ---------------------------------------------------------------------------------------------
+int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* plane_x_host, int S, float half_width,
+                              int truncate_center, int64_t* total_nodes_out, int64_t* total_members_out) {
+  ppp_ctx* ctx = c->ctx;
+  if (S <= 0 || c->n <= 0) return PPP_ERR_UNSUPPORTED;
+  BandPrep bp;
+  PPP_TRY(bands_prepare(c, plane_x_host, S, half_width, truncate_center, &bp));
+  const int64_t Mb = (int64_t)std::max(bp.max_depth, 1) * c->n;   // >= band members
+  int st = PPP_OK;
+  int32_t* idx = nullptr; double *ty = nullptr, *tz = nullptr; int32_t* n_nodes = nullptr;
+  u64 *keys = nullptr, *scratch = nullptr; float *ys = nullptr, *zs = nullptr; int64_t* summary = nullptr;
+  auto cleanup = [&]() {
+    dev_free(ctx, bp.counts); dev_free(ctx, bp.pdev); dev_free(ctx, bp.offsets); dev_free(ctx, bp.fdev);
+    dev_free(ctx, idx); dev_free(ctx, ty); dev_free(ctx, tz); dev_free(ctx, n_nodes);
+    dev_free(ctx, keys); dev_free(ctx, scratch); dev_free(ctx, ys); dev_free(ctx, zs); dev_free(ctx, summary);
+  };
+  if ((double)Mb * 72.0 > 6.0e9) {   // ~72 B of temporaries per possible member
+    cleanup();
+    return PPP_ERR_UNSUPPORTED;
+  }
+  const size_t M = (size_t)Mb;
+  auto body = [&]() -> int {
+    PPP_TRY(dev_alloc(ctx, &idx, M));
+    PPP_TRY(bands_fill(c, bp, idx));
+    PPP_TRY(dev_alloc(ctx, &ty, M)); PPP_TRY(dev_alloc(ctx, &tz, M));
+    PPP_TRY(dev_alloc(ctx, &n_nodes, (size_t)S));
+    PPP_TRY(dev_alloc(ctx, &keys, M)); PPP_TRY(dev_alloc(ctx, &ys, M)); PPP_TRY(dev_alloc(ctx, &zs, M));
+    PPP_TRY(dev_alloc(ctx, &scratch, M));
+    PPP_TRY(dev_alloc(ctx, &summary, 4));
+    PPP_CUDA(cudaMemsetAsync(summary, 0, 4 * sizeof(int64_t), ctx->stream));
+    const float* planes_dev = bp.fdev;
+    PairParams P{};
+    P.g = gs.v; P.xyz4 = c->xyz4;
+    P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
+    P.band_off = bp.offsets; P.band_idx = idx; P.S = S; P.M = Mb;
+    P.member = nullptr; P.keys = keys; P.ys = ys; P.zs = zs;
+    const int64_t per_block = (int64_t)PAIR_WARPS * PAIR_CHUNK;
+    PPP_LAUNCH(ctx, "pair_nodes", k_pair_nodes<false>, (unsigned)((Mb + per_block - 1) / per_block), PAIR_WARPS * 32, 0, P);
+    PPP_CHECK_LAUNCH();
+    // shared-memory capacity of the per-slice sort: the largest band of the previous call on this
+    // cloud, else an estimate from the mean population of a band; larger bands sort in `scratch`
+    int64_t guess = c->max_band_hint > 0 ? c->max_band_hint + c->max_band_hint / 4 : 2 * (Mb / std::max(S, 1)) + 1024;
+    int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(guess, 1024), 24576);  // <= 192 KB of u64
+    if ((size_t)smem_cap * 8 > 48 * 1024)
+      PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
+    PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, SO_THREADS, (size_t)smem_cap * 8, (const int64_t*)bp.offsets,
+               (const int32_t*)idx, (const u64*)keys, (const float*)ys, (const float*)zs, scratch, smem_cap, ty, tz, n_nodes);
+    PPP_CHECK_LAUNCH();
+    if (c->c_S_cap < S + 1) {
+      dev_free(ctx, c->c_node_off);
+      PPP_TRY(dev_alloc(ctx, &c->c_node_off, (size_t)S + 1));
+      c->c_S_cap = S + 1;
+    }
+    PPP_TRY(scan_exclusive_i32_to_i64(ctx, n_nodes, c->c_node_off, S));
+    if (c->c_cap < Mb || !c->c_y) {   // cloud-owned result buffers that hold any possible total
+      dev_free(ctx, c->c_y); dev_free(ctx, c->c_x); dev_free(ctx, c->c_z);
+      c->c_y = c->c_x = c->c_z = nullptr; c->c_cap = 0;
+      PPP_TRY(dev_alloc(ctx, &c->c_y, M)); PPP_TRY(dev_alloc(ctx, &c->c_x, M)); PPP_TRY(dev_alloc(ctx, &c->c_z, M));
+      c->c_cap = Mb;
+    }
+    NodeDest D{c->ext_y, c->ext_x, c->ext_z, c->ext_y ? c->ext_cap : 0, c->c_y, c->c_x, c->c_z, c->ext_off, c->ext_off_cap};
+    PPP_LAUNCH(ctx, "compact_nodes", k_compact_nodes_auto, (unsigned)S, 256, 0, (const int64_t*)bp.offsets,
+               (const int64_t*)c->c_node_off, S, planes_dev, (const double*)ty, (const double*)tz, D, summary);
+    PPP_CHECK_LAUNCH();
+    int64_t h[4] = {0, 0, 0, 0};
+    PPP_TRY(fetch_small(ctx, summary, sizeof(h), h));   // the one synchronisation of the chain
+    const bool ext = h[3] != 0;
+    c->out_y = ext ? c->ext_y : c->c_y;
+    c->out_x = ext ? c->ext_x : c->c_x;
+    c->out_z = ext ? c->ext_z : c->c_z;
+    c->max_band_hint = h[2];
+    *total_nodes_out = h[0];
+    *total_members_out = h[1];
+    return PPP_OK;
+  };
+  st = body();
+  cleanup();
   return st;
 }
