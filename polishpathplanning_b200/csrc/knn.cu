@@ -353,11 +353,24 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
     if (P.idx_out && !RADIUS) {
       int32_t* io = P.idx_out + row * (int64_t)k;
       float* dout = P.d2_out ? P.d2_out + row * (int64_t)k : nullptr;
-      for (int j = 0; j < k; j++) {
-        u64 key = pend_s[j * BD];
-        bool has = key != PPP_KEY_INF;
-        io[j] = has ? key_idx(key) : -1;
-        if (dout) dout[j] = has ? key_d2(key) : CUDART_INF_F;
+      if ((k & 3) == 0 && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 15) == 0) {
+        // rows are 16-byte aligned: 128-bit stores (a lane's row is contiguous, the rows of a warp are not)
+        for (int j = 0; j < k; j += 4) {
+          u64 k0 = pend_s[j * BD], k1 = pend_s[(j + 1) * BD], k2 = pend_s[(j + 2) * BD], k3 = pend_s[(j + 3) * BD];
+          reinterpret_cast<int4*>(io)[j >> 2] = make_int4(k0 != PPP_KEY_INF ? key_idx(k0) : -1, k1 != PPP_KEY_INF ? key_idx(k1) : -1,
+                                                          k2 != PPP_KEY_INF ? key_idx(k2) : -1, k3 != PPP_KEY_INF ? key_idx(k3) : -1);
+          if (dout)
+            reinterpret_cast<float4*>(dout)[j >> 2] =
+                make_float4(k0 != PPP_KEY_INF ? key_d2(k0) : CUDART_INF_F, k1 != PPP_KEY_INF ? key_d2(k1) : CUDART_INF_F,
+                            k2 != PPP_KEY_INF ? key_d2(k2) : CUDART_INF_F, k3 != PPP_KEY_INF ? key_d2(k3) : CUDART_INF_F);
+        }
+      } else {
+        for (int j = 0; j < k; j++) {
+          u64 key = pend_s[j * BD];
+          bool has = key != PPP_KEY_INF;
+          io[j] = has ? key_idx(key) : -1;
+          if (dout) dout[j] = has ? key_d2(key) : CUDART_INF_F;
+        }
       }
     }
     if (P.normals) {
@@ -410,7 +423,8 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
 // Dropping 5 mantissa bits can only misorder two candidates whose d2 agree in the upper 27 bits;
 // any such pair among the 17 smallest marks the query for the exact hand-over kernel instead
 // (measured: well under 0.1 % of the queries), so every delivered list is in the exact
-// (d2, index) order.
+// (d2, index) order.  For the same reason the low word of a parked key need not be the point index:
+// it is the candidate's position in the sorted array, which the final gather reads back.
 // ---------------------------------------------------------------------------------------------
 constexpr int C_SLOTS = 32;   // keys ordered per network pass
 constexpr int C_STORE = 36;   // storage slots: U spare ones, so a pass is only forced beyond 32 occupied
@@ -440,11 +454,15 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
   u64* store = s_keys + threadIdx.x;  // slot j of this thread at store[j * BD]
   const int R = P.R0;
   int cu = 0, cv = 0;
-  u64 tau = 0;  // inactive lanes accept nothing
+  // Acceptance threshold on d2 alone, INCLUSIVE: a candidate that ties the current K-th distance is
+  // parked too, and the tie then shows up as an ambiguous pair in the next pass (-> exact hand-over).
+  // The low key word is the candidate's SORTED POSITION, not its index: the final gather reads
+  // g.sorted[pos] (coordinates + original index in one record, from lines this warp has just used).
+  float tau = -1.0f;  // inactive lanes accept nothing
   if (act) {
     cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
     cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
-    tau = make_key(ring_bound2(g, R, cu, cv), 0);
+    tau = ring_bound2(g, R, cu, cv);
   }
   int ns = 0;            // occupied slots
   bool ambiguous = false;
@@ -468,7 +486,7 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
 #pragma unroll
       for (int i = 0; i < K; i++) store[i * BD] = keep[i];
       ns = K;
-      if (keep[K - 1] < tau) tau = keep[K - 1];
+      tau = fminf(tau, key_d2(keep[K - 1]));
     } else {
       // fewer than K so far: still put them in sorted order (cheap, and the final flush relies on it)
       u64 keep[K];
@@ -476,7 +494,7 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
       for (int i = 0; i < K; i++) keep[i] = i < ns ? store[(c[i] & 31u) * BD] : PPP_KEY_INF;
 #pragma unroll
       for (int i = 0; i < K; i++) store[i * BD] = keep[i];
-      if (ns == K && keep[K - 1] < tau) tau = keep[K - 1];
+      if (ns == K) tau = fminf(tau, key_d2(keep[K - 1]));
     }
   };
 
@@ -512,9 +530,8 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
 #pragma unroll
       for (int u = 0; u < U; u++) {
         float d2 = d2_flann(qx, qy, qz, c4[u].x, c4[u].y, c4[u].z);
-        u64 key = make_key(d2, __float_as_int(c4[u].w));
-        if (in[u] && key < tau) {
-          *wptr = key;
+        if (in[u] && d2 <= tau) {
+          *wptr = make_key(d2, s + it * U + u);
           wptr += BD;
         }
       }
@@ -542,12 +559,27 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
   if (P.idx_out) {
     int32_t* io = P.idx_out + row * (int64_t)k;
     float* dout = P.d2_out ? P.d2_out + row * (int64_t)k : nullptr;
+    int32_t id[K];
 #pragma unroll
-    for (int j = 0; j < K; j++) {
-      if (j < k) {
-        bool has = best[j] != PPP_KEY_INF;
-        io[j] = has ? key_idx(best[j]) : -1;
-        if (dout) dout[j] = has ? key_d2(best[j]) : CUDART_INF_F;
+    for (int j = 0; j < K; j++)   // original index = w of the neighbour's sorted record
+      id[j] = j < m ? __float_as_int(__ldg(&g.sorted[key_idx(best[j])].w)) : -1;
+    if (k == K && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 15) == 0) {
+      // a full row is 64 contiguous, 16-byte aligned bytes: four 128-bit stores instead of sixteen 32-bit ones
+#pragma unroll
+      for (int j = 0; j < K; j += 4) reinterpret_cast<int4*>(io)[j / 4] = make_int4(id[j], id[j + 1], id[j + 2], id[j + 3]);
+      if (dout) {
+#pragma unroll
+        for (int j = 0; j < K; j += 4)
+          reinterpret_cast<float4*>(dout)[j / 4] = make_float4(j < m ? key_d2(best[j]) : CUDART_INF_F, j + 1 < m ? key_d2(best[j + 1]) : CUDART_INF_F,
+                                                               j + 2 < m ? key_d2(best[j + 2]) : CUDART_INF_F, j + 3 < m ? key_d2(best[j + 3]) : CUDART_INF_F);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        if (j < k) {
+          io[j] = id[j];
+          if (dout) dout[j] = j < m ? key_d2(best[j]) : CUDART_INF_F;
+        }
       }
     }
   }
@@ -559,7 +591,7 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
       float4 nb[K];
 #pragma unroll
       for (int j = 0; j < K; j++)
-        if (j < m) nb[j] = __ldg(P.xyz4 + key_idx(best[j]));
+        if (j < m) nb[j] = __ldg(g.sorted + key_idx(best[j]));
       float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
       float kx = shifted ? nb[0].x : 0.f, ky = shifted ? nb[0].y : 0.f, kz = shifted ? nb[0].z : 0.f;
