@@ -190,6 +190,19 @@ def redistribute(dist, chunk, global_start, rank, world, halo, bins=4096):
 # store into them over NVLink (CUDA IPC mapping), and a stream-ordered flag per rank tells rank 0
 # when a step's results have landed.
 # -------------------------------------------------------------------------------------------------
+def peer_sink_layout(world, n_total, node_cap, S_cap):
+    """Byte layout of the PeerSink buffer (every section 256-byte aligned):
+    [normals n_total x 16][rank 0: offsets | y | x | z] ... [rank world-1: ...][flags world x 128]."""
+    a256 = lambda v: (int(v) + 255) // 256 * 256
+    normals_bytes = a256(int(n_total) * 16)
+    off_bytes = a256((int(S_cap) + 1) * 8)
+    arr_bytes = a256(int(node_cap) * 8)
+    region_bytes = off_bytes + 3 * arr_bytes
+    flags_at = normals_bytes + int(world) * region_bytes
+    return {"normals_bytes": normals_bytes, "off_bytes": off_bytes, "arr_bytes": arr_bytes, "region_bytes": region_bytes,
+            "flags_at": flags_at, "total_bytes": flags_at + int(world) * 128}
+
+
 class PeerSink:
     """Global result arrays on rank 0, written in place by all ranks.
 
@@ -212,13 +225,9 @@ class PeerSink:
         caps = torch.tensor([int(n_total), int(node_cap), int(S_cap)], dtype=torch.int64, device=device)
         dist.all_reduce(caps, op=dist.ReduceOp.MAX)
         self.n_total, self.node_cap, self.S_cap = (int(v) for v in caps.tolist())
-        a256 = lambda v: (int(v) + 255) // 256 * 256
-        self._normals_bytes = a256(self.n_total * 16)
-        self._off_bytes = a256((self.S_cap + 1) * 8)
-        self._arr_bytes = a256(self.node_cap * 8)
-        self._region_bytes = self._off_bytes + 3 * self._arr_bytes
-        self._flags_at = self._normals_bytes + world * self._region_bytes
-        total = self._flags_at + world * 128
+        lay = peer_sink_layout(world, self.n_total, self.node_cap, self.S_cap)
+        self._normals_bytes, self._off_bytes, self._arr_bytes = lay["normals_bytes"], lay["off_bytes"], lay["arr_bytes"]
+        self._region_bytes, self._flags_at, total = lay["region_bytes"], lay["flags_at"], lay["total_bytes"]
         hbuf = torch.zeros(64, dtype=torch.uint8, device=device)
         if rank == 0:
             self.base, handle = ctx.peer_buffer_alloc(total)      # zero-filled

@@ -199,3 +199,21 @@ def test_sor_threshold_pass_restatements_agree():
                 okept, othr = po.OracleCloud.sor_select(d, nv, mul, neg)
                 assert np.array_equal(kept, okept)
                 assert thr == othr or (np.isnan(thr) and np.isnan(othr))
+
+
+def test_peer_sink_layout_sections_are_disjoint_and_aligned():
+    """The one buffer every rank's kernels store into: normals, per-rank node regions, flags."""
+    for world, n_total, node_cap, S_cap in ((2, 2_000_000, 270_000, 142), (8, 8_000_001, 65_536, 71), (3, 5, 1, 0)):
+        lay = parallel.peer_sink_layout(world, n_total, node_cap, S_cap)
+        spans = [(0, n_total * 16)]
+        for r in range(world):
+            at = lay["normals_bytes"] + r * lay["region_bytes"]
+            spans += [(at, at + (S_cap + 1) * 8)]
+            spans += [(at + lay["off_bytes"] + j * lay["arr_bytes"], at + lay["off_bytes"] + j * lay["arr_bytes"] + node_cap * 8)
+                      for j in range(3)]
+        spans += [(lay["flags_at"] + 128 * r, lay["flags_at"] + 128 * r + 4) for r in range(world)]
+        assert all(a % 256 == 0 or a >= lay["flags_at"] for a, _ in spans)
+        assert all(a % 128 == 0 for a, _ in spans)
+        spans.sort()
+        assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
+        assert spans[-1][1] <= lay["total_bytes"]
