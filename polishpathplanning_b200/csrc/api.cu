@@ -22,7 +22,7 @@ void ppp_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-#define LOCK(ctx) std::lock_guard<std::recursive_mutex> _lk((ctx)->mu)
+#define LOCK(ctx) ApiScope _api_scope(ctx)
 
 #define REQUIRE(cond, msg)            \
   do {                                \

@@ -148,7 +148,7 @@ int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes) {
   ppp_ctx* ctx = c->ctx;
   int sf = (int)(stride_bytes / 4);
   int vec_ok = (stride_bytes % 16 == 0) && (((uintptr_t)pts_dev) % 16 == 0);
-  PPP_TRY(dev_alloc(ctx, &c->xyz4, (size_t)c->n));
+  PPP_TRY(dev_alloc_keep(ctx, &c->xyz4, (size_t)c->n));
   BBoxAcc* acc = nullptr;
   PPP_TRY(dev_alloc(ctx, &acc, 1));
   PPP_LAUNCH(ctx, "bbox_init", k_bbox_init, 1, 1, 0, acc);
@@ -219,9 +219,9 @@ int cloud_get_grid(ppp_cloud* c, double h, GridStore** out) {
   v.slack = (float)(h * (double)(v.nu + v.nv) * 9.5367431640625e-07 + 1e-30);
   v.n_sorted = (int)c->n_finite;
   int64_t ncells = (int64_t)v.nu * v.nv;
-  PPP_TRY(dev_alloc(ctx, &gs.sorted, (size_t)std::max<int64_t>(c->n_finite, 1)));
-  PPP_TRY(dev_alloc(ctx, &gs.order, (size_t)std::max<int64_t>(c->n_finite, 1)));
-  PPP_TRY(dev_alloc(ctx, &gs.cell_start, (size_t)ncells + 1));
+  PPP_TRY(dev_alloc_keep(ctx, &gs.sorted, (size_t)std::max<int64_t>(c->n_finite, 1)));
+  PPP_TRY(dev_alloc_keep(ctx, &gs.order, (size_t)std::max<int64_t>(c->n_finite, 1)));
+  PPP_TRY(dev_alloc_keep(ctx, &gs.cell_start, (size_t)ncells + 1));
   int32_t* counts = nullptr;
   PPP_TRY(dev_alloc(ctx, &counts, (size_t)ncells));
   PPP_CUDA(cudaMemsetAsync(counts, 0, (size_t)ncells * sizeof(int32_t), ctx->stream));

@@ -49,6 +49,10 @@ struct ppp_ctx {
   cudaStream_t aux_stream = nullptr;   // high priority: the slicing chain runs here, concurrently with the kNN kernel
   cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap later kernels
   void* fetch_host = nullptr;          // mapped pinned scratch for fetch_small (FETCH_BYTES)
+  // Temporaries of the API call in progress (ApiScope): whatever an early error return leaves behind
+  // is released when the outermost call ends.  Guarded by `mu` like everything else here.
+  std::vector<void*> temps;
+  int api_depth = 0;
   std::recursive_mutex mu;
   int64_t launches = 0;
   bool profile = false;
@@ -172,8 +176,10 @@ struct LaunchScope {
 constexpr size_t FETCH_BYTES = 64 * 1024;
 int fetch_small(ppp_ctx* ctx, const void* dev_src, size_t bytes, void* host_dst);
 
+// Stream-ordered device memory.  dev_alloc: a temporary of the current API call (tracked until
+// dev_free, see ApiScope); dev_alloc_keep: memory that outlives the call (cloud, grids, result buffers).
 template <typename T>
-int dev_alloc(ppp_ctx* ctx, T** p, size_t count) {
+int dev_alloc_keep(ppp_ctx* ctx, T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
   cudaError_t e = cudaMallocAsync((void**)p, count * sizeof(T), ctx->stream);
@@ -185,9 +191,34 @@ int dev_alloc(ppp_ctx* ctx, T** p, size_t count) {
   return PPP_OK;
 }
 template <typename T>
-void dev_free(ppp_ctx* ctx, T* p) {
-  if (p) cudaFreeAsync((void*)p, ctx->stream);
+int dev_alloc(ppp_ctx* ctx, T** p, size_t count) {
+  int st = dev_alloc_keep(ctx, p, count);
+  if (st == PPP_OK && ctx->api_depth > 0) ctx->temps.push_back((void*)*p);
+  return st;
 }
+template <typename T>
+void dev_free(ppp_ctx* ctx, T* p) {
+  if (!p) return;
+  for (size_t i = ctx->temps.size(); i-- > 0;)
+    if (ctx->temps[i] == (void*)p) { ctx->temps.erase(ctx->temps.begin() + (long)i); break; }
+  cudaFreeAsync((void*)p, ctx->stream);
+}
+
+// One per extern "C" entry point (the LOCK macro): holds the context mutex for the call and, when the
+// outermost call returns, frees the temporaries an error path did not get to.
+struct ApiScope {
+  ppp_ctx* ctx;
+  std::lock_guard<std::recursive_mutex> lk;
+  explicit ApiScope(ppp_ctx* c) : ctx(c), lk(c->mu) { ctx->api_depth++; }
+  ~ApiScope() {
+    if (--ctx->api_depth == 0 && !ctx->temps.empty()) {
+      cudaDeviceSynchronize();   // error path: kernels on either stream may still use them
+      cudaGetLastError();
+      for (void* p : ctx->temps) cudaFreeAsync(p, ctx->main_stream);
+      ctx->temps.clear();
+    }
+  }
+};
 
 // scan.cu
 int scan_exclusive_i32(ppp_ctx* ctx, const int32_t* in, int32_t* out, int64_t n);       // out[n] = total too (n+1 outputs)

@@ -767,7 +767,7 @@ static int finish_nodes(ppp_cloud* c, int S, const int64_t* band_off_dev, const 
   ppp_ctx* ctx = c->ctx;
   if (c->c_S_cap < S + 1) {
     dev_free(ctx, c->c_node_off);
-    PPP_TRY(dev_alloc(ctx, &c->c_node_off, (size_t)S + 1));
+    PPP_TRY(dev_alloc_keep(ctx, &c->c_node_off, (size_t)S + 1));
     c->c_S_cap = S + 1;
   }
   PPP_TRY(scan_exclusive_i32_to_i64(ctx, n_nodes, c->c_node_off, S));
@@ -779,7 +779,7 @@ static int finish_nodes(ppp_cloud* c, int S, const int64_t* band_off_dev, const 
   if (!ext && (c->c_cap < total || !c->c_y)) {
     dev_free(ctx, c->c_y); dev_free(ctx, c->c_x); dev_free(ctx, c->c_z);
     size_t cap = (size_t)std::max<int64_t>(total, 1);
-    PPP_TRY(dev_alloc(ctx, &c->c_y, cap)); PPP_TRY(dev_alloc(ctx, &c->c_x, cap)); PPP_TRY(dev_alloc(ctx, &c->c_z, cap));
+    PPP_TRY(dev_alloc_keep(ctx, &c->c_y, cap)); PPP_TRY(dev_alloc_keep(ctx, &c->c_x, cap)); PPP_TRY(dev_alloc_keep(ctx, &c->c_z, cap));
     c->c_cap = (int64_t)cap;
   }
   if (c->ext_off && c->ext_off_cap >= (int64_t)S + 1)   // per-slice node offsets for a remote consumer
@@ -954,14 +954,14 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
     PPP_CHECK_LAUNCH();
     if (c->c_S_cap < S + 1) {
       dev_free(ctx, c->c_node_off);
-      PPP_TRY(dev_alloc(ctx, &c->c_node_off, (size_t)S + 1));
+      PPP_TRY(dev_alloc_keep(ctx, &c->c_node_off, (size_t)S + 1));
       c->c_S_cap = S + 1;
     }
     PPP_TRY(scan_exclusive_i32_to_i64(ctx, n_nodes, c->c_node_off, S));
     if (c->c_cap < Mb || !c->c_y) {   // cloud-owned result buffers that hold any possible total
       dev_free(ctx, c->c_y); dev_free(ctx, c->c_x); dev_free(ctx, c->c_z);
       c->c_y = c->c_x = c->c_z = nullptr; c->c_cap = 0;
-      PPP_TRY(dev_alloc(ctx, &c->c_y, M)); PPP_TRY(dev_alloc(ctx, &c->c_x, M)); PPP_TRY(dev_alloc(ctx, &c->c_z, M));
+      PPP_TRY(dev_alloc_keep(ctx, &c->c_y, M)); PPP_TRY(dev_alloc_keep(ctx, &c->c_x, M)); PPP_TRY(dev_alloc_keep(ctx, &c->c_z, M));
       c->c_cap = Mb;
     }
     NodeDest D{c->ext_y, c->ext_x, c->ext_z, c->ext_y ? c->ext_cap : 0, c->c_y, c->c_x, c->c_z, c->ext_off, c->ext_off_cap};
