@@ -562,3 +562,41 @@ def test_sor_mean_distances_and_remove_outlier(ctx, tmp_path):
         tiny.sor_mean_distances(50)
     assert e.value.status == api._lib.PPP_ERR_UNSUPPORTED
     tiny.close()
+
+
+def test_sync_free_slicing_corner_cases(ctx):
+    """SectPath slicing without mid-chain fetches: bands larger than the shared-memory sort (global
+    scratch path), more planes than the offsets fetch buffer holds, planes outside the cloud and
+    non-finite planes, caller buffers too small (capacity error, then retried), repeated calls."""
+    c = synth.panel(200000, 47)
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    mn, mx = oc.minmax()
+    # 1. very wide bands: ~36k members per slice > 24576 keys of shared memory
+    planes = np.array([mn[0] + 100.0, 0.5 * (mn[0] + mx[0]), mx[0] - 90.5], np.float32)
+    for _ in range(2):                                   # second call sizes from the first one's largest band
+        g = gc.slice_contours(planes, "B", half_width=40.0)
+        o = oc.slice_contours(planes, "B", half_width=40.0)
+        assert int(np.diff(oc.slice_bands(planes, half_width=40.0)[0]).max()) > 24576
+        assert all(np.array_equal(a, b) for a, b in zip(g, o))
+    # 2. planes outside the cloud, NaN / inf planes, duplicates of one plane
+    planes = np.array([mn[0] - 50.0, np.nan, mn[0] + 7.25, mn[0] + 7.25, np.inf, mx[0] + 3.0, mx[0] - 1.5], np.float32)
+    g = gc.slice_contours(planes, "B")
+    o = oc.slice_contours(planes, "B")
+    assert all(np.array_equal(a, b) for a, b in zip(g, o))
+    # 3. caller buffers too small -> PPP_ERR_CAPACITY inside, wrapper retries with its own arrays
+    planes = synth.even_planes(c, 60)
+    small = tuple(np.empty(16, np.float64) for _ in range(3))
+    g = gc.slice_contours(planes, "B", out=small)
+    o = oc.slice_contours(planes, "B")
+    assert all(np.array_equal(a, b) for a, b in zip(g, o)) and g[1].shape[0] > 16
+    gc.close()
+    # 4. more than 8191 planes: the offsets no longer fit the mapped fetch buffer
+    c2 = synth.panel(10000, 48)
+    g2 = api.Cloud(ctx, c2)
+    o2 = po.OracleCloud(c2)
+    planes = synth.even_planes(c2, 8500)
+    g = g2.slice_contours(planes, "B")
+    o = o2.slice_contours(planes, "B")
+    assert all(np.array_equal(a, b) for a, b in zip(g, o))
+    g2.close()
