@@ -563,10 +563,12 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
 #pragma unroll
     for (int j = 0; j < K; j++)   // original index = w of the neighbour's sorted record
       id[j] = j < m ? __float_as_int(__ldg(&g.sorted[key_idx(best[j])].w)) : -1;
-    if (k == K && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 15) == 0) {
-      // a full row is 64 contiguous, 16-byte aligned bytes: four 128-bit stores instead of sixteen 32-bit ones
+    if (k == K && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 31) == 0) {
+      // a full row is 64 contiguous, 32-byte aligned bytes: two 256-bit stores instead of sixteen 32-bit ones
 #pragma unroll
-      for (int j = 0; j < K; j += 4) reinterpret_cast<int4*>(io)[j / 4] = make_int4(id[j], id[j + 1], id[j + 2], id[j + 3]);
+      for (int j = 0; j < K; j += 8)
+        st_global_256(io + j, __int_as_float(id[j]), __int_as_float(id[j + 1]), __int_as_float(id[j + 2]), __int_as_float(id[j + 3]),
+                      __int_as_float(id[j + 4]), __int_as_float(id[j + 5]), __int_as_float(id[j + 6]), __int_as_float(id[j + 7]));
       if (dout) {
 #pragma unroll
         for (int j = 0; j < K; j += 4)

@@ -183,6 +183,13 @@ __device__ __forceinline__ void accumulate_point(float acc[9], float x, float y,
   acc[8] = __fadd_rn(acc[8], z);
 }
 
+// 32 bytes with one instruction (p must be 32-byte aligned).
+__device__ __forceinline__ void st_global_256(void* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g),
+               "f"(h)
+               : "memory");
+}
+
 // Store one normal record. stride_f == 4: {nx,ny,nz,curv}; stride_f >= 8: pcl::Normal layout
 // {nx,ny,nz,0, curv,0,0,0}; other strides: nx,ny,nz at 0..2, curvature at 3.  map (optional): record
 // number of each row, negative = the row is not stored (halo rows of a slab whose records go to
@@ -195,8 +202,12 @@ __device__ __forceinline__ void store_normal(float* base, const int32_t* __restr
   }
   float* p = base + row * (int64_t)stride_f;
   if (stride_f == 8) {
-    reinterpret_cast<float4*>(p)[0] = make_float4(o[0], o[1], o[2], 0.0f);
-    reinterpret_cast<float4*>(p)[1] = make_float4(o[3], 0.0f, 0.0f, 0.0f);
+    if (((uintptr_t)base & 31) == 0) {   // one 256-bit store per pcl::Normal record (sm_100: STG.256)
+      st_global_256(p, o[0], o[1], o[2], 0.0f, o[3], 0.0f, 0.0f, 0.0f);
+    } else {
+      reinterpret_cast<float4*>(p)[0] = make_float4(o[0], o[1], o[2], 0.0f);
+      reinterpret_cast<float4*>(p)[1] = make_float4(o[3], 0.0f, 0.0f, 0.0f);
+    }
   } else if (stride_f == 4) {
     reinterpret_cast<float4*>(p)[0] = make_float4(o[0], o[1], o[2], o[3]);
   } else if (stride_f > 8) {
