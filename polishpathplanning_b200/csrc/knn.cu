@@ -575,6 +575,18 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
           reinterpret_cast<float4*>(dout)[j / 4] = make_float4(j < m ? key_d2(best[j]) : CUDART_INF_F, j + 1 < m ? key_d2(best[j + 1]) : CUDART_INF_F,
                                                                j + 2 < m ? key_d2(best[j + 2]) : CUDART_INF_F, j + 3 < m ? key_d2(best[j + 3]) : CUDART_INF_F);
       }
+    } else if ((k & 3) == 0 && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 15) == 0) {
+      // k = 4, 8, 12: rows are still 16-byte aligned
+#pragma unroll
+      for (int j = 0; j < K; j += 4) {
+        if (j < k) {
+          reinterpret_cast<int4*>(io)[j / 4] = make_int4(id[j], id[j + 1], id[j + 2], id[j + 3]);
+          if (dout)
+            reinterpret_cast<float4*>(dout)[j / 4] =
+                make_float4(j < m ? key_d2(best[j]) : CUDART_INF_F, j + 1 < m ? key_d2(best[j + 1]) : CUDART_INF_F,
+                            j + 2 < m ? key_d2(best[j + 2]) : CUDART_INF_F, j + 3 < m ? key_d2(best[j + 3]) : CUDART_INF_F);
+        }
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < K; j++) {
