@@ -261,13 +261,18 @@ def run_ours(args):
             # closes the step: no collective on the data path (parallel.PeerSink).
             t = torch.tensor([len(planes)], dtype=torch.int64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            gat["sink"] = parallel.PeerSink(ctx, dist, dev, rank, world, n_total, node_cap=max(65536, gat["own_cap"] // 4),
-                                            S_cap=int(t.item()))
-            row_map = np.where(owned, local_idx, -1).astype(np.int32)
-            with torch.cuda.stream(stream):
-                gat["row_map"] = torch.from_numpy(row_map).to(dev)
-            gat["step"] = 0
-        else:
+            try:
+                gat["sink"] = parallel.PeerSink(ctx, dist, dev, rank, world, n_total, node_cap=max(65536, gat["own_cap"] // 4),
+                                                S_cap=int(t.item()))
+                row_map = np.where(owned, local_idx, -1).astype(np.int32)
+                with torch.cuda.stream(stream):
+                    gat["row_map"] = torch.from_numpy(row_map).to(dev)
+                gat["step"] = 0
+            except RuntimeError as e:     # raised on every rank together: no CUDA IPC between these GPUs
+                if rank == 0:
+                    sys.stderr.write("bench.py: %s; using the NCCL all-gather instead\n" % e)
+                gather_mode = "nccl"
+        if gather_mode != "peer":
             with torch.cuda.stream(stream):
                 gat["own"] = torch.zeros((gat["own_cap"], 4), dtype=torch.float32, device=dev)
                 normals_d = gat["own"][:n_local]

@@ -229,14 +229,29 @@ class PeerSink:
         self._normals_bytes, self._off_bytes, self._arr_bytes = lay["normals_bytes"], lay["off_bytes"], lay["arr_bytes"]
         self._region_bytes, self._flags_at, total = lay["region_bytes"], lay["flags_at"], lay["total_bytes"]
         hbuf = torch.zeros(64, dtype=torch.uint8, device=device)
+        self.base, self._dist = None, dist
+        ok, why = 1, ""
         if rank == 0:
-            self.base, handle = ctx.peer_buffer_alloc(total)      # zero-filled
-            hbuf.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+            try:
+                self.base, handle = ctx.peer_buffer_alloc(total)      # zero-filled
+                hbuf.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+            except Exception as e:                                    # noqa: BLE001 - reported to every rank below
+                ok, why = 0, str(e)
         dist.broadcast(hbuf, 0)
         if rank != 0:
-            self.base = ctx.peer_buffer_open(hbuf.cpu().numpy().tobytes())
+            try:
+                self.base = ctx.peer_buffer_open(hbuf.cpu().numpy().tobytes())
+            except Exception as e:                                    # noqa: BLE001
+                ok, why = 0, str(e)
+        # every rank learns whether ALL mappings exist, so that callers can fall back together
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if self.base is not None:
+                (ctx.peer_buffer_free if rank == 0 else ctx.peer_buffer_close)(self.base)
+                self.base = None
+            raise RuntimeError("peer buffers are not available on every rank" + (": " + why if why else ""))
         self.normals_ptr = self.base
-        self._dist = dist
 
     def region(self, r):
         at = self.base + self._normals_bytes + r * self._region_bytes
