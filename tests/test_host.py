@@ -217,3 +217,83 @@ def test_peer_sink_layout_sections_are_disjoint_and_aligned():
         spans.sort()
         assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
         assert spans[-1][1] <= lay["total_bytes"]
+
+
+class _FakePeerCtx:
+    """Stands in for api.Context in the PeerSink protocol test: records the calls, hands out fake
+    addresses; `fail` makes the owner's allocation (or a peer's mapping) raise."""
+
+    def __init__(self, rank, fail=None):
+        self.rank, self.fail, self.calls = rank, fail, []
+
+    def peer_buffer_alloc(self, nbytes):
+        if self.fail == "alloc":
+            raise RuntimeError("no IPC")
+        self.calls.append(("alloc", nbytes))
+        return 0x10000000, bytes(range(64))
+
+    def peer_buffer_open(self, handle):
+        if self.fail == "open":
+            raise RuntimeError("cannot map")
+        assert handle == bytes(range(64))
+        self.calls.append(("open",))
+        return 0x20000000
+
+    def peer_buffer_close(self, p):
+        self.calls.append(("close", p))
+
+    def peer_buffer_free(self, p):
+        self.calls.append(("free", p))
+
+    def signal(self, p, v):
+        self.calls.append(("signal", p, v))
+
+    def wait(self, p, v):
+        self.calls.append(("wait", p, v))
+
+
+def _peer_sink_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cpu = torch.device("cpu")
+    # 1. success: one layout on all ranks (capacities are the maxima of the requests), flags, teardown order
+    ctx = _FakePeerCtx(rank)
+    sink = parallel.PeerSink(ctx, dist, cpu, rank, world, n_total=1000, node_cap=100 + 50 * rank, S_cap=7 - rank)
+    assert (sink.n_total, sink.node_cap, sink.S_cap) == (1000, 100 + 50 * (world - 1), 7)
+    lay = parallel.peer_sink_layout(world, 1000, sink.node_cap, 7)
+    assert sink.flag(1) - sink.base == lay["flags_at"] + 128
+    assert sink.region(1)["y"] - sink.base == lay["normals_bytes"] + lay["region_bytes"] + lay["off_bytes"]
+    sink.delivered(3)
+    want = [("signal", sink.flag(rank), 3)] + ([("wait", sink.flag(r), 3) for r in range(1, world)] if rank == 0 else [])
+    assert ctx.calls[-len(want):] == want
+    base = sink.base
+    sink.close()
+    assert ctx.calls[-1] == (("free", base) if rank == 0 else ("close", base))
+    # 2. a failure anywhere is raised on EVERY rank (so callers can fall back together), nothing left mapped
+    for fail_rank, kind in ((0, "alloc"), (1, "open")):
+        ctx = _FakePeerCtx(rank, fail=kind if rank == fail_rank else None)
+        try:
+            parallel.PeerSink(ctx, dist, cpu, rank, world, 1000, 100, 7)
+            raised = False
+        except RuntimeError:
+            raised = True
+        assert raised
+        opened = [c for c in ctx.calls if c[0] in ("alloc", "open")]
+        released = [c for c in ctx.calls if c[0] in ("free", "close")]
+        assert len(opened) == len(released)
+    with open(os.path.join(out_dir, "ok%d" % rank), "w") as f:
+        f.write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_peer_sink_protocol(tmp_path):
+    """PeerSink's rank protocol on CPU (gloo, world 2) with a fake context: common layout, flag
+    signalling, teardown, and collective failure when a mapping is unavailable."""
+    import torch.multiprocessing as mp
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_peer_sink_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(str(tmp_path / "ok0")) and os.path.exists(str(tmp_path / "ok1"))
