@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PPP_ABI_VERSION 1
+#define PPP_ABI_VERSION 2
 
 typedef enum ppp_status {
   PPP_OK = 0,
@@ -219,6 +219,61 @@ int ppp_peer_buffer_free(ppp_ctx* ctx, void* dev_ptr);
 int ppp_dev_download(ppp_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
 /* original index of the point at sorted position p (device array of n int32) */
 const int32_t* ppp_dev_sorted_order(ppp_cloud* cloud);
+
+/* ------------------------------------------------------------------------------------------ */
+/* multi-GPU exchange (csrc/exchange.cu).  The reference is one process on one CPU; what
+ * is sharded here is its whole-cloud estimate_normal (src/Path_Generation.cpp:323-333) and its plane
+ * sweep (src/Path_Generation.cpp:689-755).  One ppp_exch per rank (= per GPU).  A cloud that starts
+ * split by ORIGINAL INDEX (rank r holds records [starts[r], starts[r+1]) of the file) is redistributed
+ * into x-slabs of equal point count plus a halo by kernels that store straight into the destination
+ * GPU's memory over NVLink (no NCCL, no host staging); the received slab keeps ascending global index
+ * order, so all tie-breaks are those of the single-GPU run.  Results travel the same way: every normal
+ * record goes from the search kernel to its HOME rank (the rank holding that original index range),
+ * contour nodes go to rank 0's region.                                                            */
+typedef struct ppp_exch ppp_exch;
+#define PPP_EXCH_MAX_RANKS 16
+/* starts: world + 1 ascending offsets from 0 (starts[world] = total points).  cap_recv: capacity of the
+ * receive buffer in points (own slab + halo copies).  S_cap / node_cap: capacity of one rank's contour
+ * region (planes / nodes).  normal_stride_bytes: 16 {nx,ny,nz,curvature} or 32 (pcl::Normal).      */
+int ppp_exch_create(ppp_ctx* ctx, int rank, int world, const int64_t* starts, int64_t cap_recv, int S_cap, int64_t node_cap,
+                    size_t normal_stride_bytes, ppp_exch** out);
+/* Tear-down between processes: every rank disconnects (unmaps the peers' arenas), the ranks meet at a
+ * barrier of their own, then every rank destroys (an arena is not freed while a peer has it mapped).  */
+int ppp_exch_disconnect(ppp_exch* ex);
+int ppp_exch_destroy(ppp_exch* ex);
+/* ranks in other processes: ship every rank's 64-byte handle to all (any transport), then connect.   */
+int ppp_exch_ipc_handle(ppp_exch* ex, unsigned char handle[PPP_PEER_HANDLE_BYTES]);
+int ppp_exch_connect_ipc(ppp_exch* ex, const unsigned char* handles /* world x 64 bytes */);
+/* ranks in this process (one process driving several contexts / GPUs): all[r] = rank r's exchange.   */
+int ppp_exch_connect_local(ppp_exch* ex, ppp_exch* const* all);
+/* Enqueue phase 0..3 of the exchange of this rank's chunk (device records; n = starts[rank+1] -
+ * starts[rank]).  One rank per process: call 0,1,2,3 back to back.  Several ranks per process: issue
+ * phase p for every rank before phase p + 1.  halo: width of the copies on either side of a slab.   */
+int ppp_exch_phase(ppp_exch* ex, int phase, const void* chunk_dev, int64_t n, size_t stride_bytes, double halo);
+/* Wait for every rank's records, then (synchronises) report the slab: n_local points of which n_owned
+ * are owned, cuts[world + 1] (rank r owns cuts[r] <= x < cuts[r+1]; -inf / +inf at the ends), global
+ * finite x-range.  PPP_ERR_CAPACITY: cap_recv too small; PPP_ERR_CUDA: a peer did not answer in time. */
+int ppp_exch_finish(ppp_exch* ex, int64_t* n_local, int64_t* n_owned, double* cuts, double x_range[2]);
+const void* ppp_exch_slab(ppp_exch* ex);          /* device: n_local records {x, y, z, bits(global index or ~index)} */
+const int32_t* ppp_exch_row_map(ppp_exch* ex);    /* device: local row -> global index, -1 for halo copies */
+void* ppp_exch_home_normals(ppp_exch* ex);        /* device: normal records of the own index range */
+/* The slab as a cloud whose normal estimators deliver each owned row's record to its home rank; with
+ * to_rank0 != 0 ppp_dev_slice_contours also writes its nodes + per-slice offsets to rank 0's region.   */
+int ppp_exch_attach(ppp_exch* ex, int to_rank0, ppp_cloud** out);
+int ppp_exch_nodes_region(ppp_exch* ex, int r, const int64_t** offsets_dev, const double** y_dev, const double** x_dev,
+                          const double** z_dev);   /* rank 0: device pointers of rank r's contour region */
+/* signal: what this rank has enqueued so far has been delivered; wait: later work of the stream sees the
+ * results of every rank (home normals complete, rank 0's regions complete).                          */
+int ppp_exch_results_signal(ppp_exch* ex);
+int ppp_exch_results_wait(ppp_exch* ex);
+int ppp_exch_check(ppp_exch* ex);                 /* PPP_OK unless a wait has timed out (synchronises) */
+/* page-lock an existing host range (e.g. a shared-memory mapping opened by every rank's process);
+ * *dev_ptr (nullable) = the address of its first byte as kernels see it.                             */
+int ppp_host_register(void* p, size_t bytes, void** dev_ptr);
+int ppp_host_unregister(void* p);
+/* stream-ordered copies between page-locked host memory and device buffers (no synchronisation)      */
+int ppp_dev_upload(ppp_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+int ppp_dev_download_async(ppp_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes);
 
 #ifdef __cplusplus
 }

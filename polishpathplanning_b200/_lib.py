@@ -74,6 +74,26 @@ SIGNATURES = {
     "ppp_peer_buffer_free": (C.c_int, [_vp, _vp]),
     "ppp_dev_download": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "ppp_dev_sorted_order": (_vp, [_vp]),
+    "ppp_exch_create": (C.c_int, [_vp, C.c_int, C.c_int, _i64p, C.c_int64, C.c_int, C.c_int64, C.c_size_t, C.POINTER(_vp)]),
+    "ppp_exch_destroy": (C.c_int, [_vp]),
+    "ppp_exch_disconnect": (C.c_int, [_vp]),
+    "ppp_exch_ipc_handle": (C.c_int, [_vp, _vp]),
+    "ppp_exch_connect_ipc": (C.c_int, [_vp, _vp]),
+    "ppp_exch_connect_local": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "ppp_exch_phase": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_size_t, C.c_double]),
+    "ppp_exch_finish": (C.c_int, [_vp, _i64p, _i64p, _f64p, _f64p]),
+    "ppp_exch_slab": (_vp, [_vp]),
+    "ppp_exch_row_map": (_vp, [_vp]),
+    "ppp_exch_home_normals": (_vp, [_vp]),
+    "ppp_exch_attach": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "ppp_exch_nodes_region": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    "ppp_exch_results_signal": (C.c_int, [_vp]),
+    "ppp_exch_results_wait": (C.c_int, [_vp]),
+    "ppp_exch_check": (C.c_int, [_vp]),
+    "ppp_host_register": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "ppp_dev_upload": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "ppp_dev_download_async": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "ppp_host_unregister": (C.c_int, [_vp]),
 }
 
 _lib = None

@@ -111,6 +111,23 @@ class Context:
         check(self.lib.ppp_dev_download(self._h, _ptr(out), _vp(dev_ptr), out.nbytes))
         return out
 
+    def upload(self, dev_ptr, host_ptr, nbytes):
+        """Stream-ordered host -> device copy (host memory should be page-locked); does not synchronise."""
+        check(self.lib.ppp_dev_upload(self._h, _vp(dev_ptr), _vp(host_ptr), int(nbytes)))
+
+    def download_async(self, host_ptr, dev_ptr, nbytes):
+        """Stream-ordered device -> host copy; does not synchronise."""
+        check(self.lib.ppp_dev_download_async(self._h, _vp(host_ptr), _vp(dev_ptr), int(nbytes)))
+
+    def host_register(self, host_ptr, nbytes):
+        """Page-lock an existing host range; returns the address kernels use for its first byte."""
+        d = C.c_void_p(0)
+        check(self.lib.ppp_host_register(_vp(host_ptr), int(nbytes), C.byref(d)))
+        return d.value
+
+    def host_unregister(self, host_ptr):
+        check(self.lib.ppp_host_unregister(_vp(host_ptr)))
+
     def pinned_empty(self, shape, dtype):
         """numpy array over pinned host memory from ppp_host_alloc (freed with the array)."""
         dtype = np.dtype(dtype)
@@ -131,11 +148,14 @@ class Cloud:
     """points: float32 (N, stride_floats) host array (stride 8 = pcl::PointXYZRGB) or, with
     device_ptr=..., a device buffer of n records of stride_bytes."""
 
-    def __init__(self, ctx, points=None, device_ptr=None, n=None, stride_bytes=None):
+    def __init__(self, ctx, points=None, device_ptr=None, n=None, stride_bytes=None, handle=None):
         self.ctx = ctx
         self.lib = ctx.lib
         h = _vp()
-        if device_ptr is not None:
+        if handle is not None:         # an existing ppp_cloud* (e.g. from ppp_exch_attach); owned from here on
+            h = handle
+            self.n = int(self.lib.ppp_cloud_size(h))
+        elif device_ptr is not None:
             check(self.lib.ppp_dev_cloud_attach(ctx._h, _vp(device_ptr), int(n), int(stride_bytes), C.byref(h)))
             self.n = int(n)
         else:

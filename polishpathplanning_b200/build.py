@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libppp_gpu.so")
 OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["api.cu", "scan.cu", "grid.cu", "knn.cu", "slices.cu"]
+SOURCES = ["api.cu", "scan.cu", "grid.cu", "knn.cu", "slices.cu", "exchange.cu"]
 HEADERS = ["ppp_internal.cuh", "ppp_device.cuh", "sortnet.cuh", os.path.join("..", "..", "include", "ppp_gpu.h")]
 
 NVCC_FLAGS = [

@@ -35,6 +35,7 @@ struct SearchParams {
   const int64_t* offsets;
   float* normals;
   const int32_t* nmap;  // optional row map for the normal records (row -> record, < 0: not stored)
+  const NormalRoute* route;  // optional: records go to their home rank's buffer (multi-GPU)
   int nsf;
   float vpx, vpy, vpz;
   unsigned flags;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
       }
       normal_from_accumulators(acc, cnt, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
     }
-    store_normal(P.normals, P.nmap, row, P.nsf, o);
+    store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
   }
 }
 
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
         }
         normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
       }
-      store_normal(P.normals, P.nmap, row, P.nsf, o);
+      store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
     }
   } else {
     // long lists: park the sorted keys in this thread's shared-memory column (K slots) and walk
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
         }
         normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
       }
-      store_normal(P.normals, P.nmap, row, P.nsf, o);
+      store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
     }
   }
 }
@@ -429,9 +430,9 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
 constexpr int C_SLOTS = 32;   // keys ordered per network pass
 constexpr int C_STORE = 36;   // storage slots: U spare ones, so a pass is only forced beyond 32 occupied
 
-__global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
+template <int BD>
+__global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_knn16c(SearchParams P) {
   extern __shared__ u64 s_keys[];
-  constexpr int BD = 128;
   constexpr int K = 16;
   const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
   const GridView& g = P.g;
@@ -452,6 +453,10 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
   const bool fin = valid && finite3(qx, qy, qz);
   const bool act = fin && g.n_sorted > 0;
   u64* store = s_keys + threadIdx.x;  // slot j of this thread at store[j * BD]
+  // 32-bit shared-window address of slot 0: the candidate loop advances a 32-bit cursor (one
+  // predicated add per accepted candidate) instead of a 64-bit generic pointer
+  const unsigned store_sa = (unsigned)__cvta_generic_to_shared(store);
+  constexpr unsigned SLOT_B = BD * 8;
   const int R = P.R0;
   int cu = 0, cv = 0;
   // Acceptance threshold on d2 alone, INCLUSIVE: a candidate that ties the current K-th distance is
@@ -466,6 +471,7 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
   }
   int ns = 0;            // occupied slots
   bool ambiguous = false;
+  const int last = max(g.n_sorted - 1, 0);
 
   auto flush = [&]() {
     unsigned c[C_SLOTS];
@@ -479,23 +485,14 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
     // the 17th) is not decided by the composite key
 #pragma unroll
     for (int i = 0; i < K; i++) ambiguous |= (i + 1 < ns) && ((c[i] ^ c[i + 1]) < 32u);
-    if (ns > K) {
-      u64 keep[K];
+    // the K smallest, in order, to slots 0..K-1 (INF padded while fewer than K are known)
+    u64 keep[K];
 #pragma unroll
-      for (int i = 0; i < K; i++) keep[i] = store[(c[i] & 31u) * BD];
+    for (int i = 0; i < K; i++) keep[i] = i < ns ? store[(c[i] & 31u) * BD] : PPP_KEY_INF;
 #pragma unroll
-      for (int i = 0; i < K; i++) store[i * BD] = keep[i];
-      ns = K;
-      tau = fminf(tau, key_d2(keep[K - 1]));
-    } else {
-      // fewer than K so far: still put them in sorted order (cheap, and the final flush relies on it)
-      u64 keep[K];
-#pragma unroll
-      for (int i = 0; i < K; i++) keep[i] = i < ns ? store[(c[i] & 31u) * BD] : PPP_KEY_INF;
-#pragma unroll
-      for (int i = 0; i < K; i++) store[i * BD] = keep[i];
-      if (ns == K) tau = fminf(tau, key_d2(keep[K - 1]));
-    }
+    for (int i = 0; i < K; i++) store[i * BD] = keep[i];
+    if (ns >= K) tau = fminf(tau, key_d2(keep[K - 1]));
+    ns = min(ns, K);
   };
 
   constexpr int U = 4;
@@ -516,28 +513,29 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
     const int n_it = (__reduce_max_sync(0xffffffffu, e - s) + U - 1) / U + (j - 2 * R > 0 ? 1 : 0);
     // flush when some lane could run out of slots in the next iteration; the drain row flushes once
     const int trig = min(C_SLOTS - U, (2 * R + 1 - j) * C_SLOTS - 1);
+    unsigned wsa = store_sa + (unsigned)ns * SLOT_B;
+    const unsigned trig_sa = store_sa + (unsigned)trig * SLOT_B;
+    int i0 = s;
 #pragma unroll 1
-    for (int it = 0; it < n_it; it++) {
+    for (int it = 0; it < n_it; it++, i0 += U) {
       float4 c4[U];
-      bool in[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        int i = s + it * U + u;
-        in[u] = i < e;
-        c4[u] = __ldg(g.sorted + (in[u] ? i : 0));
-      }
-      u64* wptr = store + ns * BD;
+      for (int u = 0; u < U; u++) c4[u] = __ldg(g.sorted + min(i0 + u, last));   // clamped: always a valid record
 #pragma unroll
       for (int u = 0; u < U; u++) {
         float d2 = d2_flann(qx, qy, qz, c4[u].x, c4[u].y, c4[u].z);
-        if (in[u] && d2 <= tau) {
-          *wptr = make_key(d2, s + it * U + u);
-          wptr += BD;
+        if (i0 + u < e && d2 <= tau) {
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(wsa), "r"(i0 + u), "r"(__float_as_uint(d2)) : "memory");
+          wsa += SLOT_B;
         }
       }
-      ns = (int)(wptr - store) / BD;
-      if (__any_sync(0xffffffffu, ns > trig)) flush();
+      if (__any_sync(0xffffffffu, wsa > trig_sa)) {
+        ns = (int)((wsa - store_sa) / SLOT_B);
+        flush();
+        wsa = store_sa + (unsigned)ns * SLOT_B;
+      }
     }
+    ns = (int)((wsa - store_sa) / SLOT_B);
   }
   if (!valid) return;
   // slots 0..15 now hold the 16 smallest keys in order (INF padded)
@@ -550,76 +548,75 @@ __global__ void __launch_bounds__(128, 7) k_knn16c(SearchParams P) {
     return;
   }
   const int k = P.cap;
-  u64 best[K];
+  int m = 0;  // neighbours found (the list is sorted and INF padded)
 #pragma unroll
-  for (int i = 0; i < K; i++) best[i] = act ? store[i * BD] : PPP_KEY_INF;
-  int m = 0;
+  for (int j = 0; j < K; j++) m += (act && j < k && (unsigned)(store[j * BD] >> 32) != 0xFFFFFFFFu) ? 1 : 0;
+  int32_t* io = P.idx_out ? P.idx_out + row * (int64_t)k : nullptr;
+  float* dout = (P.idx_out && P.d2_out) ? P.d2_out + row * (int64_t)k : nullptr;
+  const bool al32 = k == K && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 31) == 0;
+  const bool al16 = (k & 3) == 0 && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 15) == 0;
+  const bool want_n = P.normals && fin && m >= 3;
+  const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
+  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float kx = 0.f, ky = 0.f, kz = 0.f;
+  // Eight neighbours at a time: ONE gather of the neighbour's sorted record serves both outputs (its
+  // coordinates for the covariance, its original index for the id list); eight records in flight keep
+  // the register count where the candidate loop wants it.
 #pragma unroll
-  for (int j = 0; j < K; j++) m += (j < k && best[j] != PPP_KEY_INF) ? 1 : 0;
-  if (P.idx_out) {
-    int32_t* io = P.idx_out + row * (int64_t)k;
-    float* dout = P.d2_out ? P.d2_out + row * (int64_t)k : nullptr;
-    int32_t id[K];
+  for (int jb = 0; jb < K; jb += 8) {
+    if (jb >= k) break;
+    float4 nb[8];
+    float dd[8];
 #pragma unroll
-    for (int j = 0; j < K; j++)   // original index = w of the neighbour's sorted record
-      id[j] = j < m ? __float_as_int(__ldg(&g.sorted[key_idx(best[j])].w)) : -1;
-    if (k == K && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 31) == 0) {
-      // a full row is 64 contiguous, 32-byte aligned bytes: two 256-bit stores instead of sixteen 32-bit ones
+    for (int u = 0; u < 8; u++) {
+      const u64 key = store[(jb + u) * BD];
+      const bool has = jb + u < m;
+      nb[u] = has ? __ldg(g.sorted + key_idx(key)) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      dd[u] = has ? key_d2(key) : CUDART_INF_F;
+    }
+    if (io) {
+      if (al32) {
+        // a full row is 64 contiguous, 32-byte aligned bytes: two 256-bit stores instead of sixteen 32-bit ones
+        st_global_256(io + jb, nb[0].w, nb[1].w, nb[2].w, nb[3].w, nb[4].w, nb[5].w, nb[6].w, nb[7].w);
+        if (dout) {
+          reinterpret_cast<float4*>(dout + jb)[0] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+          reinterpret_cast<float4*>(dout + jb)[1] = make_float4(dd[4], dd[5], dd[6], dd[7]);
+        }
+      } else if (al16) {
+        // k = 4, 8, 12: rows are still 16-byte aligned
+        reinterpret_cast<float4*>(io + jb)[0] = make_float4(nb[0].w, nb[1].w, nb[2].w, nb[3].w);
+        if (dout) reinterpret_cast<float4*>(dout + jb)[0] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        if (jb + 4 < k) {
+          reinterpret_cast<float4*>(io + jb)[1] = make_float4(nb[4].w, nb[5].w, nb[6].w, nb[7].w);
+          if (dout) reinterpret_cast<float4*>(dout + jb)[1] = make_float4(dd[4], dd[5], dd[6], dd[7]);
+        }
+      } else {
 #pragma unroll
-      for (int j = 0; j < K; j += 8)
-        st_global_256(io + j, __int_as_float(id[j]), __int_as_float(id[j + 1]), __int_as_float(id[j + 2]), __int_as_float(id[j + 3]),
-                      __int_as_float(id[j + 4]), __int_as_float(id[j + 5]), __int_as_float(id[j + 6]), __int_as_float(id[j + 7]));
-      if (dout) {
-#pragma unroll
-        for (int j = 0; j < K; j += 4)
-          reinterpret_cast<float4*>(dout)[j / 4] = make_float4(j < m ? key_d2(best[j]) : CUDART_INF_F, j + 1 < m ? key_d2(best[j + 1]) : CUDART_INF_F,
-                                                               j + 2 < m ? key_d2(best[j + 2]) : CUDART_INF_F, j + 3 < m ? key_d2(best[j + 3]) : CUDART_INF_F);
-      }
-    } else if ((k & 3) == 0 && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 15) == 0) {
-      // k = 4, 8, 12: rows are still 16-byte aligned
-#pragma unroll
-      for (int j = 0; j < K; j += 4) {
-        if (j < k) {
-          reinterpret_cast<int4*>(io)[j / 4] = make_int4(id[j], id[j + 1], id[j + 2], id[j + 3]);
-          if (dout)
-            reinterpret_cast<float4*>(dout)[j / 4] =
-                make_float4(j < m ? key_d2(best[j]) : CUDART_INF_F, j + 1 < m ? key_d2(best[j + 1]) : CUDART_INF_F,
-                            j + 2 < m ? key_d2(best[j + 2]) : CUDART_INF_F, j + 3 < m ? key_d2(best[j + 3]) : CUDART_INF_F);
+        for (int u = 0; u < 8; u++) {
+          if (jb + u < k) {
+            io[jb + u] = __float_as_int(nb[u].w);
+            if (dout) dout[jb + u] = dd[u];
+          }
         }
       }
-    } else {
+    }
+    if (want_n) {
+      if (jb == 0 && shifted) { kx = nb[0].x; ky = nb[0].y; kz = nb[0].z; }
 #pragma unroll
-      for (int j = 0; j < K; j++) {
-        if (j < k) {
-          io[j] = id[j];
-          if (dout) dout[j] = j < m ? key_d2(best[j]) : CUDART_INF_F;
+      for (int u = 0; u < 8; u++) {
+        if (jb + u < m) {
+          float x = nb[u].x, y = nb[u].y, z = nb[u].z;
+          if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
+          accumulate_point(acc, x, y, z);
         }
       }
     }
   }
   if (P.normals) {
     float o[4];
-    if (!fin || m < 3) {
-      o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
-    } else {
-      float4 nb[K];
-#pragma unroll
-      for (int j = 0; j < K; j++)
-        if (j < m) nb[j] = __ldg(g.sorted + key_idx(best[j]));
-      float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
-      float kx = shifted ? nb[0].x : 0.f, ky = shifted ? nb[0].y : 0.f, kz = shifted ? nb[0].z : 0.f;
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-        if (j < m) {
-          float x = nb[j].x, y = nb[j].y, z = nb[j].z;
-          if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
-          accumulate_point(acc, x, y, z);
-        }
-      }
-      normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
-    }
-    store_normal(P.normals, P.nmap, row, P.nsf, o);
+    if (want_n) normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
+    else o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
+    store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
   }
 }
 
@@ -740,7 +737,7 @@ __global__ void __launch_bounds__(128, 6) k_radius_normals32(SearchParams P) {
     }
     normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
   }
-  store_normal(P.normals, P.nmap, row, P.nsf, o);
+  store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -864,7 +861,7 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
       }
       normal_from_accumulators(acc, have, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
     }
-    if (lane == 0) store_normal(P.normals, P.nmap, row, P.nsf, o);
+    if (lane == 0) store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
   }
   __syncwarp();
   }  // slot loop
@@ -937,7 +934,7 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_radius_warp(SearchParams P
     float o[4];
     if (m < 3) o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
     else normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
-    if (lane == 0) store_normal(P.normals, P.nmap, row, P.nsf, o);
+    if (lane == 0) store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
     __syncwarp();
   }
 }
@@ -1114,7 +1111,8 @@ __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
 // Self-mode outputs are written by original index of the *indexed* points only; rows of
 // non-finite points get their defaults here (idx -1 / d2 inf / NaN normals).
 __global__ void k_default_rows(const float4* __restrict__ xyz4, int64_t n, int cap, int32_t* idx_out, float* d2_out,
-                               float* normals, int nsf, const int32_t* __restrict__ nmap) {
+                               float* normals, int nsf, const int32_t* __restrict__ nmap,
+                               const NormalRoute* __restrict__ route) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = __ldg(xyz4 + i);
@@ -1126,7 +1124,7 @@ __global__ void k_default_rows(const float4* __restrict__ xyz4, int64_t n, int c
     }
   if (normals) {
     float o[4] = {CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F};
-    store_normal(normals, nmap, i, nsf, o);
+    store_normal(normals, nmap, i, nsf, o, route);
   }
 }
 
@@ -1204,11 +1202,14 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
   PPP_TRY(prepare_fast(c, P, &redo));
   int st;
   if (P.cap <= 16) {
-    const int block = 128;
+    // block size: 96 threads hold 27 warps per SM (24 KB of candidate store per block), 128 hold 24
+    int block = 96;
+    if (const char* e = getenv("PPP_KNN_BD")) { int v = atoi(e); if (v == 64 || v == 96 || v == 128) block = v; }
     size_t smem = (size_t)C_SLOTS * 8 * block;
-    PPP_CUDA(cudaFuncSetAttribute(k_knn16c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = block == 128 ? k_knn16c<128> : (block == 96 ? k_knn16c<96> : k_knn16c<64>);
+    PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned blocks = (unsigned)((P.nq + block - 1) / block);
-    PPP_LAUNCH(ctx, P.normals ? "knn_normals" : "knn", k_knn16c, blocks, block, smem, P);
+    PPP_LAUNCH(ctx, P.normals ? "knn_normals" : "knn", kern, blocks, block, smem, P);
     PPP_CHECK_LAUNCH();
     st = PPP_OK;
   }
@@ -1239,14 +1240,14 @@ int knn_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq
   ppp_ctx* ctx = c->ctx;
   SearchParams P{};
   P.g = gs.v; P.xyz4 = c->xyz4; P.q = q_dev; P.q_sf = q_stride_f; P.nq = nq; P.first = first;
-  P.cap = k; P.kk = (int)std::min<int64_t>(k, c->n_finite); P.mode = 0; P.R0 = 2; P.r2 = 0;
+  P.cap = k; P.kk = (int)std::min<int64_t>(k, c->n_finite); P.mode = 0; P.R0 = knn_block_rings(); P.r2 = 0;
   P.idx_out = idx_dev; P.d2_out = d2_dev; P.offsets = nullptr;
-  P.normals = with_normals ? normals_dev : nullptr; P.nsf = normal_stride_f; P.nmap = c->nmap;
+  P.normals = with_normals ? normals_dev : nullptr; P.nsf = normal_stride_f; P.nmap = c->nmap; P.route = c->route;
   P.vpx = vp ? vp[0] : 0; P.vpy = vp ? vp[1] : 0; P.vpz = vp ? vp[2] : 0; P.flags = flags;
   if (!q_dev && c->n_finite < c->n && first == 0) {
     unsigned blocks = (unsigned)((c->n + 255) / 256);
     PPP_LAUNCH(ctx, "default_rows", k_default_rows, blocks, 256, 0, (const float4*)c->xyz4, c->n, k, idx_dev, d2_dev,
-               P.normals, normal_stride_f, c->nmap);
+               P.normals, normal_stride_f, c->nmap, c->route);
     PPP_CHECK_LAUNCH();
   }
   if (k <= 64 && nq > 0 && !getenv("PPP_KNN_GENERIC")) return launch_knn_fast(c, P);
@@ -1297,12 +1298,12 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int6
   SearchParams P{};
   P.g = gs.v; P.xyz4 = c->xyz4; P.q = nullptr; P.nq = count; P.first = first;
   P.mode = 1; P.r2 = r2; P.R0 = radius_rings(gs.v, std::sqrt((double)r2));
-  P.normals = normals_dev; P.nsf = normal_stride_f; P.nmap = c->nmap;
+  P.normals = normals_dev; P.nsf = normal_stride_f; P.nmap = c->nmap; P.route = c->route;
   P.vpx = vp ? vp[0] : 0; P.vpy = vp ? vp[1] : 0; P.vpz = vp ? vp[2] : 0; P.flags = flags;
   if (c->n_finite < c->n && first == 0) {
     unsigned blocks = (unsigned)((c->n + 255) / 256);
     PPP_LAUNCH(ctx, "default_rows", k_default_rows, blocks, 256, 0, (const float4*)c->xyz4, c->n, 0, (int32_t*)nullptr,
-               (float*)nullptr, normals_dev, normal_stride_f, c->nmap);
+               (float*)nullptr, normals_dev, normal_stride_f, c->nmap, c->route);
     PPP_CHECK_LAUNCH();
   }
   if (count <= 0) return PPP_OK;

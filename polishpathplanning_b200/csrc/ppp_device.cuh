@@ -195,10 +195,16 @@ __device__ __forceinline__ void st_global_256(void* p, float a, float b, float c
 // number of each row, negative = the row is not stored (halo rows of a slab whose records go to
 // another GPU's buffer over NVLink).
 __device__ __forceinline__ void store_normal(float* base, const int32_t* __restrict__ map, int64_t row, int stride_f,
-                                             const float o[4]) {
+                                             const float o[4], const NormalRoute* __restrict__ route = nullptr) {
   if (map) {
     row = __ldg(map + row);
     if (row < 0) return;
+  }
+  if (route) {   // multi-GPU: the record goes to the rank that holds this original index (NVLink store)
+    int r = 0;
+    while (r + 1 < route->world && row >= route->start[r + 1]) r++;
+    base = route->base[r];
+    row -= route->start[r];
   }
   float* p = base + row * (int64_t)stride_f;
   if (stride_f == 8) {

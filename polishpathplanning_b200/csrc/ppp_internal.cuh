@@ -77,6 +77,17 @@ struct GridView {
   int n_sorted;
 };
 
+// Where the normal records of a slab go in the multi-GPU path (exchange.cu): row i of the slab is global
+// point g = nmap[i] (negative: halo copy, not stored); its record belongs to the rank whose original
+// index range [start[r], start[r+1]) holds g and is stored at base[r] + (g - start[r]) * stride
+// -- base[r] is that rank's "home" buffer, local memory or a peer mapping over NVLink.
+constexpr int PPP_MAX_RANKS = 16;
+struct NormalRoute {
+  int world;
+  long long start[PPP_MAX_RANKS + 1];
+  float* base[PPP_MAX_RANKS];
+};
+
 struct GridStore {
   GridView v{};
   float4* sorted = nullptr;
@@ -130,6 +141,7 @@ struct ppp_cloud {
   double *ext_y = nullptr, *ext_x = nullptr, *ext_z = nullptr;  // optional caller-owned node buffers
   int64_t ext_cap = 0;
   const int32_t* nmap = nullptr;   // ppp_dev_set_normal_row_map
+  const NormalRoute* route = nullptr;  // device pointer (exchange.cu); with nmap: normals go to their home rank
   int64_t max_band_hint = 0;       // largest band of the last sync-free slicing call (sizes its shared memory)
   int64_t* ext_off = nullptr;      // ppp_dev_set_contour_offsets_buffer
   int64_t ext_off_cap = 0;
@@ -228,6 +240,7 @@ int scan_exclusive_i32_to_i64(ppp_ctx* ctx, const int32_t* in, int64_t* out, int
 int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes);
 int cloud_get_grid(ppp_cloud* c, double h, GridStore** out);
 double cloud_cell_for_k(const ppp_cloud* c, int k);
+int knn_block_rings();
 double cloud_cell_for_radius(const ppp_cloud* c, double r);
 
 // knn.cu

@@ -6,17 +6,32 @@ owns the points (and the slicing planes) of one x-interval and additionally hold
 `halo` mm on both sides, so that
   * the k nearest / radius neighbours of every OWNED point, and
   * the +-half_width band of every OWNED plane plus the nearest-neighbour reach of its pairing
-are all inside the rank's local cloud: no data-path collective is needed; the only exchange is the
-gather of results to rank 0 (normals by original index, contour nodes by plane), which is what
-the reference's downstream Spline / path connection consumes on the host.
+are all inside the rank's local cloud.
+
+Data path of one step (bench.py --gpus N, tools/multi_gpu_check.py):
+  1. the cloud starts in ONE host buffer that every rank's process has mapped (SharedHost); rank r
+     copies the records of its ORIGINAL INDEX range to its GPU over its own PCIe link;
+  2. Exchange (csrc/exchange.cu): hand-written kernels redistribute the records into x-slabs + halo by
+     storing straight into the owner GPU's memory over NVLink (no NCCL collective on the data path);
+  3. every rank runs the single-GPU path on its slab; each normal record goes from the search kernel to
+     its HOME rank (the rank that holds that original index range), contour nodes go to rank 0's region
+     or straight into the shared host buffer;
+  4. every rank copies the normals of its index range into the ONE host result array over its own PCIe
+     link; rank 0 orders the contour nodes by plane (assemble_contours): the arrays a Spline consumer
+     (include/Spline.h:10-20) and path connection read are complete on one host.
 
 Exactness guard: `halo_violations` reports owned points whose k-th neighbour distance reaches the
 edge of the local x-extent (they would need a wider halo); callers re-run those with a wider halo
 (the synthetic panels never trigger it with the default 12 mm).
 
-The functions here are backend-agnostic (numpy in / numpy out) so the world_size-2 gloo tests can
-drive them on CPU with the oracle standing in for the CUDA library.
+The slab helpers are backend-agnostic (numpy in / numpy out) so the world_size-2 gloo tests can
+drive them on CPU; Exchange / SharedHost take the context object as an argument, which lets those tests
+exercise the rank protocol with a stand-in.
 """
+import ctypes as C
+import mmap
+import os
+
 import numpy as np
 
 
@@ -111,187 +126,248 @@ def assemble_contours(S, per_rank):
     return goff, y, x, z
 
 
-# -------------------------------------------------------------------------------------------------
-# Device-side redistribution: the exchange step of the multi-GPU path (NCCL all-to-all-v).
-# -------------------------------------------------------------------------------------------------
-IDX_COL = 5    # pcl::PointXYZRGB padding floats carry the global point index (as int32 bits) ...
-OWNED_COL = 6  # ... and the "owned by this rank" flag while a record travels between ranks
 
-
-def redistribute(dist, chunk, global_start, rank, world, halo, bins=4096):
-    """Spatial redistribution of a cloud that starts out split by ORIGINAL INDEX (rank r holds the
-    records [global_start, global_start + len(chunk)) of the file, in order), e.g. each rank read
-    its share of the PCD.  Afterwards rank r holds every point of its x-slab plus the halo copies
-    from its neighbours, still in ascending global index order (so index tie-breaks are those of
-    the single-GPU run).
-
-    chunk: torch float32 (n_r, 8) PointXYZRGB records on the rank's device (or CPU with gloo).
-    Collectives: all_reduce (x range, 4096-bin x histogram -> equal-count cuts), all_to_all_single
-    (counts, then the records: the halo exchange).  Returns (local_records, global_idx int64,
-    owned bool, cuts float64 tensor on CPU)."""
-    import torch
-    dev = chunk.device
-    n = chunk.shape[0]
-    x = chunk[:, 0]
-    fin = torch.isfinite(chunk[:, 0]) & torch.isfinite(chunk[:, 1]) & torch.isfinite(chunk[:, 2])
-    big = torch.finfo(torch.float32).max
-    lo = torch.where(fin, x, torch.full_like(x, big)).min() if n else torch.tensor(big, device=dev)
-    hi = torch.where(fin, x, torch.full_like(x, -big)).max() if n else torch.tensor(-big, device=dev)
-    rng = torch.stack([lo, -hi]).to(torch.float64)
-    dist.all_reduce(rng, op=dist.ReduceOp.MIN)
-    x_min, x_max = float(rng[0]), float(-rng[1])
-    span = max(x_max - x_min, 1e-9)
-    # equal-count cuts from a global histogram (identical on every rank)
-    b = torch.clamp(((x.to(torch.float64) - x_min) / span * bins).floor().to(torch.int64), 0, bins - 1)
-    hist = torch.bincount(b[fin], minlength=bins).to(torch.int64)
-    dist.all_reduce(hist)
-    cum = torch.cumsum(hist, 0).cpu().numpy()
-    total = int(cum[-1])
-    cuts = [-np.inf]
-    for r in range(1, world):
-        k = int(np.searchsorted(cum, total * r / world, side="left"))
-        cuts.append(x_min + span * (k + 1) / bins)
-    cuts.append(np.inf)
-    cuts = np.asarray(cuts, np.float64)
-    cuts_t = torch.tensor(cuts[1:-1], dtype=torch.float64, device=dev)
-    x64 = x.to(torch.float64)
-    owner = torch.bucketize(x64, cuts_t, right=True)           # cut[r] <= x < cut[r+1]
-    owner = torch.where(fin, owner, torch.zeros_like(owner))      # non-finite points stay with rank 0
-    rec = chunk.clone()
-    gidx = torch.arange(global_start, global_start + n, device=dev, dtype=torch.int32)
-    rec[:, IDX_COL] = gidx.view(torch.float32)
-    send_parts, counts = [], []
-    cl = torch.tensor(cuts, dtype=torch.float64, device=dev)
-    for d in range(world):
-        own = owner == d
-        near = fin & ~own & (x64 >= cl[d] - halo) & (x64 < cl[d + 1] + halo)
-        sel = own | near
-        part = rec[sel]
-        part[:, OWNED_COL] = own[sel].to(torch.float32)
-        send_parts.append(part)
-        counts.append(part.shape[0])
-    send = torch.cat(send_parts, 0) if send_parts else rec[:0]
-    cnt_s = torch.tensor(counts, dtype=torch.int64, device=dev)
-    cnt_r = torch.empty_like(cnt_s)
-    dist.all_to_all_single(cnt_r, cnt_s)
-    rc = [int(v) for v in cnt_r.cpu()]
-    recv = torch.empty((sum(rc), chunk.shape[1]), dtype=chunk.dtype, device=dev)
-    dist.all_to_all_single(recv, send, output_split_sizes=rc, input_split_sizes=counts)
-    g = recv[:, IDX_COL].contiguous().view(torch.int32).to(torch.int64)
-    owned = recv[:, OWNED_COL] > 0.5
-    local = recv.clone()
-    local[:, IDX_COL] = 0.0
-    local[:, OWNED_COL] = 0.0
-    return local, g, owned, cuts
+def index_ranges(n_total, world):
+    """starts[world + 1]: rank r holds the records [starts[r], starts[r+1]) of the file."""
+    return np.asarray([(int(n_total) * r) // int(world) for r in range(int(world) + 1)], np.int64)
 
 
 # -------------------------------------------------------------------------------------------------
-# Result delivery without a collective: rank 0 owns the global result arrays, every rank's kernels
-# store into them over NVLink (CUDA IPC mapping), and a stream-ordered flag per rank tells rank 0
-# when a step's results have landed.
+# Exchange: the device-side redistribution + result delivery (csrc/exchange.cu, include/ppp_gpu.h).
 # -------------------------------------------------------------------------------------------------
-def peer_sink_layout(world, n_total, node_cap, S_cap):
-    """Byte layout of the PeerSink buffer (every section 256-byte aligned):
-    [normals n_total x 16][rank 0: offsets | y | x | z] ... [rank world-1: ...][flags world x 128]."""
-    a256 = lambda v: (int(v) + 255) // 256 * 256
-    normals_bytes = a256(int(n_total) * 16)
-    off_bytes = a256((int(S_cap) + 1) * 8)
-    arr_bytes = a256(int(node_cap) * 8)
-    region_bytes = off_bytes + 3 * arr_bytes
-    flags_at = normals_bytes + int(world) * region_bytes
-    return {"normals_bytes": normals_bytes, "off_bytes": off_bytes, "arr_bytes": arr_bytes, "region_bytes": region_bytes,
-            "flags_at": flags_at, "total_bytes": flags_at + int(world) * 128}
+class Exchange:
+    """One rank's end of the multi-GPU exchange.  `ctx` is an api.Context.
 
+    exchange(chunk_ptr, n, stride, halo) enqueues the four phases; finish() waits for every rank's
+    records and reports the slab; attach() wraps the slab as a Cloud whose normal estimators deliver
+    every owned row's record to its home rank; results_signal() / results_wait() close the step."""
 
-class PeerSink:
-    """Global result arrays on rank 0, written in place by all ranks.
+    def __init__(self, ctx, rank, world, starts, cap_recv, S_cap, node_cap, normal_stride_bytes=32):
+        from . import api
+        self._api = api
+        self.ctx, self.lib = ctx, ctx.lib
+        self.rank, self.world = int(rank), int(world)
+        self.starts = np.ascontiguousarray(starts, np.int64)
+        assert self.starts.shape[0] == self.world + 1
+        self.cap_recv, self.S_cap, self.node_cap = int(cap_recv), int(S_cap), int(node_cap)
+        self.normal_stride_bytes = int(normal_stride_bytes)
+        h = C.c_void_p()
+        api.check(self.lib.ppp_exch_create(ctx._h, self.rank, self.world, self.starts.ctypes.data_as(C.POINTER(C.c_int64)),
+                                           self.cap_recv, self.S_cap, self.node_cap, self.normal_stride_bytes, C.byref(h)))
+        self._h = h
 
-    Layout of the one peer buffer (rank 0's HBM):
-      normals   n_total x 16 B   {nx, ny, nz, curvature} in ORIGINAL index order
-      per rank  offsets (S_cap + 1) int64, then y / x / z: node_cap doubles each
-      flags     world x 128 B    flag r = number of the last step rank r has delivered
+    # -- wiring -------------------------------------------------------------------------------------
+    def handle(self):
+        buf = (C.c_ubyte * 64)()
+        self._api.check(self.lib.ppp_exch_ipc_handle(self._h, buf))
+        return bytes(buf)
 
-    Every rank passes `normals_ptr` with its local->global row map to the search
-    (Cloud.dev_set_normal_row_map + dev_normals_*), calls attach(cloud) before dev_slice_contours and
-    delivered(step) after it.  On rank 0, delivered() also makes the stream wait for every peer's flag,
-    so work queued behind it (and a host sync) sees all ranks' results of that step.  There is no ack
-    back to the writers: a consumer that reads while the next step runs must double-buffer.
-    """
+    def connect_ipc(self, handles):
+        """handles: one 64-byte handle per rank (the own entry is ignored)."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * self.world
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._api.check(self.lib.ppp_exch_connect_ipc(self._h, buf))
 
-    def __init__(self, ctx, dist, device, rank, world, n_total, node_cap, S_cap):
+    @staticmethod
+    def connect_local(exchanges):
+        """All ranks live in this process (loop-back on one GPU, or one process driving several GPUs)."""
+        arr = (C.c_void_p * len(exchanges))(*[e._h for e in exchanges])
+        for e in exchanges:
+            e._api.check(e.lib.ppp_exch_connect_local(e._h, arr))
+
+    @classmethod
+    def over_dist(cls, ctx, dist, device, rank, world, n_total, cap_recv, S_cap, node_cap, normal_stride_bytes=32, factory=None):
+        """One exchange per torch.distributed rank: agrees on the capacities (maxima over the ranks),
+        creates the arenas, all-gathers the IPC handles and connects.  A failure on any rank is raised on
+        EVERY rank, with nothing left allocated, so that callers can react together."""
         import torch
-        self.ctx, self.rank, self.world = ctx, rank, world
-        # one layout for all ranks: capacities are the maxima over the ranks' requests
-        caps = torch.tensor([int(n_total), int(node_cap), int(S_cap)], dtype=torch.int64, device=device)
+        caps = torch.tensor([int(cap_recv), int(S_cap), int(node_cap)], dtype=torch.int64, device=device)
         dist.all_reduce(caps, op=dist.ReduceOp.MAX)
-        self.n_total, self.node_cap, self.S_cap = (int(v) for v in caps.tolist())
-        lay = peer_sink_layout(world, self.n_total, self.node_cap, self.S_cap)
-        self._normals_bytes, self._off_bytes, self._arr_bytes = lay["normals_bytes"], lay["off_bytes"], lay["arr_bytes"]
-        self._region_bytes, self._flags_at, total = lay["region_bytes"], lay["flags_at"], lay["total_bytes"]
+        cap_recv, S_cap, node_cap = (int(v) for v in caps.tolist())
+        ex, ok, why = None, 1, ""
         hbuf = torch.zeros(64, dtype=torch.uint8, device=device)
-        self.base, self._dist = None, dist
-        ok, why = 1, ""
-        if rank == 0:
-            try:
-                self.base, handle = ctx.peer_buffer_alloc(total)      # zero-filled
-                hbuf.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
-            except Exception as e:                                    # noqa: BLE001 - reported to every rank below
-                ok, why = 0, str(e)
-        dist.broadcast(hbuf, 0)
-        if rank != 0:
-            try:
-                self.base = ctx.peer_buffer_open(hbuf.cpu().numpy().tobytes())
-            except Exception as e:                                    # noqa: BLE001
-                ok, why = 0, str(e)
-        # every rank learns whether ALL mappings exist, so that callers can fall back together
+        try:
+            ex = (factory or cls)(ctx, rank, world, index_ranges(n_total, world), cap_recv, S_cap, node_cap, normal_stride_bytes)
+            hbuf.copy_(torch.frombuffer(bytearray(ex.handle()), dtype=torch.uint8))
+        except Exception as e:                                         # noqa: BLE001 - reported to every rank below
+            ok, why = 0, str(e)
+        all_h = [torch.zeros_like(hbuf) for _ in range(world)]
+        dist.all_gather(all_h, hbuf)
         flag = torch.tensor([ok], dtype=torch.int32, device=device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            try:
+                ex.connect_ipc([t.cpu().numpy().tobytes() for t in all_h])
+            except Exception as e:                                     # noqa: BLE001
+                ok, why = 0, str(e)
+            flag = torch.tensor([ok], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if int(flag.item()) == 0:
-            if self.base is not None:
-                (ctx.peer_buffer_free if rank == 0 else ctx.peer_buffer_close)(self.base)
-                self.base = None
-            raise RuntimeError("peer buffers are not available on every rank" + (": " + why if why else ""))
-        self.normals_ptr = self.base
+            if ex is not None:
+                ex.close(dist)
+            else:
+                dist.barrier()       # the barrier inside the others' close()
+            raise RuntimeError("the exchange could not be set up on every rank" + (": " + why if why else ""))
+        return ex
 
-    def region(self, r):
-        at = self.base + self._normals_bytes + r * self._region_bytes
-        return {"off": at, "y": at + self._off_bytes, "x": at + self._off_bytes + self._arr_bytes,
-                "z": at + self._off_bytes + 2 * self._arr_bytes}
+    # -- one step -----------------------------------------------------------------------------------
+    def phase(self, p, chunk_ptr, n, stride_bytes, halo):
+        self._api.check(self.lib.ppp_exch_phase(self._h, int(p), C.c_void_p(chunk_ptr), int(n), int(stride_bytes), float(halo)))
 
-    def flag(self, r):
-        return self.base + self._flags_at + 128 * r
+    def exchange(self, chunk_ptr, n, stride_bytes, halo):
+        for p in range(4):
+            self.phase(p, chunk_ptr, n, stride_bytes, halo)
 
-    def attach(self, cloud):
-        """Route the contour nodes + per-slice offsets of `cloud` into this rank's region."""
-        g = self.region(self.rank)
-        cloud.dev_set_contour_buffers(g["y"], g["x"], g["z"], self.node_cap)
-        cloud.dev_set_contour_offsets_buffer(g["off"], self.S_cap + 1)
+    def finish(self):
+        nl, no = C.c_int64(0), C.c_int64(0)
+        cuts = np.zeros(self.world + 1, np.float64)
+        xr = np.zeros(2, np.float64)
+        self._api.check(self.lib.ppp_exch_finish(self._h, C.byref(nl), C.byref(no), cuts.ctypes.data_as(C.POINTER(C.c_double)),
+                                                 xr.ctypes.data_as(C.POINTER(C.c_double))))
+        return {"n_local": nl.value, "n_owned": no.value, "cuts": cuts, "x_range": xr}
 
-    def delivered(self, step):
-        """Stream-ordered: this rank's results of `step` (1, 2, ...) are in place."""
-        self.ctx.signal(self.flag(self.rank), step)
-        if self.rank == 0:
-            for r in range(1, self.world):
-                self.ctx.wait(self.flag(r), step)
+    def attach(self, to_rank0=True):
+        h = C.c_void_p()
+        self._api.check(self.lib.ppp_exch_attach(self._h, int(bool(to_rank0)), C.byref(h)))
+        return self._api.Cloud(self.ctx, handle=h)
 
-    def read(self, S_per_rank):
-        """Rank 0, after a host sync: (normals (n_total, 4), [(offsets, y, x, z) per rank])."""
+    def results_signal(self):
+        self._api.check(self.lib.ppp_exch_results_signal(self._h))
+
+    def results_wait(self):
+        self._api.check(self.lib.ppp_exch_results_wait(self._h))
+
+    def check(self):
+        self._api.check(self.lib.ppp_exch_check(self._h))
+
+    @property
+    def slab_ptr(self):
+        return self.lib.ppp_exch_slab(self._h)
+
+    @property
+    def row_map_ptr(self):
+        return self.lib.ppp_exch_row_map(self._h)
+
+    @property
+    def home_normals_ptr(self):
+        return self.lib.ppp_exch_home_normals(self._h)
+
+    @property
+    def home_rows(self):
+        return int(self.starts[self.rank + 1] - self.starts[self.rank])
+
+    def nodes_region(self, r):
+        """Rank 0: device pointers of rank r's contour region."""
+        po, py, px, pz = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._api.check(self.lib.ppp_exch_nodes_region(self._h, int(r), C.byref(po), C.byref(py), C.byref(px), C.byref(pz)))
+        return {"off": po.value, "y": py.value, "x": px.value, "z": pz.value}
+
+    def read_home_normals(self):
+        """After results_wait + a sync: the normal records of the own index range (rows, stride/4)."""
+        return self.ctx.download(self.home_normals_ptr, (self.home_rows, self.normal_stride_bytes // 4), np.float32)
+
+    def read_nodes(self, S_per_rank):
+        """Rank 0, after results_wait + a sync: [(offsets, y, x, z) per rank]."""
         assert self.rank == 0
-        normals = self.ctx.download(self.normals_ptr, (self.n_total, 4), np.float32)
         out = []
         for r in range(self.world):
-            g = self.region(r)
-            off = self.ctx.download(g["off"], (S_per_rank[r] + 1,), np.int64)
+            g = self.nodes_region(r)
+            off = self.ctx.download(g["off"], (int(S_per_rank[r]) + 1,), np.int64)
             n = int(off[-1])
             out.append((off, self.ctx.download(g["y"], (n,), np.float64), self.ctx.download(g["x"], (n,), np.float64),
                         self.ctx.download(g["z"], (n,), np.float64)))
-        return normals, out
+        return out
+
+    def close(self, dist=None):
+        """With `dist` (ranks in different processes) this is collective: everybody unmaps the peers' arenas,
+        then, after a barrier, frees its own."""
+        if getattr(self, "_h", None):
+            if dist is not None:
+                self.lib.ppp_exch_disconnect(self._h)
+                dist.barrier()
+            self.lib.ppp_exch_destroy(self._h)
+            self._h = None
+
+
+def host_region_layout(world, n_total, normal_stride_bytes, S_cap, node_cap):
+    """Byte layout of the ONE host result buffer (every section 256-byte aligned):
+    [normals n_total x stride][rank 0: offsets (S_cap + 1) int64 | y | x | z (node_cap doubles each)] ... [rank world-1]."""
+    a256 = lambda v: (int(v) + 255) // 256 * 256
+    normals_bytes = a256(int(n_total) * int(normal_stride_bytes))
+    off_bytes = a256((int(S_cap) + 1) * 8)
+    arr_bytes = a256(max(int(node_cap), 1) * 8)
+    region_bytes = off_bytes + 3 * arr_bytes
+    return {"normals_bytes": normals_bytes, "off_bytes": off_bytes, "arr_bytes": arr_bytes, "region_bytes": region_bytes,
+            "total_bytes": normals_bytes + int(world) * region_bytes}
+
+
+class SharedHost:
+    """A host buffer that EVERY rank's process maps (POSIX shared memory) and page-locks, so that each
+    GPU moves its share over its own PCIe link and the result is one array on one host.
+
+    Rank 0 creates the backing object (a file under /dev/shm; an anonymous memfd reached through
+    /proc/<pid>/fd when /dev/shm is too small), the path travels by broadcast, the others open it.
+    `ctx` (optional): page-lock the mapping through ctx.host_register; `dev_base` is then the address
+    kernels use for byte 0."""
+
+    def __init__(self, dist, rank, world, nbytes, tag, ctx=None):
+        self.rank, self.world, self.nbytes, self.ctx, self._dist = int(rank), int(world), int(nbytes), ctx, dist
+        self._fd, self._unlink, self.dev_base, self._registered = -1, None, None, False
+        path = [None]
+        if self.rank == 0:
+            p = "/dev/shm/ppp_%s_%d" % (tag, os.getpid())
+            try:
+                fd = os.open(p, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                try:
+                    os.posix_fallocate(fd, 0, self.nbytes)          # fails now (not at first touch) if tmpfs is too small
+                    self._unlink = p
+                except OSError:
+                    os.close(fd)
+                    os.unlink(p)
+                    raise
+            except OSError:
+                fd = os.memfd_create("ppp_" + tag)
+                os.ftruncate(fd, self.nbytes)
+                p = "/proc/%d/fd/%d" % (os.getpid(), fd)
+            self._fd = fd
+            path[0] = p
+        if dist is not None and self.world > 1:
+            dist.broadcast_object_list(path, src=0)
+        if self.rank != 0:
+            self._fd = os.open(path[0], os.O_RDWR)
+        self.mm = mmap.mmap(self._fd, self.nbytes, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        self._view = (C.c_char * self.nbytes).from_buffer(self.mm)
+        self.host_base = C.addressof(self._view)
+        if ctx is not None:
+            self.dev_base = ctx.host_register(self.host_base, self.nbytes)
+            self._registered = True
+
+    def array(self, dtype, shape, offset=0):
+        """numpy view of a section (no copy)."""
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        assert offset + count * dtype.itemsize <= self.nbytes
+        return np.frombuffer(self._view, dtype=dtype, count=count, offset=int(offset)).reshape(shape)
 
     def close(self):
-        """Collective: peers unmap, then rank 0 frees."""
-        if self.rank != 0:
-            self.ctx.peer_buffer_close(self.base)
-        self._dist.barrier()
-        if self.rank == 0:
-            self.ctx.peer_buffer_free(self.base)
-        self.base = None
+        """Collective: everybody unmaps, then rank 0 removes the backing object."""
+        if self._registered:
+            self.ctx.host_unregister(self.host_base)
+            self._registered = False
+        self._view = None
+        try:
+            self.mm.close()
+        except BufferError:           # a numpy view is still alive somewhere: the mapping goes with the process
+            pass
+        if self._dist is not None and self.world > 1:
+            self._dist.barrier()
+        if self._fd >= 0:
+            os.close(self._fd)
+            self._fd = -1
+        if self._unlink:
+            try:
+                os.unlink(self._unlink)
+            except OSError:
+                pass
+            self._unlink = None

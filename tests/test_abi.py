@@ -24,7 +24,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(L, n), "libppp_gpu.so does not export %s" % n
         assert n in _lib.SIGNATURES, "python binding lacks %s" % n
     assert sorted(_lib.SIGNATURES) == names
-    assert _lib.load().ppp_abi_version() == 1
+    assert _lib.load().ppp_abi_version() == 2
 
 
 def test_no_cpu_fallback():

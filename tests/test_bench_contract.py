@@ -22,6 +22,23 @@ def test_reference_arm_prints_the_contract_line():
     assert line["gpu_launches"] == 0
 
 
+def test_reference_arm_at_n_gpus_describes_the_n_gpu_workload_and_uses_all_cores():
+    """Under torchrun (OMP_NUM_THREADS=1 in the environment) rank 0 still uses every host core, and the line's
+    config is the N-GPU workload, key for key what the GPU arm prints for the same N."""
+    sys.path.insert(0, ROOT)
+    import bench
+    env = dict(os.environ, RANK="0", WORLD_SIZE="2", LOCAL_RANK="0", OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 2
+    assert line["config"] == bench.workload_config(bench.make_cfg("cfg2", 2))
+    assert line["config"]["points_total"] == 2_000_000 and line["config"]["slices_total"] == 283
+    assert line["cpu_baseline"]["cores"] == bench.host_threads()
+    assert "2000000 points" in line["cpu_baseline"]["sample"]
+
+
 def test_reference_arm_other_ranks_print_nothing():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",

@@ -119,43 +119,99 @@ def test_gloo_world2_gather(tmp_path):
     assert np.array_equal(got["off"], ref_c[0]) and np.array_equal(got["y"], ref_c[1]) and np.array_equal(got["z"], ref_c[3])
 
 
-def _redistribute_worker(rank, world, port, out_dir):
-    import torch
+def test_exchange_model_is_a_slab_partition():
+    """The restated exchange (tests/exchange_model.py, what the GPU kernels are checked against): every
+    point owned exactly once, slabs in ascending global index, halo copies exactly the points within
+    `halo` of the slab, equal-count cuts."""
+    from exchange_model import exchange_model
+    cloud = synth.panel(40000, 4)
+    cloud[11, 0] = np.nan
+    for world, halo in ((2, 12.0), (5, 12.0), (4, 90.0)):
+        starts = parallel.index_ranges(cloud.shape[0], world)
+        slabs, info = exchange_model([cloud[starts[r]:starts[r + 1]] for r in range(world)], starts, halo)
+        cuts = info["cuts"]
+        owned_all = np.concatenate([w[w >= 0] for _, w in slabs])
+        assert np.array_equal(np.sort(owned_all), np.arange(cloud.shape[0]))
+        fin = np.isfinite(cloud[:, :3]).all(axis=1)
+        counts = [int(((w >= 0)).sum()) for _, w in slabs]
+        assert max(counts) - min(counts) <= cloud.shape[0] // 100 + 2          # 4096 bins: within 1 %
+        for r, (xyz, w) in enumerate(slabs):
+            g = np.where(w >= 0, w, ~w)
+            assert np.all(np.diff(g) > 0)
+            assert np.array_equal(xyz.view(np.uint32), cloud[g, :3].view(np.uint32))
+            x = cloud[:, 0].astype(np.float64)
+            with np.errstate(invalid="ignore"):
+                want = fin & (x >= cuts[r] - halo) & (x < cuts[r + 1] + halo)
+            want[~fin] = r == 0
+            # membership may differ from the plain x-interval only by bin rounding at the two owner limits
+            diff = np.setxor1d(np.nonzero(want)[0], g)
+            assert len(diff) <= 2
+
+
+def _sharded_host_worker(rank, world, port, out_dir):
+    """The N > 1 host flow on CPU: shared host buffers, the exchange (numpy restatement), per-slab compute
+    (oracle), normal records to their home range, contours per rank, ONE result assembled on rank 0."""
     import torch.distributed as dist
+    from exchange_model import exchange_model
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    cloud = synth.panel(12000, 17)
-    cloud[100, 1] = np.nan
-    n = cloud.shape[0]
-    a, b = (n * rank) // world, (n * (rank + 1)) // world
-    local, g, owned, cuts = parallel.redistribute(dist, torch.from_numpy(cloud[a:b].copy()), a, rank, world, 12.0)
-    local, g, owned = local.numpy(), g.numpy(), owned.numpy()
-    assert np.all(np.diff(g) > 0)                                    # ascending global index
-    assert np.array_equal(local[:, :5].view(np.uint32), cloud[g][:, :5].view(np.uint32))   # records intact
-    oc = po.OracleCloud(local)
-    nrm, _ = oc.normals(k=16)
-    _, d2 = oc.knn(16)
-    assert len(parallel.halo_violations(local, owned, d2[:, -1], cuts, rank, 12.0)) == 0
-    np.savez(os.path.join(out_dir, "r%d.npz" % rank), g=g[owned], nrm=nrm[owned])
+    n, k, halo, S = 24000, 16, 12.0, 10
+    starts = parallel.index_ranges(n, world)
+    src = parallel.SharedHost(dist, rank, world, n * 32, "t_src_%d" % port)
+    cloud_h = src.array(np.float32, (n, 8))
+    if rank == 0:
+        cloud_h[...] = synth.panel(n, 5)
     dist.barrier()
+    lay = parallel.host_region_layout(world, n, 16, S, 8000)
+    dst = parallel.SharedHost(dist, rank, world, lay["total_bytes"], "t_dst_%d" % port)
+    normals_h = dst.array(np.float32, (n, 4))
+    # exchange: every rank evaluates the restatement on the shared cloud and keeps its own slab
+    slabs, info = exchange_model([cloud_h[starts[r]:starts[r + 1]] for r in range(world)], starts, halo)
+    xyz, w = slabs[rank]
+    oc = po.OracleCloud(np.ascontiguousarray(xyz))
+    nrm, _ = oc.normals(k=k)
+    own = w >= 0
+    # "home" delivery: this rank's records land in other ranks' index ranges of the one result array
+    normals_h[w[own]] = nrm[own]
+    planes = synth.even_planes(cloud_h, S)
+    pos = parallel.owned_planes(planes, info["cuts"], rank)
+    off, y, x, z = oc.slice_contours(planes[pos], "B")
+    at = lay["normals_bytes"] + rank * lay["region_bytes"]
+    dst.array(np.int64, (len(pos) + 1,), at)[...] = off
+    for j, a in enumerate((y, x, z)):
+        dst.array(np.float64, (len(a),), at + lay["off_bytes"] + j * lay["arr_bytes"])[...] = a
+    all_pos = [None] * world
+    dist.all_gather_object(all_pos, pos.tolist())
+    dist.barrier()
+    if rank == 0:
+        per_rank = []
+        for r in range(world):
+            at = lay["normals_bytes"] + r * lay["region_bytes"]
+            o = dst.array(np.int64, (len(all_pos[r]) + 1,), at).copy()
+            arrs = [dst.array(np.float64, (int(o[-1]),), at + lay["off_bytes"] + j * lay["arr_bytes"]).copy() for j in range(3)]
+            per_rank.append((np.asarray(all_pos[r], np.int64), o) + tuple(arrs))
+        goff, gy, gx, gz = parallel.assemble_contours(S, per_rank)
+        np.savez(os.path.join(out_dir, "one_host.npz"), normals=normals_h.copy(), off=goff, y=gy, z=gz)
+    dist.barrier()
+    del cloud_h, normals_h
+    src.close()
+    dst.close()
     dist.destroy_process_group()
 
 
-def test_gloo_redistribute_exchange(tmp_path):
-    """The all-to-all-v halo exchange (CPU tensors over gloo): ownership partitions the cloud and the
-    sharded normals equal the single-process ones bit for bit."""
+def test_gloo_sharded_flow_delivers_one_host_result(tmp_path):
     import torch.multiprocessing as mp
     port = 31500 + (os.getpid() % 2000)
-    mp.spawn(_redistribute_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
-    cloud = synth.panel(12000, 17)
-    cloud[100, 1] = np.nan
-    ref, _ = po.OracleCloud(cloud).normals(k=16)
-    parts = [np.load(str(tmp_path / ("r%d.npz" % r))) for r in range(2)]
-    allg = np.concatenate([p["g"] for p in parts])
-    assert np.array_equal(np.sort(allg), np.arange(cloud.shape[0]))  # every point owned exactly once
-    full = parallel.assemble_normals(cloud.shape[0], 4, [(p["g"], p["nrm"]) for p in parts])
-    assert np.array_equal(full.view(np.uint32), ref.view(np.uint32))
+    mp.spawn(_sharded_host_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(str(tmp_path / "one_host.npz"))
+    cloud = synth.panel(24000, 5)
+    oc = po.OracleCloud(cloud)
+    ref_n, _ = oc.normals(k=16)
+    ref_c = oc.slice_contours(synth.even_planes(cloud, 10), "B")
+    assert np.array_equal(got["normals"].view(np.uint32), ref_n.view(np.uint32))
+    assert np.array_equal(got["off"], ref_c[0]) and np.array_equal(got["y"], ref_c[1]) and np.array_equal(got["z"], ref_c[3])
+    assert not [f for f in os.listdir("/dev/shm") if f.startswith("ppp_t_")]      # backing objects removed
 
 
 def test_steffen_spline_restatements_agree():
@@ -201,99 +257,81 @@ def test_sor_threshold_pass_restatements_agree():
                 assert thr == othr or (np.isnan(thr) and np.isnan(othr))
 
 
-def test_peer_sink_layout_sections_are_disjoint_and_aligned():
-    """The one buffer every rank's kernels store into: normals, per-rank node regions, flags."""
-    for world, n_total, node_cap, S_cap in ((2, 2_000_000, 270_000, 142), (8, 8_000_001, 65_536, 71), (3, 5, 1, 0)):
-        lay = parallel.peer_sink_layout(world, n_total, node_cap, S_cap)
-        spans = [(0, n_total * 16)]
+def test_host_region_layout_sections_are_disjoint_and_aligned():
+    """The one host result buffer: normals, then one contour region per rank."""
+    for world, n_total, stride, S_cap, node_cap in ((2, 2_000_000, 32, 142, 270_000), (8, 8_000_001, 16, 71, 65_536), (3, 5, 32, 0, 0)):
+        lay = parallel.host_region_layout(world, n_total, stride, S_cap, node_cap)
+        spans = [(0, n_total * stride)]
         for r in range(world):
             at = lay["normals_bytes"] + r * lay["region_bytes"]
             spans += [(at, at + (S_cap + 1) * 8)]
             spans += [(at + lay["off_bytes"] + j * lay["arr_bytes"], at + lay["off_bytes"] + j * lay["arr_bytes"] + node_cap * 8)
                       for j in range(3)]
-        spans += [(lay["flags_at"] + 128 * r, lay["flags_at"] + 128 * r + 4) for r in range(world)]
-        assert all(a % 256 == 0 or a >= lay["flags_at"] for a, _ in spans)
-        assert all(a % 128 == 0 for a, _ in spans)
+        assert all(a % 256 == 0 for a, _ in spans)
         spans.sort()
         assert all(spans[i][1] <= spans[i + 1][0] for i in range(len(spans) - 1))
         assert spans[-1][1] <= lay["total_bytes"]
 
 
-class _FakePeerCtx:
-    """Stands in for api.Context in the PeerSink protocol test: records the calls, hands out fake
-    addresses; `fail` makes the owner's allocation (or a peer's mapping) raise."""
+class _FakeExchange:
+    """Stands in for parallel.Exchange in the rank-protocol test: records the calls; `fail` makes the
+    creation or the connection raise on this rank."""
+    fail = None
+    log = []
 
-    def __init__(self, rank, fail=None):
-        self.rank, self.fail, self.calls = rank, fail, []
+    def __init__(self, ctx, rank, world, starts, cap_recv, S_cap, node_cap, normal_stride_bytes):
+        if _FakeExchange.fail == "create":
+            raise RuntimeError("no memory")
+        self.rank, self.world, self.caps, self.starts = rank, world, (cap_recv, S_cap, node_cap), list(starts)
+        _FakeExchange.log.append(("create", rank))
 
-    def peer_buffer_alloc(self, nbytes):
-        if self.fail == "alloc":
-            raise RuntimeError("no IPC")
-        self.calls.append(("alloc", nbytes))
-        return 0x10000000, bytes(range(64))
+    def handle(self):
+        return bytes([self.rank]) * 64
 
-    def peer_buffer_open(self, handle):
-        if self.fail == "open":
+    def connect_ipc(self, handles):
+        if _FakeExchange.fail == "connect":
             raise RuntimeError("cannot map")
-        assert handle == bytes(range(64))
-        self.calls.append(("open",))
-        return 0x20000000
+        assert [h[0] for h in handles] == list(range(self.world)) and all(len(h) == 64 for h in handles)
+        _FakeExchange.log.append(("connect", self.rank))
 
-    def peer_buffer_close(self, p):
-        self.calls.append(("close", p))
-
-    def peer_buffer_free(self, p):
-        self.calls.append(("free", p))
-
-    def signal(self, p, v):
-        self.calls.append(("signal", p, v))
-
-    def wait(self, p, v):
-        self.calls.append(("wait", p, v))
+    def close(self, dist=None):
+        if dist is not None:
+            dist.barrier()
+        _FakeExchange.log.append(("close", self.rank))
 
 
-def _peer_sink_worker(rank, world, port, out_dir):
+def _exchange_protocol_worker(rank, world, port, out_dir):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cpu = torch.device("cpu")
-    # 1. success: one layout on all ranks (capacities are the maxima of the requests), flags, teardown order
-    ctx = _FakePeerCtx(rank)
-    sink = parallel.PeerSink(ctx, dist, cpu, rank, world, n_total=1000, node_cap=100 + 50 * rank, S_cap=7 - rank)
-    assert (sink.n_total, sink.node_cap, sink.S_cap) == (1000, 100 + 50 * (world - 1), 7)
-    lay = parallel.peer_sink_layout(world, 1000, sink.node_cap, 7)
-    assert sink.flag(1) - sink.base == lay["flags_at"] + 128
-    assert sink.region(1)["y"] - sink.base == lay["normals_bytes"] + lay["region_bytes"] + lay["off_bytes"]
-    sink.delivered(3)
-    want = [("signal", sink.flag(rank), 3)] + ([("wait", sink.flag(r), 3) for r in range(1, world)] if rank == 0 else [])
-    assert ctx.calls[-len(want):] == want
-    base = sink.base
-    sink.close()
-    assert ctx.calls[-1] == (("free", base) if rank == 0 else ("close", base))
-    # 2. a failure anywhere is raised on EVERY rank (so callers can fall back together), nothing left mapped
-    for fail_rank, kind in ((0, "alloc"), (1, "open")):
-        ctx = _FakePeerCtx(rank, fail=kind if rank == fail_rank else None)
-        try:
-            parallel.PeerSink(ctx, dist, cpu, rank, world, 1000, 100, 7)
-            raised = False
-        except RuntimeError:
-            raised = True
-        assert raised
-        opened = [c for c in ctx.calls if c[0] in ("alloc", "open")]
-        released = [c for c in ctx.calls if c[0] in ("free", "close")]
-        assert len(opened) == len(released)
+    # 1. success: one set of capacities on all ranks (maxima of the requests), handles in rank order
+    _FakeExchange.fail, _FakeExchange.log = None, []
+    ex = parallel.Exchange.over_dist(None, dist, cpu, rank, world, 1001, cap_recv=700 + 10 * rank, S_cap=7 - rank,
+                                     node_cap=100 + 50 * rank, factory=_FakeExchange)
+    assert ex.caps == (700 + 10 * (world - 1), 7, 100 + 50 * (world - 1))
+    assert ex.starts == [0, 500, 1001]
+    assert _FakeExchange.log == [("create", rank), ("connect", rank)]
+    # 2. a failure anywhere is raised on EVERY rank, nothing left open
+    for fail_rank, kind in ((0, "create"), (1, "connect")):
+        _FakeExchange.fail, _FakeExchange.log = (kind if rank == fail_rank else None), []
+        with pytest.raises(RuntimeError):
+            parallel.Exchange.over_dist(None, dist, cpu, rank, world, 1001, 700, 7, 100, factory=_FakeExchange)
+        created = [c for c in _FakeExchange.log if c[0] == "create"]
+        closed = [c for c in _FakeExchange.log if c[0] == "close"]
+        assert len(created) == len(closed)
     with open(os.path.join(out_dir, "ok%d" % rank), "w") as f:
         f.write("ok")
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_gloo_peer_sink_protocol(tmp_path):
-    """PeerSink's rank protocol on CPU (gloo, world 2) with a fake context: common layout, flag
-    signalling, teardown, and collective failure when a mapping is unavailable."""
+def test_gloo_exchange_setup_protocol(tmp_path):
+    """Exchange.over_dist on CPU (gloo, world 2) with a stand-in exchange: common capacities, index ranges,
+    handle all-gather in rank order, and collective failure when any rank cannot create / connect."""
     import torch.multiprocessing as mp
     port = 33500 + (os.getpid() % 2000)
-    mp.spawn(_peer_sink_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_exchange_protocol_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(str(tmp_path / "ok0")) and os.path.exists(str(tmp_path / "ok1"))

@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""Multi-GPU parity check (run under torchrun, one rank per GPU, NCCL):
-every rank starts with 1/G of the cloud BY INDEX, the records are redistributed into x-slabs +
-halo with an NCCL all-to-all-v (parallel.redistribute), each rank runs kNN+normals and the
-contours of its planes on its slab, the results are gathered to rank 0 and compared bit for bit
-with the single-GPU run of the whole cloud."""
+"""Multi-GPU parity check (run under torchrun, one rank per GPU):
+every rank starts with 1/G of the cloud BY INDEX on its GPU, the records are redistributed into x-slabs +
+halo by the exchange kernels over NVLink (parallel.Exchange over CUDA IPC), each rank runs kNN + normals
+and the contours of its planes on its slab, normal records travel to their home rank and contour nodes to
+rank 0, and the assembled result is compared bit for bit with the single-GPU run of the whole cloud.
+Two steps, so that the per-step flags and the re-use of every buffer are exercised; the cloud changes
+between the steps so that stale data cannot pass."""
 import os
 import sys
 
@@ -22,82 +24,67 @@ def main():
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
     dist.init_process_group("nccl", device_id=dev)
-    n, k, halo, S = int(os.environ.get("PPP_CHECK_N", "400000")), 16, 12.0, 40
-    cloud = synth.panel(n, seed=23)
-    planes = synth.even_planes(cloud, S)
-    a, b = (n * rank) // world, (n * (rank + 1)) // world
-    chunk = torch.from_numpy(cloud[a:b].copy()).to(dev)
-    local, g, owned, cuts = parallel.redistribute(dist, chunk, a, rank, world, halo)
-    local = local.contiguous()
+    n, k, halo, S = int(os.environ.get("PPP_CHECK_N", "400000")), int(os.environ.get("PPP_CHECK_K", "16")), 12.0, 40
     ctx = api.Context(lr)
-    torch.cuda.synchronize()
-    c = api.Cloud(ctx, device_ptr=local.data_ptr(), n=local.shape[0], stride_bytes=32)
-    nl = local.shape[0]
-    nrm = torch.empty((nl, 4), dtype=torch.float32, device=dev)
-    idx = torch.empty((nl, k), dtype=torch.int32, device=dev)
-    d2 = torch.empty((nl, k), dtype=torch.float32, device=dev)
-    c.dev_normals_knn(k, nrm.data_ptr(), 16, idx_ptr=idx.data_ptr(), d2_ptr=d2.data_ptr())
-    ctx.sync()
-    bad = parallel.halo_violations(local.cpu().numpy(), owned.cpu().numpy(), d2[:, -1].cpu().numpy(), cuts, rank, halo)
-    assert len(bad) == 0, "halo too narrow for %d points" % len(bad)
-    pos = parallel.owned_planes(planes, cuts, rank)
-    off, y, x, z = c.slice_contours(planes[pos], "B")
-    # neighbour ids back to global numbering
-    gidx = torch.where(idx >= 0, g[idx.clamp(min=0).to(torch.int64)], torch.full_like(idx, -1, dtype=torch.int64))
-    res = parallel.gather_to_rank0(dist, [g[owned], nrm[owned], gidx[owned]], rank, world, device=dev)
-    counts = np.diff(off)
-    node_plane = np.repeat(pos, counts).astype(np.int64)
-    res2 = parallel.gather_to_rank0(dist, [node_plane, y, x, z], rank, world, device=dev)
-    # second delivery path: no collective; every rank's kernels store into rank 0's global arrays over
-    # NVLink (parallel.PeerSink), two steps to exercise the per-step flags
-    smax = torch.tensor([len(pos)], dtype=torch.int64, device=dev)
-    dist.all_reduce(smax, op=dist.ReduceOp.MAX)
-    sink = parallel.PeerSink(ctx, dist, dev, rank, world, n, node_cap=max(4096, nl // 2), S_cap=int(smax.item()))
-    row_map = torch.where(owned, g, torch.full_like(g, -1)).to(torch.int32).contiguous()
-    torch.cuda.synchronize()
-    c.dev_set_normal_row_map(row_map.data_ptr())
-    for step in (1, 2):
-        c.dev_normals_knn(k, sink.normals_ptr, 16, idx_ptr=idx.data_ptr())
-        sink.attach(c)
-        r_dev = c.dev_slice_contours(planes[pos], "B")
-        assert r_dev["total_nodes"] <= sink.node_cap
-        sink.delivered(step)
-    c.dev_set_normal_row_map(None)
-    c.dev_set_contour_buffers(None, None, None, 0)
-    c.dev_set_contour_offsets_buffer(None, 0)
-    ctx.sync()
-    all_pos = [None] * world
-    dist.all_gather_object(all_pos, pos.tolist())
+    starts = parallel.index_ranges(n, world)
+    a, b = int(starts[rank]), int(starts[rank + 1])
+    ex = parallel.Exchange.over_dist(ctx, dist, dev, rank, world, n, int((b - a) * 1.4) + 4096, S, max(4096, n // 2), 16)
     ok = True
-    if rank == 0:
-        peer_n, peer_nodes = sink.read([len(p_) for p_ in all_pos])
-        full = api.Cloud(ctx, cloud)
-        ref_n, ref_i = full.normals_knn(k, stride_floats=4, return_idx=True)
-        got_n = parallel.assemble_normals(n, 4, [(r[0], r[1]) for r in res])
-        got_i = np.full((n, k), -2, np.int64)
-        for r in res:
-            got_i[r[0]] = r[2]
-        ro, ry, rx, rz = full.slice_contours(planes, "B")
-        per_rank = []
-        for r in res2:
-            pl, yy, xx, zz = r
-            ppos = np.unique(pl)
-            o = np.concatenate([[0], np.cumsum([(pl == s).sum() for s in ppos])]).astype(np.int64)
-            per_rank.append((ppos.astype(np.int64), o, yy, xx, zz))
-        goff, gy, gx, gz = parallel.assemble_contours(S, per_rank)
-        poff, py, px, pz = parallel.assemble_contours(
-            S, [(np.asarray(all_pos[r], np.int64),) + peer_nodes[r] for r in range(world)])
-        peer_ok_n = np.array_equal(peer_n.view(np.uint32), ref_n.view(np.uint32))
-        peer_ok_c = np.array_equal(poff, ro) and np.array_equal(py, ry) and np.array_equal(px, rx) and np.array_equal(pz, rz)
-        print("MULTI_GPU_CHECK peer_normals=%s peer_contours=%s" % (peer_ok_n, peer_ok_c), flush=True)
-        ok = (np.array_equal(got_n.view(np.uint32), ref_n.view(np.uint32)) and np.array_equal(got_i, ref_i.astype(np.int64))
-              and np.array_equal(goff, ro) and np.array_equal(gy, ry) and np.array_equal(gz, rz) and peer_ok_n and peer_ok_c)
-        print("MULTI_GPU_CHECK world=%d n=%d normals_bitexact=%s knn_ids=%s contours=%s" % (
-            world, n, np.array_equal(got_n.view(np.uint32), ref_n.view(np.uint32)), np.array_equal(got_i, ref_i.astype(np.int64)),
-            np.array_equal(goff, ro) and np.array_equal(gy, ry) and np.array_equal(gz, rz)), flush=True)
-        full.close()
-    c.close()
-    sink.close()
+    for step, seed in enumerate((23, 24)):
+        cloud = synth.panel(n, seed=seed)
+        cloud[17 + step, 1] = np.nan
+        planes = synth.even_planes(cloud, S)
+        chunk = torch.from_numpy(cloud[a:b].copy()).to(dev)
+        torch.cuda.synchronize()
+        ex.exchange(chunk.data_ptr(), b - a, 32, halo)
+        info = ex.finish()
+        c = ex.attach(to_rank0=True)
+        nl = info["n_local"]
+        idx = torch.empty((nl, k), dtype=torch.int32, device=dev)
+        d2 = torch.empty((nl, k), dtype=torch.float32, device=dev)
+        c.dev_normals_knn(k, ex.home_normals_ptr, 16, idx_ptr=idx.data_ptr(), d2_ptr=d2.data_ptr())
+        pos = parallel.owned_planes(planes, info["cuts"], rank)
+        res = c.dev_slice_contours(planes[pos], "B")
+        assert res["total_nodes"] <= ex.node_cap
+        ex.results_signal()
+        ex.results_wait()
+        ctx.sync()
+        ex.check()
+        # halo wide enough for every owned point?
+        slab = ctx.download(ex.slab_ptr, (nl, 4), np.float32)
+        owned = slab[:, 3].view(np.int32) >= 0
+        bad = parallel.halo_violations(slab, owned, d2[:, -1].cpu().numpy(), info["cuts"], rank, halo)
+        assert len(bad) == 0, "halo too narrow for %d points" % len(bad)
+        home = ex.read_home_normals()
+        # neighbour ids of the owned rows in global numbering
+        w = slab[:, 3].view(np.int32)
+        g_of_row = np.where(w >= 0, w, ~w).astype(np.int64)
+        li = idx.cpu().numpy()
+        gi = np.where(li >= 0, g_of_row[np.clip(li, 0, None)], -1)
+        res1 = parallel.gather_to_rank0(dist, [g_of_row[owned], gi[owned]], rank, world, device=dev)
+        res2 = parallel.gather_to_rank0(dist, [home], rank, world, device=dev)
+        all_pos = [None] * world
+        dist.all_gather_object(all_pos, pos.tolist())
+        if rank == 0:
+            full = api.Cloud(ctx, cloud)
+            ref_n, ref_i = full.normals_knn(k, stride_floats=4, return_idx=True)
+            ro, ry, rx, rz = full.slice_contours(planes, "B")
+            full.close()
+            got_n = np.concatenate([r[0] for r in res2], axis=0)
+            got_i = np.full((n, k), -2, np.int64)
+            for r in res1:
+                got_i[r[0]] = r[1]
+            per_rank = ex.read_nodes([len(p_) for p_ in all_pos])
+            goff, gy, gx, gz = parallel.assemble_contours(S, [(np.asarray(all_pos[r], np.int64),) + per_rank[r] for r in range(world)])
+            ok_n = np.array_equal(got_n.view(np.uint32), ref_n.view(np.uint32))
+            ok_i = np.array_equal(got_i, ref_i.astype(np.int64))
+            ok_c = np.array_equal(goff, ro) and np.array_equal(gy, ry) and np.array_equal(gx, rx) and np.array_equal(gz, rz)
+            print("MULTI_GPU_CHECK world=%d n=%d k=%d step=%d normals_bitexact=%s knn_ids=%s contours=%s" % (
+                world, n, k, step, ok_n, ok_i, ok_c), flush=True)
+            ok = ok and ok_n and ok_i and ok_c
+        c.close()
+        del chunk, idx, d2
+    ex.close(dist)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()
