@@ -450,15 +450,29 @@ def measure_multi(env, cfg, steps, warmup, verify=True):
     last = {}
     region_host = ctl_bytes + lay["normals_bytes"] + rank * lay["region_bytes"]
 
+    stage = {}
+
+    def mark(name, t0):
+        """PPP_BENCH_VERBOSE: synchronise and book the wall time since t0 under `name` (breakdown pass only)."""
+        if not stage.get("on"):
+            return t0
+        ctx.sync()
+        t1 = time.perf_counter()
+        stage[name] = stage.get(name, 0.0) + (t1 - t0)
+        return t1
+
     def slab_work(to_host):
         """Everything after the records are on this GPU: exchange, the single-GPU path on the slab, results."""
+        t_s = time.perf_counter()
         ctx.timer_begin(1)
         ex.exchange(chunk_d.data_ptr(), n_r, 32, HALO_MM)
         info = ex.finish()                                             # one synchronisation: slab size, cuts, x-range
         ctx.timer_end(1)
+        t_s = mark("exchange", t_s)
         planes = make_planes(np.float32(info["x_range"][0]), np.float32(info["x_range"][1]), S)   # getMinMax3D -> sweep
         pos = parallel.owned_planes(planes, info["cuts"], rank)
         c = ex.attach(to_rank0=not to_host)
+        t_s = mark("attach", t_s)
         if to_host:     # contour nodes + per-slice offsets straight into this rank's region of the host result
             base = dst.dev_base + region_host
             c.dev_set_contour_offsets_buffer(base, S + 1)
@@ -468,11 +482,22 @@ def measure_multi(env, cfg, steps, warmup, verify=True):
         else:
             want_y = ex.nodes_region(rank)["y"] if rank == 0 else None
         c.dev_normals_knn(k, ex.home_normals_ptr, 32, idx_ptr=idx_d.data_ptr())
+        t_s = mark("index+knn", t_s)
+        ex.results_signal(ex.NORMALS)
+        if to_host:
+            # the normals of MY index range are complete once every rank has signalled: their copy to the host
+            # (copy engine, my PCIe link) then runs under the slicing kernels, which use the auxiliary stream
+            ex.results_wait(ex.NORMALS)
+            ctx.download_async(dst.host_base + ctl_bytes + a * 32, ex.home_normals_ptr, n_r * 32)
+            t_s = mark("normals wait + d2h", t_s)
         res = c.dev_slice_contours(planes[pos], PAIRING, HALF_WIDTH, True)
+        t_s = mark("slicing", t_s)
         if res["total_nodes"] > node_cap or (want_y is not None and res["total_nodes"] and res["y"] != want_y):
             raise SystemExit("bench.py: %d contour nodes exceed the result region (%d)" % (res["total_nodes"], node_cap))
-        ex.results_signal()
-        ex.results_wait()                                              # the normals of MY index range are complete
+        if not to_host:
+            ex.results_signal(ex.CONTOURS)
+            ex.results_wait(ex.NORMALS)
+            ex.results_wait(ex.CONTOURS)                               # rank 0's regions hold every rank's contours
         last.update(nodes=res["total_nodes"], members=res["total_members"], n_local=info["n_local"], n_owned=info["n_owned"],
                     planes=planes, cuts=info["cuts"], pos=pos)
         return c
@@ -494,12 +519,15 @@ def measure_multi(env, cfg, steps, warmup, verify=True):
     table = {}
 
     def host_step():
+        t_s = time.perf_counter()
         ctx.upload(chunk_d.data_ptr(), src.host_base + a * 32, n_r * 32)          # my index range, my PCIe link
+        t_s = mark("h2d", t_s)
         c = slab_work(True)
-        ctx.download_async(dst.host_base + ctl_bytes + a * 32, ex.home_normals_ptr, n_r * 32)
         ctx.sync()
         c.close()
+        t_s = time.perf_counter()
         host_barrier()
+        stage["barrier+table"] = stage.get("barrier+table", 0.0) - t_s
         if rank == 0:
             # per-plane table into the one result buffer: where each plane's y / x / z arrays start and how many
             # nodes it has -- the (n, y, x, z) a Spline is constructed from (include/Spline.h:10-20)
@@ -514,6 +542,7 @@ def measure_multi(env, cfg, steps, warmup, verify=True):
                 at_y[pos] = reg + lay["off_bytes"] + 8 * off[:-1]
             table.update(at_y=at_y, count=cnt)
         host_barrier()
+        stage["barrier+table"] += time.perf_counter()
 
     for _ in range(min(warmup, 3)):
         host_step()
@@ -524,6 +553,14 @@ def measure_multi(env, cfg, steps, warmup, verify=True):
         host_step()
     e2e_s = env.max_over_ranks(time.perf_counter() - t0)
     env.sync_all()
+    if os.environ.get("PPP_BENCH_VERBOSE"):      # untimed: the same step with a synchronise after every stage
+        stage.clear()
+        stage["on"] = True
+        for _ in range(5):
+            host_step()
+        stage.pop("on")
+        sys.stderr.write("[rank %d] e2e stages (ms, serialised): %s\n" % (rank, {kk: round(1e3 * v / 5, 3) for kk, v in stage.items()}))
+        stage.clear()
     nodes_all = int(table["count"].sum()) if rank == 0 else 0
     h2d = n_total * 32 + world * (S * 5 * 4 + 4 * S)
     d2h = n_total * 32 + (S + world) * 8 + 3 * 8 * nodes_all

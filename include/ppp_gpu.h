@@ -262,10 +262,13 @@ void* ppp_exch_home_normals(ppp_exch* ex);        /* device: normal records of t
 int ppp_exch_attach(ppp_exch* ex, int to_rank0, ppp_cloud** out);
 int ppp_exch_nodes_region(ppp_exch* ex, int r, const int64_t** offsets_dev, const double** y_dev, const double** x_dev,
                           const double** z_dev);   /* rank 0: device pointers of rank r's contour region */
-/* signal: what this rank has enqueued so far has been delivered; wait: later work of the stream sees the
- * results of every rank (home normals complete, rank 0's regions complete).                          */
-int ppp_exch_results_signal(ppp_exch* ex);
-int ppp_exch_results_wait(ppp_exch* ex);
+/* what: PPP_EXCH_NORMALS / PPP_EXCH_CONTOURS.  signal: the results of that kind this rank has enqueued so
+ * far have been delivered; wait: later work of the stream sees every rank's results of that kind (home
+ * normals complete / rank 0's regions complete).                                                       */
+#define PPP_EXCH_NORMALS 0
+#define PPP_EXCH_CONTOURS 1
+int ppp_exch_results_signal(ppp_exch* ex, int what);
+int ppp_exch_results_wait(ppp_exch* ex, int what);
 int ppp_exch_check(ppp_exch* ex);                 /* PPP_OK unless a wait has timed out (synchronises) */
 /* page-lock an existing host range (e.g. a shared-memory mapping opened by every rank's process);
  * *dev_ptr (nullable) = the address of its first byte as kernels see it.                             */

@@ -87,8 +87,8 @@ SIGNATURES = {
     "ppp_exch_home_normals": (_vp, [_vp]),
     "ppp_exch_attach": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
     "ppp_exch_nodes_region": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
-    "ppp_exch_results_signal": (C.c_int, [_vp]),
-    "ppp_exch_results_wait": (C.c_int, [_vp]),
+    "ppp_exch_results_signal": (C.c_int, [_vp, C.c_int]),
+    "ppp_exch_results_wait": (C.c_int, [_vp, C.c_int]),
     "ppp_exch_check": (C.c_int, [_vp]),
     "ppp_host_register": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
     "ppp_dev_upload": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),

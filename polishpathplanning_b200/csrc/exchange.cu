@@ -4,7 +4,7 @@
 // destination GPU's memory over NVLink / NVSwitch -- no NCCL collective, no host staging:
 //
 //   phase 0  k_ex_minmax    x-range + finite count of the local chunk  -> every peer's slot
-//   phase 1  k_ex_hist      4096-bin x histogram over the GLOBAL range -> every peer's slot
+//   phase 1  k_ex_hist      1024-bin x histogram over the GLOBAL range -> every peer's slot
 //   phase 2  k_ex_cuts      equal-count cuts from the summed histograms (identical on every rank)
 //            k_ex_count     destinations of every record (owner slab + halo copies), per-tile counts
 //            k_ex_tilescan  per-destination exclusive scan over the tiles; send counts -> every peer
@@ -36,8 +36,8 @@
 
 namespace {
 
-constexpr int EX_BINS = 4096;
-constexpr int EX_PHASES = 6;          // 0..3 exchange, 4 results, 5 spare
+constexpr int EX_BINS = 1024;         // x histogram bins: slab populations are equal to within total / 1024
+constexpr int EX_PHASES = 6;          // 0..3 exchange, 4 normals delivered, 5 contours delivered
 constexpr int EX_TILE = 2048;         // records per block of the count / scatter kernels
 constexpr int EX_THREADS = 256;
 constexpr unsigned long long EX_TIMEOUT_NS = 10ull * 1000 * 1000 * 1000;
@@ -182,10 +182,18 @@ __global__ void __launch_bounds__(EX_THREADS) k_ex_minmax(ExView V, const float*
                                                           uint32_t step, ExScratch* sc) {
   float mn = CUDART_INF_F, mx = -CUDART_INF_F;
   unsigned cnt = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float x, y, z;
-    ex_load_xyz(raw, i, sf, vec_ok, x, y, z);
-    if (finite3(x, y, z)) { mn = fminf(mn, x); mx = fmaxf(mx, x); cnt++; }
+  constexpr int PPT = 4;   // independent loads in flight per thread
+  for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x * PPT; b0 < n; b0 += (int64_t)gridDim.x * blockDim.x * PPT) {
+    float x[PPT], y[PPT], z[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+      const int64_t i = b0 + (int64_t)j * blockDim.x + threadIdx.x;
+      x[j] = y[j] = z[j] = CUDART_NAN_F;
+      if (i < n) ex_load_xyz(raw, i, sf, vec_ok, x[j], y[j], z[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < PPT; j++)
+      if (finite3(x[j], y[j], z[j])) { mn = fminf(mn, x[j]); mx = fmaxf(mx, x[j]); cnt++; }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -193,10 +201,19 @@ __global__ void __launch_bounds__(EX_THREADS) k_ex_minmax(ExView V, const float*
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   }
-  if ((threadIdx.x & 31) == 0 && cnt) {
-    atomicMin(&sc->mn, ex_f2ord(mn));
-    atomicMax(&sc->mx, ex_f2ord(mx));
-    atomicAdd(&sc->n_fin, (unsigned long long)cnt);
+  // block-level combine, then ONE set of atomics per block (per-warp atomics on three addresses serialise in L2)
+  __shared__ float s_mn[EX_THREADS / 32], s_mx[EX_THREADS / 32];
+  __shared__ unsigned s_c[EX_THREADS / 32];
+  if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; s_c[threadIdx.x >> 5] = cnt; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned tot = 0;
+    for (int i = 0; i < EX_THREADS / 32; i++) { mn = fminf(mn, s_mn[i]); mx = fmaxf(mx, s_mx[i]); tot += s_c[i]; }
+    if (tot) {
+      atomicMin(&sc->mn, ex_f2ord(mn));
+      atomicMax(&sc->mx, ex_f2ord(mx));
+      atomicAdd(&sc->n_fin, (unsigned long long)tot);
+    }
   }
   if (!ex_last_block(&sc->ticket[0])) return;
   // last block: this rank's {min, max, finite count} into every arena, then the flag
@@ -230,7 +247,7 @@ __device__ __forceinline__ int ex_bin(float x, double gmin, double inv) {
 }
 
 // ---- phase 1: histogram of x over the global range -----------------------------------------------
-__global__ void __launch_bounds__(EX_THREADS) k_ex_hist(ExView V, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
+__global__ void __launch_bounds__(1024) k_ex_hist(ExView V, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
                                                         uint32_t step, ExScratch* sc) {
   __shared__ int32_t s_hist[EX_BINS];
   for (int i = threadIdx.x; i < EX_BINS; i += blockDim.x) s_hist[i] = 0;
@@ -239,10 +256,18 @@ __global__ void __launch_bounds__(EX_THREADS) k_ex_hist(ExView V, const float* _
   const double span = fmax(gmax - gmin, 1e-9);
   const double inv = (double)EX_BINS / span;
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float x, y, z;
-    ex_load_xyz(raw, i, sf, vec_ok, x, y, z);
-    if (finite3(x, y, z)) atomicAdd(&s_hist[ex_bin(x, gmin, inv)], 1);
+  constexpr int PPT = 4;
+  for (int64_t b0 = (int64_t)blockIdx.x * blockDim.x * PPT; b0 < n; b0 += (int64_t)gridDim.x * blockDim.x * PPT) {
+    float x[PPT], y[PPT], z[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; j++) {
+      const int64_t i = b0 + (int64_t)j * blockDim.x + threadIdx.x;
+      x[j] = y[j] = z[j] = CUDART_NAN_F;
+      if (i < n) ex_load_xyz(raw, i, sf, vec_ok, x[j], y[j], z[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < PPT; j++)
+      if (finite3(x[j], y[j], z[j])) atomicAdd(&s_hist[ex_bin(x[j], gmin, inv)], 1);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < EX_BINS; i += blockDim.x) {
@@ -325,38 +350,6 @@ __device__ __forceinline__ unsigned ex_dest_mask(const ExScratch* sc, int world,
   return m;
 }
 
-// Stable rank of this thread's record among the records of the tile that go to destination d, for
-// every d of the mask; records are taken in tile order (iteration-major, then thread order), which is
-// ascending index order.  s_warp: [warps][PPP_MAX_RANKS] scratch; run[d]: records of earlier
-// iterations (advanced here).  pos[d] is only meaningful for bits set in `mask`.
-__device__ __forceinline__ void ex_tile_ranks(unsigned mask, int world, int (*s_warp)[PPP_MAX_RANKS], int* run, int* pos) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int in_warp[PPP_MAX_RANKS];
-#pragma unroll
-  for (int d = 0; d < PPP_MAX_RANKS; d++) {
-    if (d < world) {
-      unsigned bal = __ballot_sync(0xffffffffu, (mask >> d) & 1u);
-      in_warp[d] = __popc(bal & ((1u << lane) - 1u));
-      if (lane == 0) s_warp[w][d] = __popc(bal);
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int d = 0; d < PPP_MAX_RANKS; d++) {
-    if (d < world) {
-      int base = 0, tot = 0;
-      for (int i = 0; i < EX_THREADS / 32; i++) {
-        int c = s_warp[i][d];
-        if (i < w) base += c;
-        tot += c;
-      }
-      pos[d] = run[d] + base + in_warp[d];
-      run[d] += tot;
-    }
-  }
-  __syncthreads();
-}
-
 // ---- phase 2b: per-tile destination counts --------------------------------------------------------
 __global__ void __launch_bounds__(EX_THREADS) k_ex_count(int world, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
                                                          double halo, ExScratch* sc, int32_t* __restrict__ tilecnt, int ntiles) {
@@ -417,41 +410,65 @@ __global__ void __launch_bounds__(1024) k_ex_tilescan(ExView V, int32_t* __restr
 
 // ---- phase 3: the records, straight into the destination's receive buffer ---------------------------
 // Record = {x, y, z, bits(global index)}; a halo copy carries ~global index (negative).
+// Positions are stable: records of a tile are taken in (iteration, thread) order = ascending index.  All
+// records of the tile are loaded up front (EX_ITERS independent loads per thread), the per-(iteration, warp,
+// destination) counts meet in shared memory once, a handful of threads turn them into offsets, and each
+// record's position is  base + offset(iteration, warp) + rank inside the warp (ballot).
+constexpr int EX_ITERS = EX_TILE / EX_THREADS;
+constexpr int EX_WARPS = EX_THREADS / 32;
+
 __global__ void __launch_bounds__(EX_THREADS) k_ex_scatter(ExView V, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
                                                            int64_t global_start, double halo, uint32_t step, ExScratch* sc,
                                                            const int32_t* __restrict__ tileoff, int ntiles) {
-  __shared__ int s_warp[EX_THREADS / 32][PPP_MAX_RANKS];
+  __shared__ int s_off[EX_ITERS * EX_WARPS][PPP_MAX_RANKS];
   __shared__ long long s_base[PPP_MAX_RANKS];
-  if ((int)threadIdx.x < V.world) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int world = V.world;
+  if ((int)threadIdx.x < world) {
     const int d = threadIdx.x;
     const int32_t* tab = reinterpret_cast<const int32_t*>(V.arena[V.rank] + V.off_cnt);
     long long b = 0;
     for (int s = 0; s < V.rank; s++) b += *(volatile const int32_t*)(tab + s * PPP_MAX_RANKS + d);
     s_base[d] = b + tileoff[(size_t)d * ntiles + blockIdx.x];
   }
-  __syncthreads();
-  int run[PPP_MAX_RANKS];
-#pragma unroll
-  for (int d = 0; d < PPP_MAX_RANKS; d++) run[d] = 0;
   const int64_t base = (int64_t)blockIdx.x * EX_TILE;
-  for (int it = 0; it < EX_TILE / EX_THREADS; it++) {
-    const int64_t i = base + (int64_t)it * EX_THREADS + threadIdx.x;
-    float x = 0.f, y = 0.f, z = 0.f;
-    unsigned m = 0;
-    int owner = 0;
-    if (i < n) {
-      ex_load_xyz(raw, i, sf, vec_ok, x, y, z);
-      m = ex_dest_mask(sc, V.world, x, y, z, halo, &owner);
-    }
-    int pos[PPP_MAX_RANKS];
-    ex_tile_ranks(m, V.world, s_warp, run, pos);
-    const int g = (int)(global_start + i);
+  float x[EX_ITERS], y[EX_ITERS], z[EX_ITERS];
+  unsigned mask[EX_ITERS];   // bits 0..15 destinations, bits 16..19 owner
 #pragma unroll
-    for (int d = 0; d < PPP_MAX_RANKS; d++) {
-      if (d < V.world && ((m >> d) & 1u)) {
-        const long long at = s_base[d] + pos[d];
+  for (int it = 0; it < EX_ITERS; it++) {
+    const int64_t i = base + (int64_t)it * EX_THREADS + threadIdx.x;
+    x[it] = y[it] = z[it] = 0.f;
+    if (i < n) ex_load_xyz(raw, i, sf, vec_ok, x[it], y[it], z[it]);
+  }
+#pragma unroll
+  for (int it = 0; it < EX_ITERS; it++) {
+    const int64_t i = base + (int64_t)it * EX_THREADS + threadIdx.x;
+    int owner = 0;
+    unsigned m = 0;
+    if (i < n) m = ex_dest_mask(sc, world, x[it], y[it], z[it], halo, &owner);
+    mask[it] = m | ((unsigned)owner << 16);
+    for (int d = 0; d < world; d++) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (m >> d) & 1u);
+      if (lane == 0) s_off[it * EX_WARPS + w][d] = __popc(bal);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < world) {   // exclusive scan over the (iteration, warp) pairs of one destination
+    int run = 0;
+    for (int j = 0; j < EX_ITERS * EX_WARPS; j++) { int c = s_off[j][threadIdx.x]; s_off[j][threadIdx.x] = run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < EX_ITERS; it++) {
+    const unsigned m = mask[it] & 0xFFFFu;
+    const int owner = (int)(mask[it] >> 16);
+    const int g = (int)(global_start + base + (int64_t)it * EX_THREADS + threadIdx.x);
+    for (int d = 0; d < world; d++) {
+      const unsigned bal = __ballot_sync(0xffffffffu, (m >> d) & 1u);
+      if ((m >> d) & 1u) {
+        const long long at = s_base[d] + s_off[it * EX_WARPS + w][d] + __popc(bal & ((1u << lane) - 1u));
         if (at < V.cap_recv)
-          reinterpret_cast<float4*>(V.arena[d] + V.off_recv)[at] = make_float4(x, y, z, __int_as_float(d == owner ? g : ~g));
+          reinterpret_cast<float4*>(V.arena[d] + V.off_recv)[at] = make_float4(x[it], y[it], z[it], __int_as_float(d == owner ? g : ~g));
         else
           atomicMax(&sc->err, 2);
       }
@@ -463,17 +480,23 @@ __global__ void __launch_bounds__(EX_THREADS) k_ex_scatter(ExView V, const float
 
 // After the records have landed: local row -> global index (-1 for halo copies), and the summary.
 __global__ void __launch_bounds__(256) k_ex_rowmap(ExView V, ExScratch* sc, int32_t* __restrict__ rowmap) {
-  const int32_t* tab = reinterpret_cast<const int32_t*>(V.arena[V.rank] + V.off_cnt);
-  long long n_local = 0, n_owned = 0;
-  for (int s = 0; s < V.world; s++) {
-    n_local += *(volatile const int32_t*)(tab + s * PPP_MAX_RANKS + V.rank);
-    n_owned += *(volatile const int32_t*)(tab + PPP_MAX_RANKS * PPP_MAX_RANKS + s * PPP_MAX_RANKS + V.rank);
+  __shared__ long long s_n[2];
+  if (threadIdx.x == 0) {
+    const int32_t* tab = reinterpret_cast<const int32_t*>(V.arena[V.rank] + V.off_cnt);
+    long long n_local = 0, n_owned = 0;
+    for (int s = 0; s < V.world; s++) {
+      n_local += *(volatile const int32_t*)(tab + s * PPP_MAX_RANKS + V.rank);
+      n_owned += *(volatile const int32_t*)(tab + PPP_MAX_RANKS * PPP_MAX_RANKS + s * PPP_MAX_RANKS + V.rank);
+    }
+    if (n_local > V.cap_recv) {   // senders dropped what does not fit; the receiver reports it
+      n_local = V.cap_recv;
+      if (blockIdx.x == 0) atomicMax(&sc->err, 2);
+    }
+    if (blockIdx.x == 0) { sc->n_local = n_local; sc->n_owned = n_owned; }
+    s_n[0] = n_local;
   }
-  if (n_local > V.cap_recv) {   // senders dropped what does not fit; the receiver reports it
-    n_local = V.cap_recv;
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&sc->err, 2);
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) { sc->n_local = n_local; sc->n_owned = n_owned; }
+  __syncthreads();
+  const long long n_local = s_n[0];
   const float4* recv = reinterpret_cast<const float4*>(V.arena[V.rank] + V.off_recv);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_local; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = __float_as_int(recv[i].w);
@@ -685,7 +708,7 @@ int ppp_exch_phase(ppp_exch* ex, int phase, const void* chunk_dev, int64_t n, si
   const float* raw = (const float*)chunk_dev;
   const int sf = (int)(stride_bytes / 4);
   const int vec_ok = (stride_bytes % 16 == 0) && (((uintptr_t)chunk_dev) % 16 == 0);
-  const int sweep_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, (int64_t)ctx->sm_count * 8));
+  const int sweep_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, (int64_t)ctx->sm_count * 4));
   const int ntiles = (int)std::max<int64_t>(1, (n + EX_TILE - 1) / EX_TILE);
   if (phase == 0) {
     ex->step++;
@@ -697,7 +720,9 @@ int ppp_exch_phase(ppp_exch* ex, int phase, const void* chunk_dev, int64_t n, si
   EX_REQUIRE(raw == ex->raw && n == ex->n, "phases of one step must be given the same chunk");
   if (phase == 1) {
     PPP_LAUNCH(ctx, "ex_wait", k_ex_wait, 1, 32, 0, ex->V, 0, ex->step, -1, ex->sc);
-    PPP_LAUNCH(ctx, "ex_hist", k_ex_hist, sweep_blocks, EX_THREADS, 0, ex->V, raw, n, sf, vec_ok, ex->step, ex->sc);
+    // two 1024-thread blocks per SM: every block ends with one atomic per non-empty bin
+    const int hist_blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 4095) / 4096, (int64_t)ctx->sm_count * 2));
+    PPP_LAUNCH(ctx, "ex_hist", k_ex_hist, hist_blocks, 1024, 0, ex->V, raw, n, sf, vec_ok, ex->step, ex->sc);
     PPP_CHECK_LAUNCH();
   } else if (phase == 2) {
     if (ex->tilecnt_cap < (int64_t)ntiles * ex->world) {
@@ -733,12 +758,18 @@ int ppp_exch_finish(ppp_exch* ex, int64_t* n_local, int64_t* n_owned, double* cu
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((ex->cap_recv + 255) / 256, (int64_t)ctx->sm_count * 8));
   PPP_LAUNCH(ctx, "ex_rowmap", k_ex_rowmap, blocks, 256, 0, ex->V, ex->sc, ex->rowmap);
   PPP_CHECK_LAUNCH();
-  // summary: the tail of the scratch block {n_local, n_owned, err} + {gmin, gmax, cutx}
-  struct { long long n_local, n_owned; int32_t err, pad; } tail;
-  struct { double cutx[PPP_MAX_RANKS + 1]; double gmin, gmax, inv; } mid;
-  static_assert(offsetof(ExScratch, gmin) == offsetof(ExScratch, cutx) + sizeof(double) * (PPP_MAX_RANKS + 1), "layout");
-  PPP_TRY(fetch_small(ctx, (const char*)ex->sc + offsetof(ExScratch, cutx), sizeof(mid), &mid));
-  PPP_TRY(fetch_small(ctx, (const char*)ex->sc + offsetof(ExScratch, n_local), sizeof(tail), &tail));
+  // summary: one fetch of the scratch block from the cut positions to the error word
+  struct Summary {
+    double cutx[PPP_MAX_RANKS + 1];
+    double gmin, gmax, inv;
+    int32_t sendcnt[PPP_MAX_RANKS], sendown[PPP_MAX_RANKS];
+    long long n_local, n_owned;
+    int32_t err, pad;
+  } sum;
+  static_assert(offsetof(ExScratch, pad) + sizeof(int32_t) - offsetof(ExScratch, cutx) == sizeof(Summary), "summary mirrors the scratch tail");
+  PPP_TRY(fetch_small(ctx, (const char*)ex->sc + offsetof(ExScratch, cutx), sizeof(sum), &sum));
+  struct { long long n_local, n_owned; int32_t err; } tail = {sum.n_local, sum.n_owned, sum.err};
+  struct { const double* cutx; double gmin, gmax; } mid = {sum.cutx, sum.gmin, sum.gmax};
   if (tail.err) {
     ppp_set_error(tail.err == 1 ? "ppp_exch_finish: timed out waiting for a peer rank"
                                 : "ppp_exch_finish: receive buffer too small (cap_recv %lld)", (long long)ex->cap_recv);
@@ -788,24 +819,26 @@ int ppp_exch_nodes_region(ppp_exch* ex, int r, const int64_t** offsets, const do
   return PPP_OK;
 }
 
-// Results phase.  signal: everything this rank has enqueued so far (normal records to their home ranks,
-// contour nodes to rank 0) is in place -> flag in every arena.  wait: later work of the stream (and a
-// host synchronise) sees every rank's results of this step: the home buffer holds the normals of the own
-// index range, rank 0's regions hold all contours.
-int ppp_exch_results_signal(ppp_exch* ex) {
-  if (!ex) { ppp_set_error("ppp_exch_results_signal: NULL argument"); return PPP_ERR_INVALID; }
+// Results phases.  what = PPP_EXCH_NORMALS (0): the normal records this rank's search kernels have stored
+// into their home ranks; PPP_EXCH_CONTOURS (1): the contour nodes written to rank 0's region.
+// signal: everything this rank has enqueued so far is in place -> flag in every arena.  wait: later work
+// of the stream (and a host synchronise) sees every rank's results of that kind for this step: the home
+// buffer holds the normals of the own index range / rank 0's regions hold all contours.  Signalling the
+// normals before the slicing is enqueued lets the copy of the home buffer to the host run under it.
+int ppp_exch_results_signal(ppp_exch* ex, int what) {
+  if (!ex || what < 0 || what > 1) { ppp_set_error("ppp_exch_results_signal: bad argument"); return PPP_ERR_INVALID; }
   EX_LOCK(ex);
   PPP_CUDA(cudaSetDevice(ex->ctx->device));
-  PPP_LAUNCH(ex->ctx, "ex_signal", k_ex_signal, 1, 32, 0, ex->V, 4, ex->step);
+  PPP_LAUNCH(ex->ctx, "ex_signal", k_ex_signal, 1, 32, 0, ex->V, 4 + what, ex->step);
   PPP_CHECK_LAUNCH();
   return PPP_OK;
 }
 
-int ppp_exch_results_wait(ppp_exch* ex) {
-  if (!ex) { ppp_set_error("ppp_exch_results_wait: NULL argument"); return PPP_ERR_INVALID; }
+int ppp_exch_results_wait(ppp_exch* ex, int what) {
+  if (!ex || what < 0 || what > 1) { ppp_set_error("ppp_exch_results_wait: bad argument"); return PPP_ERR_INVALID; }
   EX_LOCK(ex);
   PPP_CUDA(cudaSetDevice(ex->ctx->device));
-  PPP_LAUNCH(ex->ctx, "ex_wait", k_ex_wait, 1, 32, 0, ex->V, 4, ex->step, -1, ex->sc);
+  PPP_LAUNCH(ex->ctx, "ex_wait", k_ex_wait, 1, 32, 0, ex->V, 4 + what, ex->step, -1, ex->sc);
   PPP_CHECK_LAUNCH();
   return PPP_OK;
 }

@@ -621,6 +621,196 @@ __global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_k
 }
 
 // ---------------------------------------------------------------------------------------------
+// 16 < k <= 32 with the same composite keys and a MERGE instead of a full sort: slots 0..31 of the
+// per-thread store hold the 32 best so far in order, slots 32..47 take up to 16 newly accepted candidates.
+// A flush sorts the 16 new composite keys  (bits(d2) & ~63) | slot  (63 exchanges), folds them into the
+// kept 32 with one row of minima (the half-cleaner of a bitonic merge whose other inputs are +inf) and a
+// 32-input bitonic merge (80 exchanges), every exchange one unsigned min + one unsigned max, then moves
+// the full keys of the survivors to slots 0..31.  Dropping 6 mantissa bits leaves the order of two
+// candidates open only if their d2 agree in the upper 26 bits; such a pair among the 33 smallest sends the
+// query to the exact hand-over kernel.  (The 64-bit-key kernel this replaces kept 32 + 16 keys in 96
+// registers and spilled 304 bytes per thread.)
+// ---------------------------------------------------------------------------------------------
+template <int BD>
+__global__ void __launch_bounds__(BD, (BD == 64 ? 8 : 4)) k_knn32c(SearchParams P) {
+  extern __shared__ u64 s_keys[];
+  constexpr int K = 32, NEW = 16, SLOTS = K + NEW;
+  constexpr unsigned SMASK = 63u;   // slot bits of a composite key
+  const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
+  const GridView& g = P.g;
+  const bool valid = t < P.nq;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  int64_t row = 0;
+  if (valid) {
+    if (P.q) {
+      const float* qp = P.q + t * P.q_sf;
+      qx = __ldg(qp); qy = __ldg(qp + 1); qz = __ldg(qp + 2);
+      row = t;
+    } else {
+      float4 p = __ldg(g.sorted + P.first + t);
+      qx = p.x; qy = p.y; qz = p.z;
+      row = __float_as_int(p.w);
+    }
+  }
+  const bool fin = valid && finite3(qx, qy, qz);
+  const bool act = fin && g.n_sorted > 0;
+  u64* store = s_keys + threadIdx.x;
+  const unsigned store_sa = (unsigned)__cvta_generic_to_shared(store);
+  constexpr unsigned SLOT_B = BD * 8;
+  const int R = P.R0;
+  const int kk = P.kk;       // neighbours wanted (<= 32)
+  int cu = 0, cv = 0;
+  float tau = -1.0f;         // inclusive d2 threshold; inactive lanes accept nothing
+  if (act) {
+    cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
+    cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
+    tau = ring_bound2(g, R, cu, cv);
+  }
+  int nk = 0;                // kept (slots 0..nk-1, sorted)
+  bool ambiguous = false;
+  const int last = max(g.n_sorted - 1, 0);
+  unsigned wsa = store_sa + (unsigned)K * SLOT_B;     // cursor in the "new" region
+
+  auto flush = [&]() {
+    const int nn = (int)((wsa - store_sa) / SLOT_B) - K;
+    unsigned b[NEW];
+#pragma unroll
+    for (int i = 0; i < NEW; i++) {
+      unsigned hi = (unsigned)(store[(K + i) * BD] >> 32);   // stale slots are masked below
+      b[i] = i < nn ? ((hi & ~SMASK) | (unsigned)(K + i)) : 0xFFFFFFFFu;
+    }
+    SortNetU32<NEW>::sort(b);
+    unsigned a[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) {
+      unsigned hi = (unsigned)(store[i * BD] >> 32);
+      a[i] = i < nk ? ((hi & ~SMASK) | (unsigned)i) : 0xFFFFFFFFu;
+    }
+    // kept (ascending) ++ new (descending, +inf padded in front) is bitonic: its half-cleaner leaves the 32
+    // smallest in a[]; the smallest of what it discards is the 33rd of the union
+    unsigned next = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = K - NEW; i < K; i++) {
+      const unsigned o = b[K - 1 - i];
+      next = min(next, max(a[i], o));
+      a[i] = min(a[i], o);
+    }
+    SortNetU32<K>::bitonic_merge(a);
+    const int tot = min(nk + nn, K);
+#pragma unroll
+    for (int i = 0; i + 1 < K; i++) ambiguous |= (i + 1 < tot) && ((a[i] ^ a[i + 1]) <= SMASK);
+    ambiguous |= (nk + nn > K) && ((a[K - 1] ^ next) <= SMASK);
+    u64 keep[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) keep[i] = i < tot ? store[(a[i] & SMASK) * BD] : PPP_KEY_INF;
+#pragma unroll
+    for (int i = 0; i < K; i++) store[i * BD] = keep[i];
+    nk = tot;
+    wsa = store_sa + (unsigned)K * SLOT_B;
+    if (nk >= kk && kk > 0) tau = fminf(tau, key_d2(store[(kk - 1) * BD]));
+  };
+
+  constexpr int U = 4;
+  const unsigned trig_sa = store_sa + (unsigned)(K + NEW - U) * SLOT_B;   // room for one more iteration?
+#pragma unroll 1
+  for (int j = 0; j <= 2 * R + 1; j++) {
+    const int dv = (j & 1) ? -((j + 1) >> 1) : (j >> 1);  // rows nearest first
+    int s = 0, e = 0;
+    int v = cv + dv;
+    const bool drain = j == 2 * R + 1;
+    if (!drain && act && v >= 0 && v < g.nv) {
+      int a0 = max(cu - R, 0), b0 = min(cu + R, g.nu - 1);
+      if (a0 <= b0) {
+        const int32_t* rowp = g.cell_start + (int64_t)v * g.nu;
+        s = __ldg(rowp + a0);
+        e = __ldg(rowp + b0 + 1);
+      }
+    }
+    // the drain pseudo-row runs one empty iteration whose flush is unconditional
+    const int n_it = (__reduce_max_sync(0xffffffffu, e - s) + U - 1) / U + (j - 2 * R > 0 ? 1 : 0);
+    const unsigned trig = drain ? 0u : trig_sa;
+    int i0 = s;
+#pragma unroll 1
+    for (int it = 0; it < n_it; it++, i0 += U) {
+      float4 c4[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) c4[u] = __ldg(g.sorted + min(i0 + u, last));
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        float d2 = d2_flann(qx, qy, qz, c4[u].x, c4[u].y, c4[u].z);
+        if (i0 + u < e && d2 <= tau) {
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(wsa), "r"(i0 + u), "r"(__float_as_uint(d2)) : "memory");
+          wsa += SLOT_B;
+        }
+      }
+      if (__any_sync(0xffffffffu, wsa > trig)) flush();
+    }
+  }
+  if (!valid) return;
+  const bool complete = !act || kk == 0 || nk >= kk;
+  if (!complete || ambiguous) {
+    int slot = atomicAdd(P.redo_count, 1);
+    P.redo_list[slot] = (int32_t)t;
+    return;
+  }
+  const int k = P.cap;
+  const int m = act ? min(nk, k) : 0;
+  int32_t* io = P.idx_out ? P.idx_out + row * (int64_t)k : nullptr;
+  float* dout = (P.idx_out && P.d2_out) ? P.d2_out + row * (int64_t)k : nullptr;
+  const bool al32 = (k & 7) == 0 && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 31) == 0;
+  const bool want_n = P.normals && fin && m >= 3;
+  const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
+  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float kx = 0.f, ky = 0.f, kz = 0.f;
+#pragma unroll 1
+  for (int jb = 0; jb < k; jb += 8) {
+    float4 nb[8];
+    float dd[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const bool has = jb + u < m;
+      const u64 key = has ? store[(jb + u) * BD] : 0ull;
+      nb[u] = has ? __ldg(g.sorted + key_idx(key)) : make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      dd[u] = has ? key_d2(key) : CUDART_INF_F;
+    }
+    if (io) {
+      if (al32) {
+        st_global_256(io + jb, nb[0].w, nb[1].w, nb[2].w, nb[3].w, nb[4].w, nb[5].w, nb[6].w, nb[7].w);
+        if (dout) {
+          reinterpret_cast<float4*>(dout + jb)[0] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+          reinterpret_cast<float4*>(dout + jb)[1] = make_float4(dd[4], dd[5], dd[6], dd[7]);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (jb + u < k) {
+            io[jb + u] = __float_as_int(nb[u].w);
+            if (dout) dout[jb + u] = dd[u];
+          }
+        }
+      }
+    }
+    if (want_n) {
+      if (jb == 0 && shifted) { kx = nb[0].x; ky = nb[0].y; kz = nb[0].z; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (jb + u < m) {
+          float x = nb[u].x, y = nb[u].y, z = nb[u].z;
+          if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
+          accumulate_point(acc, x, y, z);
+        }
+      }
+    }
+  }
+  if (P.normals) {
+    float o[4];
+    if (want_n) normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
+    else o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
+    store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fixed-radius normals (NormalEstimation::setRadiusSearch, the reference's default r = 2.5) with
 // the same composite-key idea: every candidate with d2 < r2 is parked in one of 32 slots, ONE
 // 32-input network on 32-bit composite keys orders them at the end, and the covariance is
@@ -1208,6 +1398,15 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
     size_t smem = (size_t)C_SLOTS * 8 * block;
     auto kern = block == 128 ? k_knn16c<128> : (block == 96 ? k_knn16c<96> : k_knn16c<64>);
     PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned blocks = (unsigned)((P.nq + block - 1) / block);
+    PPP_LAUNCH(ctx, P.normals ? "knn_normals" : "knn", kern, blocks, block, smem, P);
+    PPP_CHECK_LAUNCH();
+    st = PPP_OK;
+  }
+  else if (P.cap <= 32 && !getenv("PPP_KNN32_OLD")) {
+    const int block = 64;
+    size_t smem = (size_t)48 * 8 * block;
+    auto kern = k_knn32c<64>;
     unsigned blocks = (unsigned)((P.nq + block - 1) / block);
     PPP_LAUNCH(ctx, P.normals ? "knn_normals" : "knn", kern, blocks, block, smem, P);
     PPP_CHECK_LAUNCH();

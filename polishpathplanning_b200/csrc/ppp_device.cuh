@@ -227,8 +227,8 @@ __device__ __forceinline__ void store_normal(float* base, const int32_t* __restr
 // around (cu, cv)  (R_prev = -1: the whole (2R+1)^2 block).  [ulo, uhi] optionally restricts the
 // visited cell columns (callers that only want points of an x-interval).
 template <typename F>
-__device__ __forceinline__ void visit_annulus(const GridView& g, int cu, int cv, int R_prev, int R, F&& f,
-                                              int ulo = -2147483647, int uhi = 2147483647) {
+__device__ __forceinline__ void visit_annulus_pos(const GridView& g, int cu, int cv, int R_prev, int R, F&& f,
+                                                  int ulo = -2147483647, int uhi = 2147483647) {
   int v0 = max(cv - R, 0), v1 = min(cv + R, g.nv - 1);
   ulo = max(ulo, 0);
   uhi = min(uhi, g.nu - 1);
@@ -239,21 +239,28 @@ __device__ __forceinline__ void visit_annulus(const GridView& g, int cu, int cv,
       int a = max(cu - R, ulo), b = min(cu + R, uhi);
       if (a <= b) {
         int s = __ldg(row + a), e = __ldg(row + b + 1);
-        for (int i = s; i < e; i++) f(__ldg(g.sorted + i));
+        for (int i = s; i < e; i++) f(__ldg(g.sorted + i), i);
       }
     } else {
       int a = max(cu - R, ulo), b = min(cu - R_prev - 1, uhi);
       if (a <= b) {
         int s = __ldg(row + a), e = __ldg(row + b + 1);
-        for (int i = s; i < e; i++) f(__ldg(g.sorted + i));
+        for (int i = s; i < e; i++) f(__ldg(g.sorted + i), i);
       }
       a = max(cu + R_prev + 1, ulo); b = min(cu + R, uhi);
       if (a <= b) {
         int s = __ldg(row + a), e = __ldg(row + b + 1);
-        for (int i = s; i < e; i++) f(__ldg(g.sorted + i));
+        for (int i = s; i < e; i++) f(__ldg(g.sorted + i), i);
       }
     }
   }
+}
+
+// The same, for callers that do not need the sorted position of the visited record.
+template <typename F>
+__device__ __forceinline__ void visit_annulus(const GridView& g, int cu, int cv, int R_prev, int R, F&& f,
+                                              int ulo = -2147483647, int uhi = 2147483647) {
+  visit_annulus_pos(g, cu, cv, R_prev, R, [&](float4 c, int) { f(c); }, ulo, uhi);
 }
 
 __device__ __forceinline__ bool block_covers_grid(const GridView& g, int cu, int cv, int R) {

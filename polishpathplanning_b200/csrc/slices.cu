@@ -56,7 +56,7 @@ __device__ __forceinline__ void for_memberships(const BandSet& b, float x, F&& f
 }
 
 __global__ void __launch_bounds__(256) k_band_count(BandSet b, const float4* __restrict__ xyz4, int64_t n, int64_t chunk,
-                                                    int use_smem, int32_t* __restrict__ counts) {
+                                                    int use_smem, int w_is_flag, int32_t* __restrict__ counts) {
   extern __shared__ int32_t s_cnt[];
   if (use_smem) {
     for (int t = threadIdx.x; t < b.S; t += blockDim.x) s_cnt[t] = 0;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) k_band_count(BandSet b, const float4* __r
   int64_t beg = (int64_t)blockIdx.x * chunk, end = min(beg + chunk, n);
   for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
     float4 p = __ldg(xyz4 + i);
-    if (p.w != p.w) continue;
+    if (w_is_flag && p.w != p.w) continue;   // packed cloud: w = NaN marks a non-finite point
     for_memberships(b, p.x, [&](int t) {
       if (use_smem) atomicAdd(s_cnt + t, 1);
       else atomicAdd(counts + __ldg(b.slice + t), 1);
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) k_band_count(BandSet b, const float4* __r
 }
 
 __global__ void __launch_bounds__(256) k_band_fill(BandSet b, const float4* __restrict__ xyz4, int64_t n, int64_t chunk,
-                                                   int use_smem, int32_t* __restrict__ cursor,
+                                                   int use_smem, int w_is_flag, int32_t* __restrict__ cursor,
                                                    const int64_t* __restrict__ offsets, int32_t* __restrict__ idx_out) {
   extern __shared__ int32_t s_mem[];
   int32_t* s_cnt = s_mem;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) k_band_fill(BandSet b, const float4* __re
     __syncthreads();
     for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
       float4 p = __ldg(xyz4 + i);
-      if (p.w != p.w) continue;
+      if (w_is_flag && p.w != p.w) continue;   // packed cloud: w = NaN marks a non-finite point
       for_memberships(b, p.x, [&](int t) { atomicAdd(s_cnt + t, 1); });
     }
     __syncthreads();
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256) k_band_fill(BandSet b, const float4* __re
   }
   for (int64_t i = beg + threadIdx.x; i < end; i += blockDim.x) {
     float4 p = __ldg(xyz4 + i);
-    if (p.w != p.w) continue;
+    if (w_is_flag && p.w != p.w) continue;   // packed cloud: w = NaN marks a non-finite point
     for_memberships(b, p.x, [&](int t) {
       int s = __ldg(b.slice + t);
       int pos = use_smem ? s_base[t] + atomicAdd(s_cnt + t, 1) : atomicAdd(cursor + s, 1);
@@ -205,15 +205,19 @@ __device__ __forceinline__ int cta_flag_rank(bool flag, int* s_warp, int& runnin
 // metric 1: Eigen norm sqrtf(dx^2 + (dy^2 + dz^2)), ties -> highest index (std::map<float,int>
 //           overwrite in src/Path_Generation.cpp:143-150: equal keys keep the last j).
 // Searches the grid ring by ring; gives up after RMAX rings and scans the side's member list.
+// Returns {original index, sorted position} of the winner ({-1, -1}: the side is empty).  `list`: the band's
+// members as original indices (by_pos == 0) or as sorted positions (by_pos != 0); the position of a winner
+// found by scanning an index list is unknown (-1) -- rec_of() then reads the packed cloud instead.
 template <bool MEMBER>
-__device__ int nn_side(const GridView& g, const float4* __restrict__ xyz4, float qx, float qy, float qz, float lo,
-                       float hi, float plane, bool want_left, int metric, const int32_t* list, int nlist,
-                       const uint32_t* __restrict__ member) {
-  if (nlist <= 0) return -1;
+__device__ int2 nn_side(const GridView& g, const float4* __restrict__ xyz4, float qx, float qy, float qz, float lo,
+                        float hi, float plane, bool want_left, int metric, const int32_t* list, int nlist,
+                        const uint32_t* __restrict__ member, int by_pos) {
+  if (nlist <= 0) return make_int2(-1, -1);
   const int RMAX = 6;
   u64 best = PPP_KEY_INF;
+  int best_pos = -1;
   // membership of the slice: the x-interval of the band, or (explicit index lists) a bitmap
-  auto consider = [&](float cx, float cy, float cz, int idx) {
+  auto consider = [&](float cx, float cy, float cz, int idx, int pos) {
     if (MEMBER) { if (!((__ldg(member + (idx >> 5)) >> (idx & 31)) & 1u)) return; }
     else if (cx < lo || cx > hi) return;
     if (want_left ? !(cx > plane) : !(cx < plane)) return;
@@ -225,7 +229,7 @@ __device__ int nn_side(const GridView& g, const float4* __restrict__ xyz4, float
       float nn = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz))));
       key = ((u64)__float_as_uint(nn) << 32) | (u64)(~(uint32_t)idx);
     }
-    if (key < best) best = key;
+    if (key < best) { best = key; best_pos = pos; }
   };
   int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
   int cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
@@ -239,7 +243,7 @@ __device__ int nn_side(const GridView& g, const float4* __restrict__ xyz4, float
   int R = 1, R_prev = -1;
   bool done = false;
   while (true) {
-    visit_annulus(g, cu, cv, R_prev, R, [&](float4 c) { consider(c.x, c.y, c.z, __float_as_int(c.w)); }, ulo, uhi);
+    visit_annulus_pos(g, cu, cv, R_prev, R, [&](float4 c, int pos) { consider(c.x, c.y, c.z, __float_as_int(c.w), pos); }, ulo, uhi);
     if (best != PPP_KEY_INF) {
       float b2 = ring_bound2(g, R, cu, cv);
       float v = __uint_as_float((uint32_t)(best >> 32));
@@ -252,15 +256,29 @@ __device__ int nn_side(const GridView& g, const float4* __restrict__ xyz4, float
   }
   if (!done) {
     best = PPP_KEY_INF;
+    best_pos = -1;
     for (int t = 0; t < nlist; t++) {
-      int idx = list[t];
-      float4 c = __ldg(xyz4 + idx);
-      consider(c.x, c.y, c.z, idx);
+      const int e = list[t];
+      if (by_pos) {
+        float4 c = __ldg(g.sorted + e);
+        consider(c.x, c.y, c.z, __float_as_int(c.w), e);
+      } else {
+        float4 c = __ldg(xyz4 + e);
+        consider(c.x, c.y, c.z, e, -1);
+      }
     }
   }
-  if (best == PPP_KEY_INF) return -1;
+  if (best == PPP_KEY_INF) return make_int2(-1, -1);
   uint32_t low = (uint32_t)(best & 0xFFFFFFFFull);
-  return metric == 0 ? (int)low : (int)(~low);
+  return make_int2(metric == 0 ? (int)low : (int)(~low), best_pos);
+}
+
+// Record {x, y, z, bits(original index)} of a point given as {original index, sorted position or -1}.
+__device__ __forceinline__ float4 rec_of(const GridView& g, const float4* __restrict__ xyz4, int2 h) {
+  if (h.y >= 0) return __ldg(g.sorted + h.y);
+  float4 c = __ldg(xyz4 + h.x);
+  c.w = __int_as_float(h.x);
+  return c;
 }
 
 // kdtree.nearestKSearch(p, 1) for a CLOUD POINT p: the lowest index among the points at float
@@ -268,15 +286,15 @@ __device__ int nn_side(const GridView& g, const float4* __restrict__ xyz4, float
 // cell: d2 == 0 in float needs every coordinate difference below ~3.7e-23, which distinct floats
 // only manage below 1e-15 in magnitude, far from any cell boundary other than the grid origin
 // (and nothing lies below the origin: it is the cloud minimum).  So the own cell is enough.
-__device__ int nn_full(const GridView& g, float qx, float qy, float qz, int self_idx) {
+__device__ int2 nn_full(const GridView& g, float qx, float qy, float qz, int2 self) {
   int cu = clampi(cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h), 0, g.nu - 1);
   int cv = clampi(cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h), 0, g.nv - 1);
   const int32_t* cs = g.cell_start + (int64_t)cv * g.nu + cu;
-  int best = self_idx;
+  int2 best = self;
   for (int i = __ldg(cs), e = __ldg(cs + 1); i < e; i++) {
     float4 c = __ldg(g.sorted + i);
     int idx = __float_as_int(c.w);
-    if (idx < best && d2_flann(qx, qy, qz, c.x, c.y, c.z) == 0.0f) best = idx;
+    if (idx < best.x && d2_flann(qx, qy, qz, c.x, c.y, c.z) == 0.0f) best = make_int2(idx, i);
   }
   return best;
 }
@@ -354,13 +372,13 @@ __global__ void __launch_bounds__(1024) k_contour(ContourParams P, int smem_cap)
     // nearest right of every left, nearest left of every right (flag-independent) ...
     for (int i = threadIdx.x; i < nL; i += (int)blockDim.x) {
       float4 pl = __ldg(P.xyz4 + El[i]);
-      int r = nn_side<MEMBER>(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 1, Er, nR, P.member);
+      int r = nn_side<MEMBER>(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 1, Er, nR, P.member, 0).x;
       posR[i] = lower_pos(Er, nR, r);
       fl[i] = 0;
     }
     for (int j = threadIdx.x; j < nR; j += (int)blockDim.x) {
       float4 pr = __ldg(P.xyz4 + Er[j]);
-      int l = nn_side<MEMBER>(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 1, El, nL, P.member);
+      int l = nn_side<MEMBER>(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 1, El, nL, P.member, 0).x;
       posL[j] = lower_pos(El, nL, l);
       fr[j] = 0;
     }
@@ -441,7 +459,20 @@ struct PairParams {
   float* ys;
   float* zs;
   const uint32_t* member;   // optional membership bitmap (explicit index lists)
+  int by_pos;               // band_idx holds SORTED POSITIONS (bands built from the cell-major order: members
+                            // that are neighbours in the list are neighbours in space) instead of original indices
 };
+
+// Member m of the band lists as {original index, sorted position or -1} and its record.
+__device__ __forceinline__ int2 member_handle(const PairParams& P, int64_t m, float4* rec) {
+  const int e = __ldg(P.band_idx + m);
+  if (P.by_pos) {
+    *rec = __ldg(P.g.sorted + e);
+    return make_int2(__float_as_int(rec->w), e);
+  }
+  *rec = __ldg(P.xyz4 + e);
+  return make_int2(e, -1);
+}
 
 // Each warp takes PAIR_CHUNK consecutive members, keeps the left ones (about half) in a small
 // shared-memory list and then works on that list with all lanes busy: a thread-per-member
@@ -468,8 +499,9 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
       int l = 0, r = P.S;
       while (l < r) { int mid = (l + r) >> 1; if (__ldg(P.band_off + mid + 1) <= m) l = mid + 1; else r = mid; }
       s = l;
-      const float x = __ldg(&P.xyz4[__ldg(P.band_idx + m)].x);
-      isL = __fsub_rn(x, __ldg(P.planes + s)) > 0.0f;
+      float4 rec;
+      member_handle(P, m, &rec);
+      isL = __fsub_rn(rec.x, __ldg(P.planes + s)) > 0.0f;
       if (!isL) { P.keys[m] = PPP_KEY_INF; P.ys[m] = 0.f; P.zs[m] = 0.f; }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, isL);
@@ -488,18 +520,19 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
     const int64_t bo = __ldg(P.band_off + s);
     const int32_t* band = P.band_idx + bo;
     const int B = (int)(__ldg(P.band_off + s + 1) - bo);
-    const float4 pl = __ldg(P.xyz4 + __ldg(P.band_idx + m));
+    float4 pl;
+    member_handle(P, m, &pl);
     u64 key = PPP_KEY_INF;
     float y = 0.f, z = 0.f;
-    int ri = nn_side<MEMBER>(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, band, B, P.member);
-    if (ri >= 0) {
-      float4 pr = __ldg(P.xyz4 + ri);
-      int rc = nn_full(P.g, pr.x, pr.y, pr.z, ri);
-      int li = nn_side<MEMBER>(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, band, B, P.member);
-      float4 pl2 = __ldg(P.xyz4 + li);
-      int lc = nn_full(P.g, pl2.x, pl2.y, pl2.z, li);
-      float4 a = __ldg(P.xyz4 + rc);  // index_right
-      float4 b = __ldg(P.xyz4 + lc);  // index_left
+    const int2 ri = nn_side<MEMBER>(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, band, B, P.member, P.by_pos);
+    if (ri.x >= 0) {
+      const float4 pr = rec_of(P.g, P.xyz4, ri);
+      const int2 rc = nn_full(P.g, pr.x, pr.y, pr.z, ri);
+      const int2 li = nn_side<MEMBER>(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, band, B, P.member, P.by_pos);
+      const float4 pl2 = rec_of(P.g, P.xyz4, li);
+      const int2 lc = nn_full(P.g, pl2.x, pl2.y, pl2.z, li);
+      const float4 a = rec_of(P.g, P.xyz4, rc);  // index_right
+      const float4 b = rec_of(P.g, P.xyz4, lc);  // index_left
       float t = __fdiv_rn(__fsub_rn(plane, a.x), __fsub_rn(b.x, a.x));
       y = __fadd_rn(a.y, __fmul_rn(t, __fsub_rn(b.y, a.y)));
       z = __fadd_rn(a.z, __fmul_rn(t, __fsub_rn(b.z, a.z)));
@@ -519,6 +552,7 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
 constexpr int SO_THREADS = 1024;
 
 __global__ void __launch_bounds__(SO_THREADS) k_slice_order(const int64_t* __restrict__ band_off, const int32_t* __restrict__ band_idx,
+                                                           const float4* __restrict__ sorted_if_pos,
                                                            const u64* __restrict__ keys_g, const float* __restrict__ ys,
                                                            const float* __restrict__ zs, u64* __restrict__ scratch,
                                                            int smem_cap, double* __restrict__ ty, double* __restrict__ tz,
@@ -552,11 +586,16 @@ __global__ void __launch_bounds__(SO_THREADS) k_slice_order(const int64_t* __res
     int r = cta_flag_rank(first, s_warp, nodes);
     if (first) {
       int slot = (int)(uint32_t)(key & 0xFFFFFFFFull);
-      int idx = __ldg(band_idx + o + slot);
-      int lo_idx = idx, hi_idx = idx, lo_slot = slot, hi_slot = slot;
+      // original index of a member: the list entry itself, or (position lists) the w of its sorted record
+      auto id_of = [&](int sl) {
+        const int e = __ldg(band_idx + o + sl);
+        return sorted_if_pos ? __float_as_int(__ldg(&sorted_if_pos[e].w)) : e;
+      };
+      int lo_idx = -1, hi_idx = -1, lo_slot = slot, hi_slot = slot;
       for (int j = i + 1; j < nv && (k[j] >> 32) == (key >> 32); j++) {
+        if (lo_idx < 0) lo_idx = hi_idx = id_of(slot);   // ids are only needed when a y value repeats
         int sl = (int)(uint32_t)(k[j] & 0xFFFFFFFFull);
-        int id = __ldg(band_idx + o + sl);
+        int id = id_of(sl);
         if (id < lo_idx) { lo_idx = id; lo_slot = sl; }
         if (id > hi_idx) { hi_idx = id; hi_slot = sl; }
       }
@@ -647,10 +686,17 @@ struct BandPrep {
   unsigned blocks = 1;
   int64_t chunk = 0;
   int max_depth = 0;          // most bands any single x can belong to
+  const float4* src = nullptr;  // records the bands are drawn from: the packed cloud (entries = original indices) ...
+  int64_t n_src = 0;            // ... or the cell-major sorted array of a grid (entries = sorted positions)
+  int w_is_flag = 1;
 };
 
-static int bands_prepare(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center, BandPrep* bp) {
+static int bands_prepare(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center, BandPrep* bp,
+                         const GridStore* by_pos_of = nullptr) {
   ppp_ctx* ctx = c->ctx;
+  bp->src = by_pos_of ? by_pos_of->v.sorted : c->xyz4;
+  bp->n_src = by_pos_of ? (int64_t)by_pos_of->v.n_sorted : c->n;
+  bp->w_is_flag = by_pos_of ? 0 : 1;
   std::vector<float> lo(S), hi(S);
   std::vector<int32_t> perm(S);
   for (int s = 0; s < S; s++) {
@@ -702,11 +748,11 @@ static int bands_prepare(ppp_cloud* c, const float* plane_x_host, int S, float h
   bp->b = BandSet{bp->fdev + 3 * (size_t)S, bp->fdev + 4 * (size_t)S, bp->pdev, Sv};
   bp->Sv = Sv;
   bp->use_smem = Sv <= BAND_SMEM_BINS / 2;  // fill needs two arrays
-  bp->blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((c->n + 1023) / 1024, (int64_t)ctx->sm_count * 8));
-  bp->chunk = (c->n + bp->blocks - 1) / bp->blocks;
-  if (c->n > 0 && Sv > 0) {
-    PPP_LAUNCH(ctx, "band_count", k_band_count, bp->blocks, 256, bp->use_smem ? (size_t)Sv * 4 : 0, bp->b, (const float4*)c->xyz4,
-               c->n, bp->chunk, bp->use_smem, bp->counts);
+  bp->blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((bp->n_src + 1023) / 1024, (int64_t)ctx->sm_count * 8));
+  bp->chunk = (bp->n_src + bp->blocks - 1) / bp->blocks;
+  if (bp->n_src > 0 && Sv > 0) {
+    PPP_LAUNCH(ctx, "band_count", k_band_count, bp->blocks, 256, bp->use_smem ? (size_t)Sv * 4 : 0, bp->b, bp->src,
+               bp->n_src, bp->chunk, bp->use_smem, bp->w_is_flag, bp->counts);
     PPP_CHECK_LAUNCH();
   }
   PPP_TRY(scan_exclusive_i32_to_i64(ctx, bp->counts, bp->offsets, S));
@@ -716,10 +762,10 @@ static int bands_prepare(ppp_cloud* c, const float* plane_x_host, int S, float h
 
 static int bands_fill(ppp_cloud* c, const BandPrep& bp, int32_t* idx) {
   ppp_ctx* ctx = c->ctx;
-  if (c->n <= 0 || bp.Sv <= 0) return PPP_OK;
+  if (bp.n_src <= 0 || bp.Sv <= 0) return PPP_OK;
   if (bp.use_smem) PPP_CUDA(cudaFuncSetAttribute(k_band_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, BAND_SMEM_BINS * 4));
-  PPP_LAUNCH(ctx, "band_fill", k_band_fill, bp.blocks, 256, bp.use_smem ? (size_t)bp.Sv * 8 : 0, bp.b, (const float4*)c->xyz4, c->n,
-             bp.chunk, bp.use_smem, bp.counts, (const int64_t*)bp.offsets, idx);
+  PPP_LAUNCH(ctx, "band_fill", k_band_fill, bp.blocks, 256, bp.use_smem ? (size_t)bp.Sv * 8 : 0, bp.b, bp.src, bp.n_src,
+             bp.chunk, bp.use_smem, bp.w_is_flag, bp.counts, (const int64_t*)bp.offsets, idx);
   PPP_CHECK_LAUNCH();
   return PPP_OK;
 }
@@ -813,7 +859,7 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     P.g = gs.v; P.xyz4 = c->xyz4;
     P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
     P.band_off = band_off_dev; P.band_idx = band_idx_dev; P.S = S; P.M = band_total;
-    P.member = member_bits;
+    P.member = member_bits; P.by_pos = 0;
     PPP_TRY(dev_alloc(ctx, &P.keys, M)); PPP_TRY(dev_alloc(ctx, &P.ys, M)); PPP_TRY(dev_alloc(ctx, &P.zs, M));
     if (band_total > 0) {
       const int64_t per_block = (int64_t)PAIR_WARPS * PAIR_CHUNK;
@@ -830,7 +876,7 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
       if ((size_t)smem_cap * 8 > 48 * 1024)
         PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
       PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, SO_THREADS, (size_t)smem_cap * 8, band_off_dev, band_idx_dev,
-                 (const u64*)P.keys, (const float*)P.ys, (const float*)P.zs, scratch, smem_cap, ty, tz, n_nodes);
+                 (const float4*)nullptr, (const u64*)P.keys, (const float*)P.ys, (const float*)P.zs, scratch, smem_cap, ty, tz, n_nodes);
       PPP_CHECK_LAUNCH();
     }
     st = finish_nodes(c, S, band_off_dev, planes_dev, n_nodes, ty, tz, total_nodes_out);
@@ -909,8 +955,11 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
                               int truncate_center, int64_t* total_nodes_out, int64_t* total_members_out) {
   ppp_ctx* ctx = c->ctx;
   if (S <= 0 || c->n <= 0) return PPP_ERR_UNSUPPORTED;
+  // Bands are drawn from the grid's cell-major array and hold SORTED POSITIONS: consecutive members of a band
+  // are neighbours in space, so the pairing searches of a warp walk the same cells (L1 / L2 reuse instead of a
+  // DRAM gather per member), and every record they need is one contiguous-ish load from the sorted array.
   BandPrep bp;
-  PPP_TRY(bands_prepare(c, plane_x_host, S, half_width, truncate_center, &bp));
+  PPP_TRY(bands_prepare(c, plane_x_host, S, half_width, truncate_center, &bp, &gs));
   const int64_t Mb = (int64_t)std::max(bp.max_depth, 1) * c->n;   // >= band members
   int st = PPP_OK;
   int32_t* idx = nullptr; double *ty = nullptr, *tz = nullptr; int32_t* n_nodes = nullptr;
@@ -939,7 +988,7 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
     P.g = gs.v; P.xyz4 = c->xyz4;
     P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
     P.band_off = bp.offsets; P.band_idx = idx; P.S = S; P.M = Mb;
-    P.member = nullptr; P.keys = keys; P.ys = ys; P.zs = zs;
+    P.member = nullptr; P.keys = keys; P.ys = ys; P.zs = zs; P.by_pos = 1;
     const int64_t per_block = (int64_t)PAIR_WARPS * PAIR_CHUNK;
     PPP_LAUNCH(ctx, "pair_nodes", k_pair_nodes<false>, (unsigned)((Mb + per_block - 1) / per_block), PAIR_WARPS * 32, 0, P);
     PPP_CHECK_LAUNCH();
@@ -950,7 +999,7 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
     if ((size_t)smem_cap * 8 > 48 * 1024)
       PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
     PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, SO_THREADS, (size_t)smem_cap * 8, (const int64_t*)bp.offsets,
-               (const int32_t*)idx, (const u64*)keys, (const float*)ys, (const float*)zs, scratch, smem_cap, ty, tz, n_nodes);
+               (const int32_t*)idx, gs.v.sorted, (const u64*)keys, (const float*)ys, (const float*)zs, scratch, smem_cap, ty, tz, n_nodes);
     PPP_CHECK_LAUNCH();
     if (c->c_S_cap < S + 1) {
       dev_free(ctx, c->c_node_off);

@@ -232,11 +232,15 @@ class Exchange:
         self._api.check(self.lib.ppp_exch_attach(self._h, int(bool(to_rank0)), C.byref(h)))
         return self._api.Cloud(self.ctx, handle=h)
 
-    def results_signal(self):
-        self._api.check(self.lib.ppp_exch_results_signal(self._h))
+    NORMALS, CONTOURS = 0, 1
 
-    def results_wait(self):
-        self._api.check(self.lib.ppp_exch_results_wait(self._h))
+    def results_signal(self, what):
+        """what: Exchange.NORMALS / Exchange.CONTOURS -- this rank's results of that kind are delivered."""
+        self._api.check(self.lib.ppp_exch_results_signal(self._h, int(what)))
+
+    def results_wait(self, what):
+        """Later work of the stream sees every rank's results of that kind."""
+        self._api.check(self.lib.ppp_exch_results_wait(self._h, int(what)))
 
     def check(self):
         self._api.check(self.lib.ppp_exch_check(self._h))

@@ -51,6 +51,47 @@ def panel(n, seed=0, density=1.0, noise_sigma=0.0):
     return reference_ctor_scale(to_pointxyzrgb(panel_metres(n, seed, density, noise_sigma)))
 
 
+def _records_mm(xyz_mm):
+    """(n, 3) millimetre coordinates -> the cloud as the reference's constructor leaves it (stored in metres
+    as float32, then x, y, z *= 1000 in float32)."""
+    xyz_m = (np.asarray(xyz_mm, np.float64).astype(np.float32) / np.float32(1000.0)).astype(np.float32)
+    return reference_ctor_scale(to_pointxyzrgb(xyz_m))
+
+
+def cylinder(n, seed=0, density=1.0, aspect=4.0):
+    """A CLOSED workpiece: the lateral surface of a cylinder whose axis is y, ~density points/mm^2, length =
+    aspect x radius.  Not a height field: above every (x, y) there are two sheets, and near x = +-R the
+    surface is vertical -- a grid over two axes piles whole strips of it into single columns."""
+    rng = np.random.default_rng(seed)
+    R = np.sqrt(n / density / (2 * np.pi * aspect))
+    L = aspect * R
+    th = rng.random(n) * 2 * np.pi
+    y = rng.random(n) * L
+    x = R * np.cos(th) + R          # x in [0, 2R]: planes x = const cut it into two arcs
+    z = R * np.sin(th)
+    return _records_mm(np.stack([x, y, z], axis=1))
+
+
+def box_with_walls(n, seed=0, density=1.0, wall=0.35):
+    """An open box: a flat floor of side L with four VERTICAL walls of height wall x L (a steep-sided
+    workpiece).  Points are spread by area at ~density points/mm^2."""
+    rng = np.random.default_rng(seed)
+    L = np.sqrt(n / density / (1 + 4 * wall))
+    H = wall * L
+    n_floor = int(round(n / (1 + 4 * wall)))
+    n_wall = n - n_floor
+    fx, fy = rng.random(n_floor) * L, rng.random(n_floor) * L
+    floor = np.stack([fx, fy, 0.3 * np.sin(fx / 37.0) * np.cos(fy / 29.0)], axis=1)
+    side = rng.integers(0, 4, n_wall)
+    t, h = rng.random(n_wall) * L, rng.random(n_wall) * H
+    zero, full = np.zeros(n_wall), np.full(n_wall, L)
+    wx = np.select([side == 0, side == 1, side == 2, side == 3], [zero, full, t, t])
+    wy = np.select([side == 0, side == 1, side == 2, side == 3], [t, t, zero, full])
+    walls = np.stack([wx, wy, h], axis=1)
+    pts = np.concatenate([floor, walls], axis=0)
+    return _records_mm(pts[rng.permutation(n)])
+
+
 def write_pcd(path, cloud, binary=True):
     """PCD v0.7, FIELDS x y z rgb (rgb packed as float, as PCL writes PointXYZRGB)."""
     n = cloud.shape[0]

@@ -1,12 +1,12 @@
 """numpy restatement of the device exchange (polishpathplanning_b200/csrc/exchange.cu) -- TEST CHECKER.
 
-Same arithmetic, step by step: float32 min/max of the finite x, a 4096-bin histogram over the global
+Same arithmetic, step by step: float32 min/max of the finite x, a 1024-bin histogram over the global
 range in double, equal-count cuts in integer arithmetic, owner by bin, halo copies by comparing x with
 the cut positions, destination order = ascending global index.  The GPU tests compare the slabs the
 kernels deliver with this; the gloo tests use it as the exchange stand-in on CPU."""
 import numpy as np
 
-BINS = 4096
+BINS = 1024
 
 
 def exchange_model(chunks, starts, halo):

@@ -110,12 +110,14 @@ def test_sharded_pipeline_equals_single_cloud(world, stride):
             clouds.append(c)
             idx.append(torch.empty((infos[r]["n_local"], k), dtype=torch.int32, device="cuda:0"))
             c.dev_normals_knn(k, exs[r].home_normals_ptr, stride, idx_ptr=idx[r].data_ptr())
+            exs[r].results_signal(parallel.Exchange.NORMALS)
             pos.append(parallel.owned_planes(planes, infos[r]["cuts"], r))
             res = c.dev_slice_contours(planes[pos[r]], "B")
             assert res["y"] == exs[0].nodes_region(r)["y"]          # delivered in place, not to the cloud's own buffers
-            exs[r].results_signal()
+            exs[r].results_signal(parallel.Exchange.CONTOURS)
         for r in range(world):
-            exs[r].results_wait()
+            exs[r].results_wait(parallel.Exchange.NORMALS)
+            exs[r].results_wait(parallel.Exchange.CONTOURS)
             ctxs[r].sync()
         got_n = np.concatenate([exs[r].read_home_normals() for r in range(world)], axis=0)
         assert np.array_equal(got_n.view(np.uint32), ref_n.view(np.uint32))

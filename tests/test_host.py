@@ -134,7 +134,7 @@ def test_exchange_model_is_a_slab_partition():
         assert np.array_equal(np.sort(owned_all), np.arange(cloud.shape[0]))
         fin = np.isfinite(cloud[:, :3]).all(axis=1)
         counts = [int(((w >= 0)).sum()) for _, w in slabs]
-        assert max(counts) - min(counts) <= cloud.shape[0] // 100 + 2          # 4096 bins: within 1 %
+        assert max(counts) - min(counts) <= cloud.shape[0] // 100 + 2          # 1024 bins: within 1 %
         for r, (xyz, w) in enumerate(slabs):
             g = np.where(w >= 0, w, ~w)
             assert np.all(np.diff(g) > 0)

@@ -43,11 +43,13 @@ def main():
         idx = torch.empty((nl, k), dtype=torch.int32, device=dev)
         d2 = torch.empty((nl, k), dtype=torch.float32, device=dev)
         c.dev_normals_knn(k, ex.home_normals_ptr, 16, idx_ptr=idx.data_ptr(), d2_ptr=d2.data_ptr())
+        ex.results_signal(ex.NORMALS)
         pos = parallel.owned_planes(planes, info["cuts"], rank)
         res = c.dev_slice_contours(planes[pos], "B")
         assert res["total_nodes"] <= ex.node_cap
-        ex.results_signal()
-        ex.results_wait()
+        ex.results_signal(ex.CONTOURS)
+        ex.results_wait(ex.NORMALS)
+        ex.results_wait(ex.CONTOURS)
         ctx.sync()
         ex.check()
         # halo wide enough for every owned point?
