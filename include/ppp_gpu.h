@@ -160,6 +160,11 @@ int ppp_sor_mean_distances(ppp_cloud* cloud, int mean_k, unsigned flags, float* 
 int ppp_coverage_mark(ppp_cloud* cloud, const float* q, size_t nq, size_t q_stride_bytes, double radius,
                       unsigned char* flags);
 
+/* The same for nodes that each bring their own radius, as Area2Cloud calls it per path node
+ * (src/Path_Generation.cpp:466-470); only |radius| matters (PCL squares it), a NaN radius marks nothing. */
+int ppp_coverage_mark_radii(ppp_cloud* cloud, const float* q, size_t nq, size_t q_stride_bytes, const double* radii,
+                            unsigned char* flags);
+
 /* estimate_normal() followed by the plane sweep, as one call: what SectPath-derived GenPath does
  * (src/Path_Alg/path_dynamic_alg.cpp:343-366: estimate_normal(); kdtree.setInputCloud; sweep).
  * Exactly the results of ppp_normals_knn (k >= 1, radius = 0) or ppp_normals_radius (k = 0,

@@ -677,6 +677,22 @@ int ppo_planes(int variant, float min_x, float max_x, double tool_radius, float*
   } else if (variant == 2) {
     float m = min_x; m += 40;
     while (m < max_x) { v.push_back(m); m += 40; }
+  } else if (variant == 4) {
+    // gen-3 two-thread sweep (src/Path_Alg/path_dynamic_alg.cpp:308-366): centre path at the float centre, the two
+    // workers count in INT from the int-truncated bounding box (include/Path_Generate_Algorithm.h:110-117)
+    const int mn = (int)min_x, mx = (int)max_x;
+    std::vector<float> front, back;
+    int loc = (mx + mn) / 2 - step;
+    while (mx > loc && loc > mn) { front.insert(front.begin(), (float)loc); loc -= step; if (step <= 0) break; }
+    loc = (mx + mn) / 2 + step;
+    while (mx > loc && loc > mn) { back.push_back((float)loc); loc += step; if (step <= 0) break; }
+    v = front; v.push_back((min_x + max_x) / 2); v.insert(v.end(), back.begin(), back.end());
+  } else if (variant == 5) {
+    // gen-3 single-direction sweep (src/Path_Alg/dynamic_alg_sdir.cpp:349-374): int loc = min_pt.x + toolRadius
+    int loc = (int)(min_x + tool_radius);
+    v.push_back((float)loc);
+    loc += step;
+    while (loc < max_x) { v.push_back((float)loc); loc += step; if (step <= 0) break; }
   } else {
     std::vector<float> front, back;
     float loc = (min_x + max_x) / 2 - step;

@@ -260,7 +260,7 @@ def normal_from_list(pts, nb, q, viewpoint=(0, 0, 0), cov_variant=0):
     return out
 
 
-PLANE_VARIANTS = {"gen2_contact": 0, "gen2_slicing": 1, "gen1_slicing": 2, "sectpath": 3}
+PLANE_VARIANTS = {"gen2_contact": 0, "gen2_slicing": 1, "gen1_slicing": 2, "sectpath": 3, "gen3_two_thread": 4, "gen3_sdir": 5}
 
 
 def planes(variant, min_x, max_x, tool_radius):

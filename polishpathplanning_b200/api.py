@@ -333,6 +333,17 @@ class Cloud:
                                          _ptr(flags)))
         return flags
 
+    def coverage_mark_radii(self, queries, radii, flags=None):
+        """compute_coverage for nodes with one radius each (Area2Cloud); flags updated in place and returned."""
+        queries = np.ascontiguousarray(queries, np.float32)
+        radii = np.ascontiguousarray(radii, np.float64)
+        assert radii.shape[0] == queries.shape[0]
+        if flags is None:
+            flags = np.zeros(self.n, np.uint8)
+        check(self.lib.ppp_coverage_mark_radii(self._h, _ptr(queries), queries.shape[0], queries.shape[1] * 4, _ptr(radii),
+                                               _ptr(flags)))
+        return flags
+
     # ---- device-resident pipeline ---------------------------------------------------------------
     def dev_index(self, k_hint=16, radius_hint=0.0):
         check(self.lib.ppp_dev_index(self._h, int(k_hint), float(radius_hint)))

@@ -713,6 +713,44 @@ int ppp_coverage_mark(ppp_cloud* c, const float* q, size_t nq, size_t q_stride_b
   return PPP_OK;
 }
 
+// compute_coverage for a batch of nodes that each bring their OWN radius: what Area2Cloud does for every path
+// node (src/Path_Generation.cpp:466-470: compute_coverage(point, comput_lan), the half-width of the node's
+// contact ellipse; the value is negative there and PCL squares it, so only |radius| matters).
+// A NaN radius marks nothing.
+int ppp_coverage_mark_radii(ppp_cloud* c, const float* q, size_t nq, size_t q_stride_bytes, const double* radii,
+                            unsigned char* flags) {
+  REQUIRE(c && (flags || c->n == 0), "NULL argument");
+  REQUIRE(nq == 0 || (q && radii), "queries / radii are NULL");
+  REQUIRE(q_stride_bytes >= 12 && q_stride_bytes % 4 == 0, "query stride must be >= 12 and a multiple of 4");
+  ppp_ctx* ctx = c->ctx;
+  LOCK(ctx);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  if (c->n == 0 || nq == 0) return PPP_OK;
+  std::vector<float> r2(nq);
+  double rmax = 0;
+  for (size_t i = 0; i < nq; i++) {
+    r2[i] = (float)(radii[i] * radii[i]);   // [upstream] pcl::KdTreeFLANN::radiusSearch squares the radius in double
+    if (std::isfinite(radii[i])) rmax = std::max(rmax, std::fabs(radii[i]));
+  }
+  if (!(rmax > 0)) return PPP_OK;
+  GridStore* g;
+  PPP_TRY(cloud_get_grid(c, cloud_cell_for_radius(c, rmax), &g));
+  unsigned char* f_d = nullptr; float* q_d = nullptr; float* r_d = nullptr;
+  PPP_TRY(dev_alloc(ctx, &f_d, (size_t)c->n));
+  PPP_TRY(dev_alloc(ctx, (char**)&q_d, nq * q_stride_bytes + 16));
+  PPP_TRY(dev_alloc(ctx, &r_d, nq));
+  PPP_CUDA(cudaMemcpyAsync(f_d, flags, (size_t)c->n, cudaMemcpyHostToDevice, ctx->stream));
+  PPP_CUDA(cudaMemcpyAsync(q_d, q, nq * q_stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PPP_CUDA(cudaMemcpyAsync(r_d, r2.data(), nq * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  int st = coverage_mark_launch(c, *g, q_d, (int64_t)nq, (int)(q_stride_bytes / 4), (float)(rmax * rmax), f_d, r_d);
+  if (st == PPP_OK) PPP_CUDA(cudaMemcpyAsync(flags, f_d, (size_t)c->n, cudaMemcpyDeviceToHost, ctx->stream));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  dev_free(ctx, f_d); dev_free(ctx, (char*)q_d); dev_free(ctx, r_d);
+  if (st != PPP_OK) return st;
+  PPP_CUDA(e);
+  return PPP_OK;
+}
+
 // compute_transform's device part for a batch of query points (src/Path_Generation.cpp:362-400):
 // kNN(k) of each query, then computePointPrincipalCurvatures around neighbour [0] on the given
 // normals (n records of normal_stride_bytes, nx ny nz first).  out: nq x 5 floats

@@ -1250,7 +1250,8 @@ __global__ void __launch_bounds__(128) k_principal_curvatures(const int32_t* __r
 
 // compute_coverage (src/Path_Generation.cpp:483-496): every point within `radius` of a query gets
 // its coverage flag set.  No ordering is needed, so candidates are marked as they are scanned.
-__global__ void __launch_bounds__(128) k_coverage_mark(SearchParams P, unsigned char* __restrict__ flags) {
+__global__ void __launch_bounds__(128) k_coverage_mark(SearchParams P, unsigned char* __restrict__ flags,
+                                                       const float* __restrict__ r2_per_query) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= P.nq) return;
   const GridView& g = P.g;
@@ -1259,7 +1260,8 @@ __global__ void __launch_bounds__(128) k_coverage_mark(SearchParams P, unsigned 
   if (!finite3(qx, qy, qz) || g.n_sorted == 0) return;
   int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
   int cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
-  const float r2 = P.r2;
+  const float r2 = r2_per_query ? __ldg(r2_per_query + t) : P.r2;   // the block radius R0 covers the largest of them
+  if (!(r2 > 0.0f)) return;                                        // NaN / zero radius: nothing is strictly inside
   visit_annulus(g, cu, cv, -1, P.R0, [&](float4 c) {
     if (d2_flann(qx, qy, qz, c.x, c.y, c.z) < r2) flags[__float_as_int(c.w)] = 1;
   });
@@ -1562,14 +1564,14 @@ int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int6
 }
 
 int coverage_mark_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq, int q_stride_f, float r2,
-                         unsigned char* flags_dev) {
+                         unsigned char* flags_dev, const float* r2_per_query_dev) {
   ppp_ctx* ctx = c->ctx;
   if (nq <= 0) return PPP_OK;
   SearchParams P{};
   P.g = gs.v; P.xyz4 = c->xyz4; P.q = q_dev; P.q_sf = q_stride_f; P.nq = nq;
   P.mode = 1; P.r2 = r2; P.R0 = radius_rings(gs.v, std::sqrt((double)r2));
   unsigned blocks = (unsigned)((nq + 127) / 128);
-  PPP_LAUNCH(ctx, "coverage_mark", k_coverage_mark, blocks, 128, 0, P, flags_dev);
+  PPP_LAUNCH(ctx, "coverage_mark", k_coverage_mark, blocks, 128, 0, P, flags_dev, r2_per_query_dev);
   PPP_CHECK_LAUNCH();
   return PPP_OK;
 }

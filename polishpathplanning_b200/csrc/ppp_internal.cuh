@@ -259,7 +259,7 @@ int principal_curvatures_launch(ppp_cloud* c, const int32_t* idx_dev, int64_t nq
 int sor_mean_distances_launch(ppp_cloud* c, const GridStore& gs, int mean_k, int sqrt_float, float* dist_dev,
                               unsigned long long* n_valid_dev);
 int coverage_mark_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq, int q_stride_f, float r2,
-                         unsigned char* flags_dev);
+                         unsigned char* flags_dev, const float* r2_per_query_dev = nullptr);
 
 // slices.cu
 int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_width, int truncate_center, int sort_bands,

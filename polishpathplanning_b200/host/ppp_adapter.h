@@ -126,6 +126,26 @@ inline Contours slice_contours(ppp_cloud* c, const std::vector<float>& planes, i
   return r;
 }
 
+// rangedX_index(position): ONE band pass in the common case.  The index buffer is sized from the previous call
+// on this thread (bands of neighbouring planes have similar populations); only when it turns out too small does
+// the library report the required size and a second pass fill it.  (The reference's sweep loops call this once
+// per plane, src/Path_Generation.cpp:716-723.)
+inline std::vector<int> ranged_x_index(ppp_cloud* c, int position) {
+  static thread_local int64_t cap_hint = 16384;
+  const float px = (float)position;
+  int64_t off[2] = {0, 0};
+  std::vector<int> idx((size_t)cap_hint);
+  int st = ppp_slice_bands(c, &px, 1, 2.0f, 1, off, idx.data(), (int64_t)idx.size());
+  if (st == PPP_ERR_CAPACITY) {
+    idx.resize((size_t)off[1]);
+    st = ppp_slice_bands(c, &px, 1, 2.0f, 1, off, idx.data(), (int64_t)idx.size());
+  }
+  check(st, "ppp_slice_bands");
+  idx.resize((size_t)off[1]);
+  cap_hint = std::max<int64_t>(16384, off[1] + off[1] / 4);
+  return idx;
+}
+
 // insert_point with the caller's index list (strictly ascending, as rangedX_index returns it)
 inline MAP insert_point(ppp_cloud* c, const std::vector<int>& indices, float plane_x, int mode) {
   int64_t n = 0;
@@ -178,12 +198,7 @@ public:
   }
 
   std::vector<int> rangedX_index(int position) {  // PassThrough "x", [-2 + position, 2 + position]
-    float px = (float)position;
-    int64_t off[2] = {0, 0};
-    ppp_host::check(ppp_slice_bands(dev_.get(*cloud), &px, 1, 2.0f, 1, off, nullptr, 0), "ppp_slice_bands(size)");
-    std::vector<int> idx((size_t)off[1]);
-    ppp_host::check(ppp_slice_bands(dev_.get(*cloud), &px, 1, 2.0f, 1, off, idx.data(), off[1]), "ppp_slice_bands");
-    return idx;
+    return ppp_host::ranged_x_index(dev_.get(*cloud), position);
   }
 
   MAP insert_point(std::vector<int> indices, Eigen::Vector3f PlanePoint) {
@@ -349,12 +364,7 @@ protected:
   }
 
   std::vector<int> rangedX_index(int position) {
-    float px = (float)position;
-    int64_t off[2] = {0, 0};
-    ppp_host::check(ppp_slice_bands(dev_.get(*cloud), &px, 1, 2.0f, 1, off, nullptr, 0), "ppp_slice_bands(size)");
-    std::vector<int> idx((size_t)off[1]);
-    ppp_host::check(ppp_slice_bands(dev_.get(*cloud), &px, 1, 2.0f, 1, off, idx.data(), off[1]), "ppp_slice_bands");
-    return idx;
+    return ppp_host::ranged_x_index(dev_.get(*cloud), position);
   }
   MAP insert_point(std::vector<int> indices, Eigen::Vector3f PlanePoint) {
     return ppp_host::insert_point(dev_.get(*cloud), indices, PlanePoint[0], PPP_PAIR_SECT);

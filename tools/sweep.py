@@ -72,7 +72,7 @@ def main():
         c.close()
         del raw, nrm
         torch.cuda.empty_cache()
-    print("%-18s %10s %8s %10s %12s %10s %s" % ("stage", "points", "param", "ms", "Mpts/s", "alg GB/s", "ok"))
+    print("%-18s %10s %8s %10s %12s %10s %s" % ("stage", "points", "param", "ms", "Gpts/s", "alg GB/s", "ok"))
     for r in rows:
         print("%-18s %10d %8s %10.3f %12.1f %10.1f %s" % r)
     ctx.close()
