@@ -348,7 +348,15 @@ def roofline_of(prof, steps, n_local, k, members, nodes):
 
 
 # ---- one GPU ------------------------------------------------------------------------------------
-def measure_single(env, cfg, steps, warmup):
+def normals_call(c, cfg, normals_ptr, stride, idx_ptr):
+    """estimate_normal: k-nearest (the benchmark's configuration) or the reference's own radius 2.5 mode."""
+    if cfg.get("radius"):
+        c.dev_normals_radius(cfg["radius"], normals_ptr, stride)
+    else:
+        c.dev_normals_knn(cfg["k"], normals_ptr, stride, idx_ptr=idx_ptr)
+
+
+def measure_single(env, cfg, steps, warmup, e2e=True):
     from polishpathplanning_b200 import api, synth
     torch, ctx, dev = env.torch, env.ctx, env.dev
     n, k, S = cfg["n_total"], cfg["k"], cfg["S"]
@@ -363,13 +371,18 @@ def measure_single(env, cfg, steps, warmup):
 
     def dev_step():
         c = api.Cloud(ctx, device_ptr=raw_d.data_ptr(), n=n, stride_bytes=32)
-        c.dev_normals_knn(k, normals_d.data_ptr(), 32, idx_ptr=idx_d.data_ptr())
+        normals_call(c, cfg, normals_d.data_ptr(), 32, idx_d.data_ptr())
         res = c.dev_slice_contours(planes, PAIRING, HALF_WIDTH, True)
         last["nodes"], last["members"] = res["total_nodes"], res["total_members"]
         c.close()
 
     total_ms, _, launches, t_wall = timed_device_steps(env, dev_step, steps, warmup)
     prof = kernel_profile(env, dev_step, steps)
+    if not e2e:
+        del raw_d, normals_d, idx_d
+        return {"units": n, "total_ms": total_ms, "launches": launches, "t_wall": t_wall, "prof": prof, "e2e_s": float("nan"),
+                "h2d": 0, "d2h": 0, "n_local": n, "members": last.get("members", 0), "nodes": last.get("nodes", 0),
+                "exchange_ms": None, "parity": None}
 
     # ---- end to end through the host-pointer C ABI (pinned buffers) ----
     pin_cloud = ctx.pinned_empty(cloud.shape, np.float32)
@@ -406,7 +419,7 @@ def measure_single(env, cfg, steps, warmup):
 
 
 # ---- N GPUs, one rank each ----------------------------------------------------------------------
-def measure_multi(env, cfg, steps, warmup, verify=True):
+def measure_multi(env, cfg, steps, warmup, verify=True, e2e=True):
     from polishpathplanning_b200 import api, parallel, synth
     torch, ctx, dev, dist, rank, world = env.torch, env.ctx, env.dev, env.dist, env.rank, env.world
     n_total, k, S = cfg["n_total"], cfg["k"], cfg["S"]
@@ -421,7 +434,7 @@ def measure_multi(env, cfg, steps, warmup, verify=True):
         cloud_h[...] = synth.panel(n_total, seed=0)
     dist.barrier()
     cap_recv = int(n_r * 1.25) + 65536
-    node_cap = max(262144, n_r // 3)
+    node_cap = max(262144, n_r // 3, int(0.25 * 4 * np.sqrt(n_total) * S / world) + 65536)   # ~14 % of the band members become nodes
     ex = parallel.Exchange.over_dist(ctx, dist, dev, rank, world, n_total, cap_recv, S, node_cap, 32)
     cap_recv, node_cap = ex.cap_recv, ex.node_cap
     lay = parallel.host_region_layout(world, n_total, 32, S, node_cap)
@@ -481,7 +494,7 @@ def measure_multi(env, cfg, steps, warmup, verify=True):
             want_y = base + lay["off_bytes"]
         else:
             want_y = ex.nodes_region(rank)["y"] if rank == 0 else None
-        c.dev_normals_knn(k, ex.home_normals_ptr, 32, idx_ptr=idx_d.data_ptr())
+        normals_call(c, cfg, ex.home_normals_ptr, 32, idx_d.data_ptr())
         t_s = mark("index+knn", t_s)
         ex.results_signal(ex.NORMALS)
         if to_host:
@@ -513,6 +526,17 @@ def measure_multi(env, cfg, steps, warmup, verify=True):
         sys.stderr.write("[rank %d] own step %.4f ms; exchange %.4f ms; n_local %d; kernels %s\n" % (
             rank, own_ms / steps, ex_ms / max(ex_regions, 1), last["n_local"],
             {kk: round(v[0] / steps, 4) for kk, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:5]}))
+
+    if not e2e:
+        out = {"units": n_total, "total_ms": total_ms, "launches": launches, "t_wall": t_wall, "prof": prof, "e2e_s": float("nan"),
+               "h2d": 0, "d2h": 0, "n_local": last["n_local"], "members": last["members"], "nodes": last["nodes"],
+               "exchange_ms": exchange_ms, "parity": None}
+        del cloud_h, arrive
+        ex.close(dist)
+        src.close()
+        dst.close()
+        del chunk_d, idx_d
+        return out
 
     # ---- end to end: ONE host buffer in, ONE host buffer out ----
     normals_h = dst.array(np.float32, (n_total, 8), ctl_bytes)

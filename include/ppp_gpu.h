@@ -96,7 +96,11 @@ int ppp_cloud_set_cell_hint(ppp_cloud* cloud, float cell_size);
 int ppp_knn(ppp_cloud* cloud, const float* q, size_t nq, size_t q_stride_bytes, int k,
             int32_t* idx_out /* nq*k, -1 padded */, float* d2_out /* nullable */);
 /* two-call sizing: idx_out == NULL writes counts only; otherwise offsets (nq+1) must be the
- * exclusive scan of counts and lists are written sorted by (d2, idx). Membership d2 < (float)(r*r). */
+ * exclusive scan of counts and lists are written sorted by (d2, idx). Membership d2 < (float)(r*r).
+ * LIMIT: a list is ordered in shared memory, so the fill call (and ppp_normals_radius on clouds whose
+ * queries have more than 32 neighbours) returns PPP_ERR_UNSUPPORTED when ANY query has more than
+ * ~900 neighbours (sharedMemPerBlockOptin / 256 entries; at the reference's radius 2.5 that is a scan
+ * denser than ~45 points/mm^2).  Counts-only calls have no limit.                                  */
 int ppp_radius(ppp_cloud* cloud, const float* q, size_t nq, size_t q_stride_bytes, double radius,
                int32_t* counts, const int64_t* offsets, int32_t* idx_out, float* d2_out);
 

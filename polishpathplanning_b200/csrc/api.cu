@@ -181,7 +181,8 @@ static int cloud_new(ppp_ctx* ctx, size_t n, ppp_cloud** out) {
   ppp_cloud* c = new ppp_cloud();
   c->ctx = ctx;
   c->n = (int64_t)n;
-  c->grids.reserve(8);
+  c->grids.reserve(48);   // pointers into these vectors are handed out: they never reallocate
+  c->mps.reserve(16);
   *out = c;
   return PPP_OK;
 }
@@ -224,6 +225,10 @@ int ppp_cloud_free(ppp_cloud* c) {
   for (auto& g : c->grids) {
     dev_free(ctx, g.sorted); dev_free(ctx, g.cell_start); dev_free(ctx, g.order);
     if (g.ready) cudaEventDestroy(g.ready);
+  }
+  for (auto& m : c->mps) {
+    dev_free(ctx, m.choice);
+    if (m.ready) cudaEventDestroy(m.ready);
   }
   dev_free(ctx, c->c_node_off); dev_free(ctx, c->c_y); dev_free(ctx, c->c_x); dev_free(ctx, c->c_z);
   delete c;
@@ -389,7 +394,19 @@ int ppp_dev_normals_knn(ppp_cloud* c, int k, const float vp[3], unsigned flags, 
   if (count < 0) count = c->n_finite - first;
   REQUIRE(first >= 0 && first + count <= c->n_finite, "query range outside the indexed points");
   GridStore* g;
-  PPP_TRY(cloud_get_grid(c, cloud_cell_for_k(c, k), &g));
+  const double h = cloud_cell_for_k(c, k);
+  PPP_TRY(cloud_get_grid(c, h, &g));
+  PPP_TRY(cloud_decide_projection(c, *g));
+  if (c->mp_state == 1 && first == 0 && count == c->n_finite && k <= 64) {
+    // not a height field: one grid per axis pair, every point searched in the projection that spreads its
+    // neighbourhood out best (three launches, each warp leaves at once unless some of its points are its own)
+    MPSet* mp;
+    PPP_TRY(cloud_get_mp(c, h, knn_block_rings(), &mp));
+    for (int p = 0; p < 3; p++)
+      PPP_TRY(knn_launch(c, *mp->g[p], nullptr, count, 0, 0, k, knn_idx_dev, knn_d2_dev, normals_dev != nullptr, vp, flags,
+                         normals_dev, (int)(normal_stride_bytes / 4), mp->choice, p));
+    return PPP_OK;
+  }
   return knn_launch(c, *g, nullptr, count, 0, first, k, knn_idx_dev, knn_d2_dev, normals_dev != nullptr, vp, flags,
                     normals_dev, (int)(normal_stride_bytes / 4));
 }
@@ -404,13 +421,23 @@ int ppp_dev_normals_radius(ppp_cloud* c, double radius, const float vp[3], unsig
   if (count < 0) count = c->n_finite - first;
   REQUIRE(first >= 0 && first + count <= c->n_finite, "query range outside the indexed points");
   GridStore* g;
-  PPP_TRY(cloud_get_grid(c, cloud_cell_for_radius(c, radius), &g));
+  const double h = cloud_cell_for_radius(c, radius);
+  PPP_TRY(cloud_get_grid(c, h, &g));
   float r2 = (float)(radius * radius);  // [upstream] pcl::KdTreeFLANN::radiusSearch
+  PPP_TRY(cloud_decide_projection(c, *g));
+  if (c->mp_state == 1 && first == 0 && count == c->n_finite) {
+    MPSet* mp;
+    PPP_TRY(cloud_get_mp(c, h, 2, &mp));     // cloud_cell_for_radius sizes the cells so that two rings cover the radius
+    for (int p = 0; p < 3; p++)
+      PPP_TRY(normals_radius_launch(c, *mp->g[p], 0, count, r2, vp, flags, normals_dev, (int)(normal_stride_bytes / 4), mp->choice, p));
+    return PPP_OK;
+  }
   return normals_radius_launch(c, *g, first, count, r2, vp, flags, normals_dev, (int)(normal_stride_bytes / 4));
 }
 
 static int pick_any_grid(ppp_cloud* c, GridStore** g) {
-  if (!c->grids.empty()) { *g = &c->grids.back(); return PPP_OK; }
+  for (size_t i = c->grids.size(); i-- > 0;)
+    if (c->grids[i].drop == c->drop) { *g = &c->grids[i]; return PPP_OK; }
   return cloud_get_grid(c, cloud_cell_for_k(c, 16), g);
 }
 
@@ -426,23 +453,26 @@ int ppp_dev_slice_contours(ppp_cloud* c, const float* plane_x_host, int S, float
   PPP_CUDA(cudaSetDevice(ctx->device));
   GridStore* g;
   PPP_TRY(pick_any_grid(c, &g));
+  PPP_TRY(cloud_decide_projection(c, *g));
+  MPSet* mp = nullptr;
+  if (c->mp_state == 1) PPP_TRY(cloud_get_mp(c, g->h, knn_block_rings(), &mp));
   int st;
   int64_t M = 0, total = 0;
   {
     // The slicing chain depends on the packed cloud and the grid only, not on the neighbour
     // search: it runs on the high-priority auxiliary stream, concurrently with a kNN / normals
     // kernel still executing on the main stream; the main stream waits for it on scope exit.
-    AuxScope aux(ctx, g->ready);
+    AuxScope aux(ctx, mp ? mp->ready : g->ready);   // (the projections are built after the primary grid)
     // SectPath pairing: the chain without mid-way host round trips, unless its allocation bound is too large
     st = pairing_mode == PPP_PAIR_SECT && !getenv("PPP_SLICE_SYNC")
-             ? slice_contours_sect_async(c, *g, plane_x_host, S, half_width, truncate_center, &total, &M)
+             ? slice_contours_sect_async(c, *g, plane_x_host, S, half_width, truncate_center, &total, &M, mp)
              : PPP_ERR_UNSUPPORTED;
     if (st == PPP_ERR_UNSUPPORTED) {
       int64_t* boff = nullptr; int32_t* bidx = nullptr; float* planes = nullptr;
       std::vector<int64_t> off_h;
       st = bands_launch(c, plane_x_host, S, half_width, truncate_center, pairing_mode == PPP_PAIR_GEN2, &boff, &bidx, &M,
                         &planes, &off_h);
-      if (st == PPP_OK) st = contours_launch(c, *g, planes, S, boff, bidx, M, off_h, pairing_mode, &total);
+      if (st == PPP_OK) st = contours_launch(c, *g, planes, S, boff, bidx, M, off_h, pairing_mode, &total, nullptr, mp);
       dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, planes);
     }
   }
@@ -810,8 +840,11 @@ int ppp_insert_point(ppp_cloud* c, const int32_t* indices, int64_t m, float plan
   PPP_CUDA(cudaSetDevice(ctx->device));
   GridStore* g;
   PPP_TRY(pick_any_grid(c, &g));
+  PPP_TRY(cloud_decide_projection(c, *g));
+  MPSet* mp = nullptr;
+  if (c->mp_state == 1) PPP_TRY(cloud_get_mp(c, g->h, knn_block_rings(), &mp));
   int64_t total = 0;
-  PPP_TRY(contours_from_indices_launch(c, *g, indices, m, plane_x, pairing_mode, &total));
+  PPP_TRY(contours_from_indices_launch(c, *g, indices, m, plane_x, pairing_mode, &total, mp));
   *n_nodes = total;
   int st = PPP_OK;
   if (y) {

@@ -142,6 +142,134 @@ __global__ void __launch_bounds__(256) k_cell_scatter(GridView g, const float4* 
   order[slot] = (int)i;
 }
 
+// Surface density around a sample of the points: block b takes point b * stride_s of the cloud and looks at
+// every stride_m-th point.  Each thread keeps the two smallest squared distances it meets -- in space, and in
+// projection onto the two axes of largest extent (the primary column grid); the 8th smallest of the block's 512
+// values of either kind is (almost always exactly) the 8th nearest point of the subsample.  The 3-D value gives
+// the surface density whatever the shape; the ratio of the two says how the surface projects: ~1 for a height
+// field, 2-3 where sheets cover each other, tens along a vertical wall or the silhouette of a closed shape.
+// out: [0, S) squared 3-D distance, [S, 2S) squared projected distance.
+constexpr int DS_KTH = 8;
+constexpr int DS_THREADS = 512;
+__device__ __forceinline__ float ds_ord2f(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+  return __uint_as_float(b);
+}
+
+// kth smallest of the 2 * DS_THREADS values in s (one warp; the values are consumed)
+__device__ __forceinline__ float ds_kth_smallest(const float* s) {
+  float v[2 * DS_THREADS / 32];
+#pragma unroll
+  for (int i = 0; i < 2 * DS_THREADS / 32; i++) v[i] = s[i * 32 + (threadIdx.x & 31)];
+  float kth = CUDART_INF_F;
+  for (int r = 0; r < DS_KTH; r++) {
+    float mine = CUDART_INF_F;
+    int at = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * DS_THREADS / 32; i++) if (v[i] < mine) { mine = v[i]; at = i; }
+    float w = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w = fminf(w, __shfl_xor_sync(0xffffffffu, w, o));
+    kth = w;
+    const unsigned holders = __ballot_sync(0xffffffffu, mine == w && w < CUDART_INF_F);
+    if (holders && (int)(threadIdx.x & 31) == __ffs(holders) - 1) {   // remove it from ONE lane's values
+#pragma unroll
+      for (int i = 0; i < 2 * DS_THREADS / 32; i++) if (i == at) v[i] = CUDART_INF_F;
+    }
+  }
+  return kth;
+}
+
+__global__ void __launch_bounds__(DS_THREADS) k_density_sample(const float4* __restrict__ xyz4, int64_t n, int64_t stride_s,
+                                                               int64_t stride_m, const BBoxAcc* __restrict__ acc,
+                                                               float* __restrict__ out, int S) {
+  __shared__ float s_d[2 * DS_THREADS], s_p[2 * DS_THREADS];
+  // the axis the primary grid does not span: smallest extent, ties drop z, then y (as cloud_ingest decides)
+  int drop = 2;
+  {
+    double ext[3];
+    for (int d = 0; d < 3; d++) ext[d] = (double)ds_ord2f(acc->mx[d]) - (double)ds_ord2f(acc->mn[d]);
+    if (ext[1] < ext[drop]) drop = 1;
+    if (ext[0] < ext[drop]) drop = 0;
+  }
+  const float4 q = __ldg(xyz4 + (int64_t)blockIdx.x * stride_s);
+  const bool qfin = q.w == q.w;
+  float d0 = CUDART_INF_F, d1 = CUDART_INF_F, p0 = CUDART_INF_F, p1 = CUDART_INF_F;
+  if (qfin) {
+    constexpr int PPT = 4;   // independent (scattered) loads in flight per thread
+    for (int64_t j0 = (int64_t)threadIdx.x * stride_m; j0 < n; j0 += (int64_t)DS_THREADS * PPT * stride_m) {
+      float4 p[PPT];
+#pragma unroll
+      for (int u = 0; u < PPT; u++) {
+        const int64_t j = j0 + (int64_t)u * DS_THREADS * stride_m;
+        p[u] = j < n ? __ldg(xyz4 + j) : make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+      }
+#pragma unroll
+      for (int u = 0; u < PPT; u++) {
+        const float dx = q.x - p[u].x, dy = q.y - p[u].y, dz = q.z - p[u].z;
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        if (!(d2 > 0.0f) || !(d2 < CUDART_INF_F)) continue;     // the sample itself, exact duplicates, non-finite points
+        const float p2 = drop == 0 ? dy * dy + dz * dz : (drop == 1 ? dx * dx + dz * dz : dx * dx + dy * dy);
+        if (d2 < d0) { d1 = d0; d0 = d2; } else if (d2 < d1) d1 = d2;
+        if (p2 < p0) { p1 = p0; p0 = p2; } else if (p2 < p1) p1 = p2;
+      }
+    }
+  }
+  s_d[threadIdx.x] = d0; s_d[DS_THREADS + threadIdx.x] = d1;
+  s_p[threadIdx.x] = p0; s_p[DS_THREADS + threadIdx.x] = p1;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const float r2 = ds_kth_smallest(s_d);
+    if (threadIdx.x == 0) out[blockIdx.x] = r2;
+  } else if (threadIdx.x < 64) {
+    const float r2 = ds_kth_smallest(s_p);
+    if ((threadIdx.x & 31) == 0) out[S + blockIdx.x] = r2;
+  }
+}
+
+struct G3 { GridView g[3]; };
+
+// Points in the (2R+1)^2 cell block around p in grid g.
+__device__ __forceinline__ int block_population(const GridView& g, float x, float y, float z, int R) {
+  const int cu = cell_coord_raw(axis_of(x, y, z, g.au), g.min_u, g.inv_h);
+  const int cv = cell_coord_raw(axis_of(x, y, z, g.av), g.min_v, g.inv_h);
+  const int a = max(cu - R, 0), b = min(cu + R, g.nu - 1);
+  if (a > b) return 0;
+  int cnt = 0;
+  for (int v = max(cv - R, 0); v <= min(cv + R, g.nv - 1); v++) {
+    const int32_t* row = g.cell_start + (int64_t)v * g.nu;
+    cnt += __ldg(row + b + 1) - __ldg(row + a);
+  }
+  return cnt;
+}
+
+// choice[i]: the projection whose candidate block around point i holds the fewest points.  Every block is a
+// superset of the 3-D ball of radius R*h around the point (projecting only shortens distances), so the smallest
+// block is simply the one with the fewest points that are NOT neighbours.  hist[p]: how many points chose p.
+__global__ void __launch_bounds__(256) k_mp_choose(G3 G, const float4* __restrict__ xyz4, int64_t n, int R,
+                                                   unsigned char* __restrict__ choice, unsigned long long* __restrict__ hist) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int pick = -1;
+  if (i < n) {
+    const float4 p = __ldg(xyz4 + i);
+    pick = 0;
+    if (p.w == p.w) {
+      int best_cnt = 2147483647;
+#pragma unroll
+      for (int k = 2; k >= 0; k--) {     // ties: prefer x,y then x,z then y,z
+        const int cnt = block_population(G.g[k], p.x, p.y, p.z, R);
+        if (cnt < best_cnt) { pick = k; best_cnt = cnt; }
+      }
+    }
+    choice[i] = (unsigned char)pick;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const unsigned bal = __ballot_sync(0xffffffffu, pick == k);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(hist + k, (unsigned long long)__popc(bal));
+  }
+}
+
 }  // namespace
 
 int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes) {
@@ -158,9 +286,26 @@ int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes) {
     PPP_LAUNCH(ctx, "pack_bbox", k_pack_bbox, blocks, 256, 0, (const float*)pts_dev, c->n, sf, vec_ok, c->xyz4, acc);
     PPP_CHECK_LAUNCH();
   }
+  // surface density + projection quality from a sample (same synchronisation as the bounding box)
+  constexpr int DS_SAMPLES = 128;
+  const int64_t ds_m = std::min<int64_t>(c->n, 16384);                 // subsample every block searches
+  const int64_t stride_m = ds_m > 0 ? std::max<int64_t>(1, c->n / ds_m) : 1;
+  const int ds_s = (int)std::min<int64_t>(DS_SAMPLES, c->n);
+  const int64_t stride_s = ds_s > 0 ? std::max<int64_t>(1, c->n / ds_s) : 1;
+  float* ds_out = nullptr;
+  PPP_TRY(dev_alloc(ctx, &ds_out, (size_t)2 * DS_SAMPLES + sizeof(BBoxAcc) / 4 + 4));
+  if (ds_s > 0) {
+    PPP_LAUNCH(ctx, "density_sample", k_density_sample, ds_s, DS_THREADS, 0, (const float4*)c->xyz4, c->n, stride_s, stride_m,
+               (const BBoxAcc*)acc, ds_out, DS_SAMPLES);
+    PPP_CHECK_LAUNCH();
+  }
   BBoxAcc h;
-  PPP_TRY(fetch_small(ctx, acc, sizeof(h), &h));
+  PPP_CUDA(cudaMemcpyAsync(ds_out + 2 * DS_SAMPLES, acc, sizeof(BBoxAcc), cudaMemcpyDeviceToDevice, ctx->stream));
+  std::vector<float> ds_h((size_t)2 * DS_SAMPLES + sizeof(BBoxAcc) / 4);
+  PPP_TRY(fetch_small(ctx, ds_out, ds_h.size() * sizeof(float), ds_h.data()));   // ONE fetch: samples + bounding box
+  memcpy(&h, ds_h.data() + 2 * DS_SAMPLES, sizeof(h));
   dev_free(ctx, acc);
+  dev_free(ctx, ds_out);
   c->n_finite = (int64_t)h.n_finite;
   for (int d = 0; d < 3; d++) {
     // [upstream] getMinMax3D starts from +/-FLT_MAX; an all-non-finite cloud keeps those.
@@ -173,10 +318,37 @@ int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes) {
   int drop = 2;  // the axis with the smallest extent is not gridded (ties: drop z, then y)
   if (ext[1] < ext[drop]) drop = 1;
   if (ext[0] < ext[drop]) drop = 0;
+  c->drop = drop;
   c->au = drop == 0 ? 1 : 0;
   c->av = drop == 2 ? 1 : 2;
   double area = std::max(ext[c->au], 1e-9) * std::max(ext[c->av], 1e-9);
-  c->density = c->n_finite > 0 ? (double)c->n_finite / area : 0.0;
+  c->density = c->n_finite > 0 ? (double)c->n_finite / area : 0.0;     // fallback: points per bounding-rectangle area
+  // sampled estimate: the area out to the k-th neighbour of a Poisson process is Gamma(k) distributed (median
+  // 7.67 for k = 8); the samples saw every stride_m-th point only
+  std::vector<float> r2;
+  int piled = 0;
+  for (int i = 0; i < ds_s; i++)
+    if (std::isfinite(ds_h[i]) && ds_h[i] > 0) {
+      r2.push_back(ds_h[i]);
+      piled += ds_h[DS_SAMPLES + i] * 4.0f < ds_h[i] ? 1 : 0;   // the same count within 1/4 of the area: 4x denser in projection
+    }
+  // Not a height field over the primary axis pair if a noticeable share of the surface piles up in projection
+  // (vertical walls, silhouettes of closed shapes): use one column grid per axis pair (MPSet).
+  c->mp_state = (r2.size() >= 32 && c->n_finite >= 4096 && piled * 25 > (int)r2.size()) ? 1 : 0;
+  if (const char* e = getenv("PPP_PROJECTIONS")) {            // tuning / test aid: 1 = never, 3 = always
+    if (e[0] == '1') c->mp_state = 0;
+    if (e[0] == '3') c->mp_state = 1;
+  }
+  if (getenv("PPP_DEBUG"))
+    fprintf(stderr, "[ppp] ingest: %d of %zu samples pile up in projection -> %s\n", piled, r2.size(),
+            c->mp_state ? "three projections" : "one column grid");
+  if (r2.size() >= 16 && c->n_finite >= 64) {
+    std::nth_element(r2.begin(), r2.begin() + r2.size() / 2, r2.end());
+    const double r2_med = (double)r2[r2.size() / 2];
+    const double seen = (double)((c->n + stride_m - 1) / stride_m) * ((double)c->n_finite / (double)c->n);
+    const double rho_sub = 7.67 / (3.14159265358979 * r2_med);
+    c->density = rho_sub * (double)c->n_finite / std::max(seen, 1.0);
+  }
   return PPP_OK;
 }
 
@@ -206,23 +378,31 @@ double cloud_cell_for_radius(const ppp_cloud* c, double r) {
   return r * 0.5 * (1.0 + 1e-3);
 }
 
-int cloud_get_grid(ppp_cloud* c, double h, GridStore** out) {
+int cloud_get_grid(ppp_cloud* c, double h, GridStore** out) { return cloud_get_grid_drop(c, h, c->drop, out); }
+
+int cloud_get_grid_drop(ppp_cloud* c, double h, int drop, GridStore** out) {
   ppp_ctx* ctx = c->ctx;
+  const int au = drop == 0 ? 1 : 0, av = drop == 2 ? 1 : 2;
   // cap the dense cell table (nu*nv <= 2^28) by growing h if needed
-  double eu = c->n_finite ? (double)c->bmax[c->au] - (double)c->bmin[c->au] : 0.0;
-  double ev = c->n_finite ? (double)c->bmax[c->av] - (double)c->bmin[c->av] : 0.0;
+  double eu = c->n_finite ? (double)c->bmax[au] - (double)c->bmin[au] : 0.0;
+  double ev = c->n_finite ? (double)c->bmax[av] - (double)c->bmin[av] : 0.0;
   if (!(h > 0)) h = 1.0;
   while ((std::floor(eu / h) + 2) * (std::floor(ev / h) + 2) > 268435456.0) h *= 1.5;
   for (auto& g : c->grids)
-    if (std::fabs(g.h - h) <= 1e-9 * h) { *out = &g; return PPP_OK; }
+    if (g.drop == drop && std::fabs(g.h - h) <= 1e-9 * h) { *out = &g; return PPP_OK; }
+  if (c->grids.size() >= c->grids.capacity()) {
+    ppp_set_error("too many different cell sizes on one cloud (%zu grids)", c->grids.size());
+    return PPP_ERR_UNSUPPORTED;   // pointers into c->grids are handed out: the vector must not reallocate
+  }
   GridStore gs;
   gs.h = h;
+  gs.drop = drop;
   GridView& v = gs.v;
-  v.au = c->au; v.av = c->av;
+  v.au = au; v.av = av;
   v.h = (float)h;
   v.inv_h = 1.0f / v.h;
-  v.min_u = c->n_finite ? c->bmin[c->au] : 0.0f;
-  v.min_v = c->n_finite ? c->bmin[c->av] : 0.0f;
+  v.min_u = c->n_finite ? c->bmin[au] : 0.0f;
+  v.min_v = c->n_finite ? c->bmin[av] : 0.0f;
   v.nu = (int)std::floor(eu * (double)v.inv_h) + 2;
   v.nv = (int)std::floor(ev * (double)v.inv_h) + 2;
   // rounding slack: cell coordinates are exact to a few ulps of (a-min)*inv_h
@@ -254,6 +434,45 @@ int cloud_get_grid(ppp_cloud* c, double h, GridStore** out) {
   PPP_CUDA(cudaEventRecord(gs.ready, ctx->stream));
   c->grids.push_back(gs);
   *out = &c->grids.back();
+  return PPP_OK;
+}
+
+// Whether the primary column grid is enough was decided at ingest from the sample (c->mp_state).
+int cloud_decide_projection(ppp_cloud* c, const GridStore& g) {
+  (void)g;
+  if (c->mp_state < 0) c->mp_state = 0;
+  return PPP_OK;
+}
+
+int cloud_get_mp(ppp_cloud* c, double h, int R0, MPSet** out) {
+  ppp_ctx* ctx = c->ctx;
+  for (auto& m : c->mps)
+    if (m.R0 == R0 && std::fabs(m.h - h) <= 1e-9 * h) { *out = &m; return PPP_OK; }
+  if (c->mps.size() >= c->mps.capacity()) { ppp_set_error("too many multi-projection index sets on one cloud"); return PPP_ERR_UNSUPPORTED; }
+  MPSet m;
+  m.h = h; m.R0 = R0;
+  for (int p = 0; p < 3; p++) PPP_TRY(cloud_get_grid_drop(c, h, p, &m.g[p]));
+  PPP_TRY(dev_alloc_keep(ctx, &m.choice, (size_t)std::max<int64_t>(c->n, 1)));
+  unsigned long long* hist = nullptr;
+  PPP_TRY(dev_alloc(ctx, &hist, 3));
+  PPP_CUDA(cudaMemsetAsync(hist, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  if (c->n > 0) {
+    G3 G;
+    for (int p = 0; p < 3; p++) G.g[p] = m.g[p]->v;
+    PPP_LAUNCH(ctx, "mp_choose", k_mp_choose, (unsigned)((c->n + 255) / 256), 256, 0, G, (const float4*)c->xyz4, c->n, R0,
+               m.choice, hist);
+    PPP_CHECK_LAUNCH();
+  }
+  if (getenv("PPP_DEBUG")) {
+    unsigned long long hh[3] = {0, 0, 0};
+    PPP_TRY(fetch_small(ctx, hist, sizeof(hh), hh));
+    fprintf(stderr, "[ppp] projections chosen (h = %g, R0 = %d): yz %llu, xz %llu, xy %llu\n", h, R0, hh[0], hh[1], hh[2]);
+  }
+  dev_free(ctx, hist);
+  PPP_CUDA(cudaEventCreateWithFlags(&m.ready, cudaEventDisableTiming));
+  PPP_CUDA(cudaEventRecord(m.ready, ctx->stream));
+  c->mps.push_back(m);
+  *out = &c->mps.back();
   return PPP_OK;
 }
 

@@ -43,7 +43,15 @@ struct SearchParams {
   int32_t* redo_list;   // query numbers t (fast kernel appends; generic kernel consumes)
   int32_t* redo_count;
   int use_redo;         // generic kernel: take the query number from redo_list[thread]
+  // multi-projection index: this launch answers only the self-queries whose point chose projection my_proj
+  const unsigned char* choice;   // per original index, nullptr: every query
+  int my_proj;
 };
+
+// Self-query `row` belongs to this launch?  (Warps none of whose lanes do leave at once.)
+__device__ __forceinline__ bool query_is_mine(const SearchParams& P, bool valid, int64_t row) {
+  return valid && (P.choice == nullptr || __ldg(P.choice + row) == P.my_proj);
+}
 
 __device__ __forceinline__ void list_insert(u64* L, int BD, int& cnt, int cap, u64 key) {
   int j = cnt < cap ? cnt++ : cap - 1;
@@ -78,9 +86,9 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
     qx = p.x; qy = p.y; qz = p.z;
     row = __float_as_int(p.w);
   }
+  if (!P.use_redo && P.choice && __ldg(P.choice + row) != P.my_proj) return;
   u64* L = s_keys + threadIdx.x;
   int cnt = 0;
-  const bool self = P.q == nullptr;
   const bool fin = finite3(qx, qy, qz);
   if (fin && g.n_sorted > 0) {
     int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
   constexpr int BD = 128;  // launch block size (immediate shared-memory offsets)
   const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
   const GridView& g = P.g;
-  const bool valid = t < P.nq;
+  bool valid = t < P.nq;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   int64_t row = 0;
   if (valid) {
@@ -192,6 +200,8 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
     }
   }
   const bool self = P.q == nullptr;
+  valid = query_is_mine(P, valid, row);
+  if (P.choice && !__any_sync(0xffffffffu, valid)) return;   // none of this warp's points chose this projection
   const bool fin = valid && finite3(qx, qy, qz);
   const bool act = fin && g.n_sorted > 0;
   u64* pend_s = s_keys + threadIdx.x;
@@ -436,7 +446,7 @@ __global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_k
   constexpr int K = 16;
   const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
   const GridView& g = P.g;
-  const bool valid = t < P.nq;
+  bool valid = t < P.nq;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   int64_t row = 0;
   if (valid) {
@@ -450,6 +460,8 @@ __global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_k
       row = __float_as_int(p.w);
     }
   }
+  valid = query_is_mine(P, valid, row);
+  if (P.choice && !__any_sync(0xffffffffu, valid)) return;   // none of this warp's points chose this projection
   const bool fin = valid && finite3(qx, qy, qz);
   const bool act = fin && g.n_sorted > 0;
   u64* store = s_keys + threadIdx.x;  // slot j of this thread at store[j * BD]
@@ -638,7 +650,7 @@ __global__ void __launch_bounds__(BD, (BD == 64 ? 8 : 4)) k_knn32c(SearchParams 
   constexpr unsigned SMASK = 63u;   // slot bits of a composite key
   const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
   const GridView& g = P.g;
-  const bool valid = t < P.nq;
+  bool valid = t < P.nq;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   int64_t row = 0;
   if (valid) {
@@ -652,6 +664,8 @@ __global__ void __launch_bounds__(BD, (BD == 64 ? 8 : 4)) k_knn32c(SearchParams 
       row = __float_as_int(p.w);
     }
   }
+  valid = query_is_mine(P, valid, row);
+  if (P.choice && !__any_sync(0xffffffffu, valid)) return;   // none of this warp's points chose this projection
   const bool fin = valid && finite3(qx, qy, qz);
   const bool act = fin && g.n_sorted > 0;
   u64* store = s_keys + threadIdx.x;
@@ -823,7 +837,7 @@ __global__ void __launch_bounds__(128, 6) k_radius_normals32(SearchParams P) {
   constexpr int U = 4;
   const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
   const GridView& g = P.g;
-  const bool valid = t < P.nq;
+  bool valid = t < P.nq;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   int64_t row = 0;
   if (valid) {
@@ -831,6 +845,8 @@ __global__ void __launch_bounds__(128, 6) k_radius_normals32(SearchParams P) {
     qx = p.x; qy = p.y; qz = p.z;
     row = __float_as_int(p.w);
   }
+  valid = query_is_mine(P, valid, row);
+  if (P.choice && !__any_sync(0xffffffffu, valid)) return;
   const bool act = valid && g.n_sorted > 0;  // self queries are finite by construction
   u64* store = s_keys + threadIdx.x;
   const int R = P.R0;
@@ -1150,7 +1166,8 @@ __global__ void __launch_bounds__(128) k_radius_count(SearchParams P, int32_t* _
       qx = p.x; qy = p.y; qz = p.z;
       row = __float_as_int(p.w);
     }
-    if (finite3(qx, qy, qz) && g.n_sorted > 0) {
+    const bool mine = P.use_redo || P.choice == nullptr || P.q != nullptr || __ldg(P.choice + row) == P.my_proj;
+    if (mine && finite3(qx, qy, qz) && g.n_sorted > 0) {
       int cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
       int cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
       const float r2 = P.r2;
@@ -1158,7 +1175,7 @@ __global__ void __launch_bounds__(128) k_radius_count(SearchParams P, int32_t* _
         cnt += d2_flann(qx, qy, qz, c.x, c.y, c.z) < r2 ? 1 : 0;
       });
     }
-    if (counts) counts[row] = cnt;
+    if (counts && mine) counts[row] = cnt;
   }
   int m = cnt;
 #pragma unroll
@@ -1437,7 +1454,7 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
 
 int knn_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq, int q_stride_f, int64_t first, int k,
                int32_t* idx_dev, float* d2_dev, bool with_normals, const float vp[3], unsigned flags,
-               float* normals_dev, int normal_stride_f) {
+               float* normals_dev, int normal_stride_f, const unsigned char* choice, int my_proj) {
   ppp_ctx* ctx = c->ctx;
   SearchParams P{};
   P.g = gs.v; P.xyz4 = c->xyz4; P.q = q_dev; P.q_sf = q_stride_f; P.nq = nq; P.first = first;
@@ -1445,6 +1462,7 @@ int knn_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, int64_t nq
   P.idx_out = idx_dev; P.d2_out = d2_dev; P.offsets = nullptr;
   P.normals = with_normals ? normals_dev : nullptr; P.nsf = normal_stride_f; P.nmap = c->nmap; P.route = c->route;
   P.vpx = vp ? vp[0] : 0; P.vpy = vp ? vp[1] : 0; P.vpz = vp ? vp[2] : 0; P.flags = flags;
+  P.choice = q_dev ? nullptr : choice; P.my_proj = my_proj;
   if (!q_dev && c->n_finite < c->n && first == 0) {
     unsigned blocks = (unsigned)((c->n + 255) / 256);
     PPP_LAUNCH(ctx, "default_rows", k_default_rows, blocks, 256, 0, (const float4*)c->xyz4, c->n, k, idx_dev, d2_dev,
@@ -1494,13 +1512,15 @@ int radius_fill_launch(ppp_cloud* c, const GridStore& gs, const float* q_dev, in
 }
 
 int normals_radius_launch(ppp_cloud* c, const GridStore& gs, int64_t first, int64_t count, float r2,
-                          const float vp[3], unsigned flags, float* normals_dev, int normal_stride_f) {
+                          const float vp[3], unsigned flags, float* normals_dev, int normal_stride_f,
+                          const unsigned char* choice, int my_proj) {
   ppp_ctx* ctx = c->ctx;
   SearchParams P{};
   P.g = gs.v; P.xyz4 = c->xyz4; P.q = nullptr; P.nq = count; P.first = first;
   P.mode = 1; P.r2 = r2; P.R0 = radius_rings(gs.v, std::sqrt((double)r2));
   P.normals = normals_dev; P.nsf = normal_stride_f; P.nmap = c->nmap; P.route = c->route;
   P.vpx = vp ? vp[0] : 0; P.vpy = vp ? vp[1] : 0; P.vpz = vp ? vp[2] : 0; P.flags = flags;
+  P.choice = choice; P.my_proj = my_proj;
   if (c->n_finite < c->n && first == 0) {
     unsigned blocks = (unsigned)((c->n + 255) / 256);
     PPP_LAUNCH(ctx, "default_rows", k_default_rows, blocks, 256, 0, (const float4*)c->xyz4, c->n, 0, (int32_t*)nullptr,

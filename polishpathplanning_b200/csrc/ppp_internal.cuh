@@ -90,6 +90,7 @@ struct NormalRoute {
 
 struct GridStore {
   GridView v{};
+  int drop = 2;              // the axis this grid does NOT span (2: cells over x, y)
   float4* sorted = nullptr;
   int32_t* cell_start = nullptr;
   int32_t* order = nullptr;  // original index per sorted position
@@ -123,14 +124,31 @@ struct AuxScope {
   }
 };
 
+// Multi-projection index (workpieces that are not height fields: closed shapes, vertical walls).  A column
+// grid over two axes piles a surface that runs along the third axis into a few cells; with one grid per axis
+// pair every point has at least one projection in which its neighbourhood is spread out (any surface normal
+// has a component >= 0.577 along some axis, so the foreshortening is <= 1.73).  choice[i] = the projection
+// whose candidate block around point i holds the fewest points (while holding enough).  Results do not
+// depend on the choice -- every grid gives the exact answer -- only the amount of scanning does.
+struct MPSet {
+  double h = 0;
+  int R0 = 0;
+  GridStore* g[3] = {nullptr, nullptr, nullptr};   // g[p]: the grid that drops axis p
+  unsigned char* choice = nullptr;                 // per ORIGINAL index: 0..2
+  cudaEvent_t ready = nullptr;                     // recorded once all three grids and the choice are built
+};
+
 struct ppp_cloud {
   ppp_ctx* ctx = nullptr;
   int64_t n = 0;
   int64_t n_finite = 0;
   float4* xyz4 = nullptr;  // original order, w = 0 (finite) / NaN (non-finite point)
   float bmin[3] = {0, 0, 0}, bmax[3] = {0, 0, 0};
-  double density = 0;  // finite points per unit area of the (u, v) bounding rectangle
+  double density = 0;  // finite points per unit area of the SURFACE around a typical point (sampled, see cloud_ingest)
   int au = 0, av = 1;
+  int drop = 2;        // primary projection: the axis of smallest extent is not gridded
+  int mp_state = -1;   // -1 not decided yet, 0 the primary column grid is enough, 1 multi-projection index
+  std::vector<MPSet> mps;
   float cell_hint = 0;
   std::vector<GridStore> grids;
   // results of the last ppp_dev_slice_contours (owned by the cloud)
@@ -238,21 +256,30 @@ int scan_exclusive_i32_to_i64(ppp_ctx* ctx, const int32_t* in, int64_t* out, int
 
 // grid.cu
 int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes);
-int cloud_get_grid(ppp_cloud* c, double h, GridStore** out);
+int cloud_get_grid(ppp_cloud* c, double h, GridStore** out);               // primary projection
+int cloud_get_grid_drop(ppp_cloud* c, double h, int drop, GridStore** out);
+// Decides (once per cloud, one synchronisation) whether the primary column grid `g` piles points up; afterwards
+// c->mp_state is 0 or 1.
+int cloud_decide_projection(ppp_cloud* c, const GridStore& g);
+// The three grids of cell size h and the per-point choice for candidate blocks of (2*R0+1)^2 cells.
+int cloud_get_mp(ppp_cloud* c, double h, int R0, MPSet** out);
 double cloud_cell_for_k(const ppp_cloud* c, int k);
 int knn_block_rings();
 double cloud_cell_for_radius(const ppp_cloud* c, double r);
 
 // knn.cu
+// choice / my_proj (multi-projection index): only the self-queries whose point chose projection my_proj are
+// answered by this call (through the grid `g`, which must be that projection's); the caller loops over the three.
 int knn_launch(ppp_cloud* c, const GridStore& g, const float* q_dev, int64_t nq, int q_stride_f, int64_t first,
                int k, int32_t* idx_dev, float* d2_dev, bool with_normals, const float vp[3], unsigned flags,
-               float* normals_dev, int normal_stride_f);
+               float* normals_dev, int normal_stride_f, const unsigned char* choice = nullptr, int my_proj = 0);
 int radius_count_launch(ppp_cloud* c, const GridStore& g, const float* q_dev, int64_t nq, int q_stride_f,
                         int64_t first, float r2, int32_t* counts_dev);
 int radius_fill_launch(ppp_cloud* c, const GridStore& g, const float* q_dev, int64_t nq, int q_stride_f,
                        int64_t first, float r2, const int64_t* offsets_dev, int32_t* idx_dev, float* d2_dev);
 int normals_radius_launch(ppp_cloud* c, const GridStore& g, int64_t first, int64_t count, float r2,
-                          const float vp[3], unsigned flags, float* normals_dev, int normal_stride_f);
+                          const float vp[3], unsigned flags, float* normals_dev, int normal_stride_f,
+                          const unsigned char* choice = nullptr, int my_proj = 0);
 
 int principal_curvatures_launch(ppp_cloud* c, const int32_t* idx_dev, int64_t nq, int k, const float* normals_dev,
                                 int normal_stride_f, float* out_dev, int32_t* nn0_dev);
@@ -267,8 +294,8 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
                  std::vector<int64_t>* offsets_host_out);
 int contours_launch(ppp_cloud* c, const GridStore& g, const float* planes_dev, int S, const int64_t* band_off_dev,
                     const int32_t* band_idx_dev, int64_t band_total, const std::vector<int64_t>& band_off_host, int mode,
-                    int64_t* total_nodes_out, const uint32_t* member_bits = nullptr);
+                    int64_t* total_nodes_out, const uint32_t* member_bits = nullptr, const MPSet* mp = nullptr);
 int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* plane_x_host, int S, float half_width,
-                              int truncate_center, int64_t* total_nodes_out, int64_t* total_members_out);
+                              int truncate_center, int64_t* total_nodes_out, int64_t* total_members_out, const MPSet* mp = nullptr);
 int contours_from_indices_launch(ppp_cloud* c, const GridStore& gs, const int32_t* idx_host, int64_t m, float plane_x,
-                                 int mode, int64_t* total_nodes_out);
+                                 int mode, int64_t* total_nodes_out, const MPSet* mp = nullptr);

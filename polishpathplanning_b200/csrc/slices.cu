@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(1024) k_band_sort(const int64_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 struct ContourParams {
   GridView g;
+  GridView g3[3];                // multi-projection index: g3[choice[point]] is searched for that point
+  const unsigned char* choice;   // nullptr: the single grid g
   const float4* xyz4;
   const float* planes;   // S, original order
   const float* lo;       // S, original order
@@ -174,6 +176,12 @@ struct ContourParams {
   int32_t* n_nodes;      // S
   const uint32_t* member; // optional membership bitmap (explicit index lists)
 };
+
+// The grid in which the neighbourhood of point `idx` is searched.
+template <typename PARAMS>
+__device__ __forceinline__ const GridView& grid_for(const PARAMS& P, int idx) {
+  return P.choice ? P.g3[__ldg(P.choice + idx)] : P.g;
+}
 
 __device__ __forceinline__ uint32_t f2ord_dev(float f) {
   uint32_t b = __float_as_uint(f);
@@ -213,7 +221,10 @@ __device__ int2 nn_side(const GridView& g, const float4* __restrict__ xyz4, floa
                         float hi, float plane, bool want_left, int metric, const int32_t* list, int nlist,
                         const uint32_t* __restrict__ member, int by_pos) {
   if (nlist <= 0) return make_int2(-1, -1);
-  const int RMAX = 6;
+  // Ring by ring while that is cheaper than walking the band's member list (~2.5 points per cell against
+  // nlist entries); a band along the silhouette of a closed shape has tens of thousands of members whose
+  // nearest member on the other side can be centimetres away.
+  const int RMAX = max(6, min(64, (int)(0.5f * sqrtf(0.4f * (float)nlist))));
   u64 best = PPP_KEY_INF;
   int best_pos = -1;
   // membership of the slice: the x-interval of the band, or (explicit index lists) a bitmap
@@ -372,13 +383,13 @@ __global__ void __launch_bounds__(1024) k_contour(ContourParams P, int smem_cap)
     // nearest right of every left, nearest left of every right (flag-independent) ...
     for (int i = threadIdx.x; i < nL; i += (int)blockDim.x) {
       float4 pl = __ldg(P.xyz4 + El[i]);
-      int r = nn_side<MEMBER>(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 1, Er, nR, P.member, 0).x;
+      int r = nn_side<MEMBER>(grid_for(P, El[i]), P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 1, Er, nR, P.member, 0).x;
       posR[i] = lower_pos(Er, nR, r);
       fl[i] = 0;
     }
     for (int j = threadIdx.x; j < nR; j += (int)blockDim.x) {
       float4 pr = __ldg(P.xyz4 + Er[j]);
-      int l = nn_side<MEMBER>(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 1, El, nL, P.member, 0).x;
+      int l = nn_side<MEMBER>(grid_for(P, Er[j]), P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 1, El, nL, P.member, 0).x;
       posL[j] = lower_pos(El, nL, l);
       fr[j] = 0;
     }
@@ -447,6 +458,8 @@ __global__ void __launch_bounds__(1024) k_contour(ContourParams P, int smem_cap)
 // index of the left query decides between equal-y nodes (k_slice_order).
 struct PairParams {
   GridView g;
+  GridView g3[3];                // multi-projection index: g3[choice[point]] is searched for that point
+  const unsigned char* choice;   // nullptr: the single grid g
   const float4* xyz4;
   const float* planes;
   const float* lo;
@@ -521,18 +534,20 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
     const int32_t* band = P.band_idx + bo;
     const int B = (int)(__ldg(P.band_off + s + 1) - bo);
     float4 pl;
-    member_handle(P, m, &pl);
+    const int2 hq = member_handle(P, m, &pl);
+    const GridView& gq = grid_for(P, hq.x);     // the left point's neighbourhood grid
     u64 key = PPP_KEY_INF;
     float y = 0.f, z = 0.f;
-    const int2 ri = nn_side<MEMBER>(P.g, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, band, B, P.member, P.by_pos);
+    const int2 ri = nn_side<MEMBER>(gq, P.xyz4, pl.x, pl.y, pl.z, lo, hi, plane, false, 0, band, B, P.member, P.by_pos);
     if (ri.x >= 0) {
-      const float4 pr = rec_of(P.g, P.xyz4, ri);
-      const int2 rc = nn_full(P.g, pr.x, pr.y, pr.z, ri);
-      const int2 li = nn_side<MEMBER>(P.g, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, band, B, P.member, P.by_pos);
-      const float4 pl2 = rec_of(P.g, P.xyz4, li);
-      const int2 lc = nn_full(P.g, pl2.x, pl2.y, pl2.z, li);
-      const float4 a = rec_of(P.g, P.xyz4, rc);  // index_right
-      const float4 b = rec_of(P.g, P.xyz4, lc);  // index_left
+      const float4 pr = rec_of(gq, P.xyz4, ri);
+      const int2 rc = nn_full(gq, pr.x, pr.y, pr.z, ri);
+      const GridView& gr = grid_for(P, ri.x);   // ... and the right point's
+      const int2 li = nn_side<MEMBER>(gr, P.xyz4, pr.x, pr.y, pr.z, lo, hi, plane, true, 0, band, B, P.member, P.by_pos);
+      const float4 pl2 = rec_of(gr, P.xyz4, li);
+      const int2 lc = nn_full(gr, pl2.x, pl2.y, pl2.z, li);
+      const float4 a = rec_of(gq, P.xyz4, rc);  // index_right
+      const float4 b = rec_of(gr, P.xyz4, lc);  // index_left
       float t = __fdiv_rn(__fsub_rn(plane, a.x), __fsub_rn(b.x, a.x));
       y = __fadd_rn(a.y, __fmul_rn(t, __fsub_rn(b.y, a.y)));
       z = __fadd_rn(a.z, __fmul_rn(t, __fsub_rn(b.z, a.z)));
@@ -843,9 +858,16 @@ static int finish_nodes(ppp_cloud* c, int S, const int64_t* band_off_dev, const 
 }
 
 // band_off_host: S+1 offsets (for sizing shared memory).  Variant A needs index-sorted bands.
+template <typename PARAMS>
+static void set_grids(PARAMS& P, const GridStore& gs, const MPSet* mp) {
+  P.g = gs.v;
+  P.choice = mp ? mp->choice : nullptr;
+  for (int p = 0; p < 3; p++) P.g3[p] = mp ? mp->g[p]->v : gs.v;
+}
+
 int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, int S, const int64_t* band_off_dev,
                     const int32_t* band_idx_dev, int64_t band_total, const std::vector<int64_t>& band_off_host, int mode,
-                    int64_t* total_nodes_out, const uint32_t* member_bits) {
+                    int64_t* total_nodes_out, const uint32_t* member_bits, const MPSet* mp) {
   ppp_ctx* ctx = c->ctx;
   *total_nodes_out = 0;
   size_t M = (size_t)std::max<int64_t>(band_total, 1);
@@ -856,7 +878,7 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
   int st = PPP_OK;
   if (mode == PPP_PAIR_SECT) {
     PairParams P{};
-    P.g = gs.v; P.xyz4 = c->xyz4;
+    set_grids(P, gs, mp); P.xyz4 = c->xyz4;
     P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
     P.band_off = band_off_dev; P.band_idx = band_idx_dev; P.S = S; P.M = band_total;
     P.member = member_bits; P.by_pos = 0;
@@ -883,7 +905,7 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     dev_free(ctx, P.keys); dev_free(ctx, P.ys); dev_free(ctx, P.zs); dev_free(ctx, scratch);
   } else {
     ContourParams P{};
-    P.g = gs.v; P.xyz4 = c->xyz4;
+    set_grids(P, gs, mp); P.xyz4 = c->xyz4;
     P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
     P.band_off = band_off_dev; P.band_idx = band_idx_dev; P.mode = mode;
     P.ty = ty; P.tz = tz; P.n_nodes = n_nodes;
@@ -917,7 +939,7 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
 // returns it): one slice whose members are exactly `indices`; membership tests use a bitmap
 // instead of the band's x-interval.
 int contours_from_indices_launch(ppp_cloud* c, const GridStore& gs, const int32_t* idx_host, int64_t m, float plane_x,
-                                 int mode, int64_t* total_nodes_out) {
+                                 int mode, int64_t* total_nodes_out, const MPSet* mp) {
   ppp_ctx* ctx = c->ctx;
   *total_nodes_out = 0;
   float stage[3] = {plane_x, -INFINITY, INFINITY};
@@ -936,7 +958,7 @@ int contours_from_indices_launch(ppp_cloud* c, const GridStore& gs, const int32_
     PPP_CHECK_LAUNCH();
   }
   std::vector<int64_t> offv = {0, m};
-  int st = contours_launch(c, gs, planes, 1, boff, bidx, m, offv, mode, total_nodes_out, bits);
+  int st = contours_launch(c, gs, planes, 1, boff, bidx, m, offv, mode, total_nodes_out, bits, mp);
   dev_free(ctx, planes); dev_free(ctx, boff); dev_free(ctx, bidx); dev_free(ctx, bits);
   return st;
 }
@@ -952,14 +974,16 @@ int contours_from_indices_launch(ppp_cloud* c, const GridStore& gs, const int32_
 // Returns PPP_ERR_UNSUPPORTED (nothing launched) when the bound is too large to allocate blindly.
 // ---------------------------------------------------------------------------------------------
 int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* plane_x_host, int S, float half_width,
-                              int truncate_center, int64_t* total_nodes_out, int64_t* total_members_out) {
+                              int truncate_center, int64_t* total_nodes_out, int64_t* total_members_out, const MPSet* mp) {
   ppp_ctx* ctx = c->ctx;
   if (S <= 0 || c->n <= 0) return PPP_ERR_UNSUPPORTED;
   // Bands are drawn from the grid's cell-major array and hold SORTED POSITIONS: consecutive members of a band
   // are neighbours in space, so the pairing searches of a warp walk the same cells (L1 / L2 reuse instead of a
   // DRAM gather per member), and every record they need is one contiguous-ish load from the sorted array.
   BandPrep bp;
-  PPP_TRY(bands_prepare(c, plane_x_host, S, half_width, truncate_center, &bp, &gs));
+  // (With the multi-projection index a position means something different in every grid: lists of original
+  // indices are used there.)
+  PPP_TRY(bands_prepare(c, plane_x_host, S, half_width, truncate_center, &bp, mp ? nullptr : &gs));
   const int64_t Mb = (int64_t)std::max(bp.max_depth, 1) * c->n;   // >= band members
   int st = PPP_OK;
   int32_t* idx = nullptr; double *ty = nullptr, *tz = nullptr; int32_t* n_nodes = nullptr;
@@ -985,10 +1009,10 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
     PPP_CUDA(cudaMemsetAsync(summary, 0, 4 * sizeof(int64_t), ctx->stream));
     const float* planes_dev = bp.fdev;
     PairParams P{};
-    P.g = gs.v; P.xyz4 = c->xyz4;
+    set_grids(P, gs, mp); P.xyz4 = c->xyz4;
     P.planes = planes_dev; P.lo = planes_dev + S; P.hi = planes_dev + 2 * (size_t)S;
     P.band_off = bp.offsets; P.band_idx = idx; P.S = S; P.M = Mb;
-    P.member = nullptr; P.keys = keys; P.ys = ys; P.zs = zs; P.by_pos = 1;
+    P.member = nullptr; P.keys = keys; P.ys = ys; P.zs = zs; P.by_pos = mp ? 0 : 1;
     const int64_t per_block = (int64_t)PAIR_WARPS * PAIR_CHUNK;
     PPP_LAUNCH(ctx, "pair_nodes", k_pair_nodes<false>, (unsigned)((Mb + per_block - 1) / per_block), PAIR_WARPS * 32, 0, P);
     PPP_CHECK_LAUNCH();
@@ -999,7 +1023,7 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
     if ((size_t)smem_cap * 8 > 48 * 1024)
       PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
     PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, SO_THREADS, (size_t)smem_cap * 8, (const int64_t*)bp.offsets,
-               (const int32_t*)idx, gs.v.sorted, (const u64*)keys, (const float*)ys, (const float*)zs, scratch, smem_cap, ty, tz, n_nodes);
+               (const int32_t*)idx, mp ? (const float4*)nullptr : gs.v.sorted, (const u64*)keys, (const float*)ys, (const float*)zs, scratch, smem_cap, ty, tz, n_nodes);
     PPP_CHECK_LAUNCH();
     if (c->c_S_cap < S + 1) {
       dev_free(ctx, c->c_node_off);

@@ -322,6 +322,8 @@ class SharedHost:
         if self.rank == 0:
             p = "/dev/shm/ppp_%s_%d" % (tag, os.getpid())
             try:
+                if os.environ.get("PPP_SHM_MEMFD"):               # test aid: take the memfd route
+                    raise OSError("memfd requested")
                 fd = os.open(p, os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
                 try:
                     os.posix_fallocate(fd, 0, self.nbytes)          # fails now (not at first touch) if tmpfs is too small

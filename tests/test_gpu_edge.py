@@ -210,6 +210,26 @@ def test_error_codes(ctx):
     gc.close()
 
 
+def test_radius_lists_beyond_the_shared_memory_limit_fail_loudly(ctx):
+    """The documented limit of the radius paths (include/ppp_gpu.h): a query with more than ~900 neighbours cannot be
+    ordered in shared memory; the call says so (PPP_ERR_UNSUPPORTED) instead of truncating.  Counting still works."""
+    rng = np.random.default_rng(3)
+    pts = synth.to_pointxyzrgb((rng.random((6000, 3)) * 4.0).astype(np.float32))     # 6000 points within a 4 mm cube
+    gc = api.Cloud(ctx, pts)
+    cnt = np.empty(6000, np.int32)
+    api.check(gc.lib.ppp_radius(gc._h, None, 0, 0, 2.5, cnt.ctypes.data_as(api._vp), None, None, None))
+    assert cnt.max() > 1500
+    with pytest.raises(api.PPPError) as e:
+        gc.radius(2.5)
+    assert e.value.status == api._lib.PPP_ERR_UNSUPPORTED and "shared-memory" in str(e.value)
+    with pytest.raises(api.PPPError) as e:
+        gc.normals_radius(2.5)
+    assert e.value.status == api._lib.PPP_ERR_UNSUPPORTED
+    nk = gc.normals_knn(16)                     # the k-nearest path has no such limit
+    assert np.isfinite(nk[:, 0]).all()
+    gc.close()
+
+
 def test_reference_interface_mirror(ctx, tmp_path):
     """./main-shaped flow: PCD in metres -> ctor scaling -> estimate_normal -> plane sweep."""
     metres = synth.to_pointxyzrgb(synth.panel_metres(30000, 21))

@@ -200,9 +200,14 @@ def _sharded_host_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_gloo_sharded_flow_delivers_one_host_result(tmp_path):
+@pytest.mark.parametrize("memfd", [False, True])
+def test_gloo_sharded_flow_delivers_one_host_result(tmp_path, memfd, monkeypatch):
+    """memfd = True: the backing object is an anonymous memfd reached through /proc/<pid>/fd (what SharedHost
+    falls back to when /dev/shm is too small for the cloud)."""
     import torch.multiprocessing as mp
-    port = 31500 + (os.getpid() % 2000)
+    if memfd:
+        monkeypatch.setenv("PPP_SHM_MEMFD", "1")
+    port = 31500 + (os.getpid() % 2000) + (7 if memfd else 0)
     mp.spawn(_sharded_host_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     got = np.load(str(tmp_path / "one_host.npz"))
     cloud = synth.panel(24000, 5)

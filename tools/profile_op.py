@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-kernel CUDA-event times of one operation (kernels serialised).  python tools/profile_op.py radius|knn16|knn32|contoursA"""
+"""Per-kernel CUDA-event times of one operation (kernels serialised).  python tools/profile_op.py radius|knn16|knn32|contoursA|contoursB [points] [slices]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -10,7 +10,8 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 ctx = api.Context(0); dev = torch.device("cuda", 0)
 cloud = synth.panel(n, 0); raw = torch.from_numpy(cloud).to(dev)
 nrm = torch.empty((n, 8), dtype=torch.float32, device=dev); idx = torch.empty((n, 64), dtype=torch.int32, device=dev)
-planes = synth.even_planes(cloud, 200)
+S = int(sys.argv[3]) if len(sys.argv) > 3 else 200
+planes = synth.even_planes(cloud, S)
 def step():
     c = api.Cloud(ctx, device_ptr=raw.data_ptr(), n=n, stride_bytes=32)
     if op == "radius": c.dev_normals_radius(2.5, nrm.data_ptr(), 32)
