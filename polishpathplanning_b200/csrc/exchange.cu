@@ -5,11 +5,11 @@
 //
 //   phase 0  k_ex_minmax    x-range + finite count of the local chunk  -> every peer's slot
 //   phase 1  k_ex_hist      1024-bin x histogram over the GLOBAL range -> every peer's slot
-//   phase 2  k_ex_cuts      equal-count cuts from the summed histograms (identical on every rank)
-//            k_ex_count     destinations of every record (owner slab + halo copies), per-tile counts
-//            k_ex_tilescan  per-destination exclusive scan over the tiles; send counts -> every peer
+//   phase 2  k_ex_count     equal-count cuts from the summed histograms (identical on every rank, derived by
+//                           every block), destinations of every record (owner slab + halo copies), per-tile
+//                           counts; send counts -> every peer
 //   phase 3  k_ex_scatter   records -> the destination's receive buffer at
-//                           (sum of the counts of lower ranks) + (tile offset) + (rank inside the tile),
+//                           (sum of the counts of lower ranks) + (counts of the rank's earlier tiles) + (rank inside the tile),
 //                           i.e. in ascending GLOBAL INDEX order, so every (d2, index) tie-break and the
 //                           El / Er insertion order are those of the single-GPU run
 //   phase 4  results        normals go straight from the search kernels to their HOME rank (the rank
@@ -285,35 +285,43 @@ __global__ void __launch_bounds__(1024) k_ex_hist(ExView V, const float* __restr
   ex_publish(V, 1, step);
 }
 
-// ---- phase 2a: equal-count cuts (one block) -------------------------------------------------------
-// cut r = upper edge of the first bin at which the cumulative count reaches total * r / world
-// (integer arithmetic, so every rank computes the same bins from the same histograms).
-__global__ void __launch_bounds__(1024) k_ex_cuts(ExView V, ExScratch* sc) {
-  __shared__ long long s_cum[EX_BINS];
-  __shared__ long long s_part[1024];
+// ---- phase 2: equal-count cuts + destination counts -------------------------------------------------
+// The slab limits every rank derives, identically, from the summed histograms.
+struct ExCuts {
+  int32_t cutbin[PPP_MAX_RANKS + 1];
+  double cutx[PPP_MAX_RANKS + 1];
+  double gmin, gmax, inv;
+};
+
+// cut r = upper edge of the first bin at which the cumulative count reaches total * r / world (integer
+// arithmetic, so every rank -- and every block -- computes the same bins from the same histograms).
+// Block-wide; EX_BINS / blockDim.x bins per thread.  C lives in shared memory.
+__device__ void ex_compute_cuts(const ExView& V, uint32_t step, ExCuts* C, long long* s_cum /* EX_BINS */, long long* s_part /* blockDim.x */) {
   const int32_t* H = reinterpret_cast<const int32_t*>(V.arena[V.rank] + V.off_hist);
-  constexpr int PER = EX_BINS / 1024;
-  long long v[PER];
+  const int per = EX_BINS / (int)blockDim.x;
   long long sum = 0;
-#pragma unroll
-  for (int j = 0; j < PER; j++) {
+  for (int j = 0; j < per; j++) {
     long long t = 0;
-    for (int r = 0; r < V.world; r++) t += *(volatile const int32_t*)(H + (size_t)r * EX_BINS + threadIdx.x * PER + j);
-    v[j] = t;
+    for (int r = 0; r < V.world; r++) t += *(volatile const int32_t*)(H + (size_t)r * EX_BINS + threadIdx.x * per + j);
+    s_cum[threadIdx.x * per + j] = t;
     sum += t;
   }
   s_part[threadIdx.x] = sum;
   __syncthreads();
-  // inclusive scan of the 1024 partial sums (Hillis-Steele)
-  for (int o = 1; o < 1024; o <<= 1) {
+  for (int o = 1; o < (int)blockDim.x; o <<= 1) {     // inclusive scan of the per-thread sums (Hillis-Steele)
     long long t = (int)threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
     __syncthreads();
     s_part[threadIdx.x] += t;
     __syncthreads();
   }
   long long run = s_part[threadIdx.x] - sum;
-#pragma unroll
-  for (int j = 0; j < PER; j++) { run += v[j]; s_cum[threadIdx.x * PER + j] = run; }
+  for (int j = 0; j < per; j++) { run += s_cum[threadIdx.x * per + j]; s_cum[threadIdx.x * per + j] = run; }
+  if (threadIdx.x == 0) {
+    double gmin, gmax;
+    ex_global_range(V, step, gmin, gmax);
+    C->gmin = gmin; C->gmax = gmax;
+    C->inv = (double)EX_BINS / fmax(gmax - gmin, 1e-9);
+  }
   __syncthreads();
   const long long total = s_cum[EX_BINS - 1];
   if ((int)threadIdx.x <= V.world) {
@@ -327,17 +335,19 @@ __global__ void __launch_bounds__(1024) k_ex_cuts(ExView V, ExScratch* sc) {
       while (lo < hi) { int m = (lo + hi) >> 1; if (s_cum[m] * V.world >= total * r) hi = m; else lo = m + 1; }
       cb = lo + 1;
     }
-    sc->cutbin[r] = cb;
-    const double span = fmax(sc->gmax - sc->gmin, 1e-9);
-    sc->cutx[r] = r == 0 ? -CUDART_INF : (r == V.world ? CUDART_INF : sc->gmin + span * (double)cb / (double)EX_BINS);
+    C->cutbin[r] = cb;
+    const double span = fmax(C->gmax - C->gmin, 1e-9);
+    C->cutx[r] = r == 0 ? -CUDART_INF : (r == V.world ? CUDART_INF : C->gmin + span * (double)cb / (double)EX_BINS);
   }
+  __syncthreads();
 }
 
 // Destination mask of one record: bit d set = rank d receives it; *owner = the slab that owns it.
 // Owner by BIN (consistent with the cuts by construction); halo copies by comparing x with the cut
 // positions.  Non-finite points belong to rank 0 (they keep their place in the index numbering and
 // get a NaN normal there, as in PCL) and are never anybody's halo.
-__device__ __forceinline__ unsigned ex_dest_mask(const ExScratch* sc, int world, float x, float y, float z, double halo, int* owner) {
+template <typename CUTS>
+__device__ __forceinline__ unsigned ex_dest_mask(const CUTS* sc, int world, float x, float y, float z, double halo, int* owner) {
   if (!finite3(x, y, z)) { *owner = 0; return 1u; }
   const int b = ex_bin(x, sc->gmin, sc->inv);
   int o = 0;
@@ -350,12 +360,22 @@ __device__ __forceinline__ unsigned ex_dest_mask(const ExScratch* sc, int world,
   return m;
 }
 
-// ---- phase 2b: per-tile destination counts --------------------------------------------------------
-__global__ void __launch_bounds__(EX_THREADS) k_ex_count(int world, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
-                                                         double halo, ExScratch* sc, int32_t* __restrict__ tilecnt, int ntiles) {
+// Every block derives the cuts itself (a thousand bins: cheaper than one more launch between two waits), counts
+// the destinations of its tile, and the last block publishes this rank's send counts to every peer.
+__global__ void __launch_bounds__(EX_THREADS) k_ex_count(ExView V, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
+                                                         double halo, uint32_t step, ExScratch* sc, int32_t* __restrict__ tilecnt,
+                                                         int ntiles) {
+  __shared__ long long s_cum[EX_BINS];
+  __shared__ long long s_part[EX_THREADS];
+  __shared__ ExCuts C;
   __shared__ int s_cnt[PPP_MAX_RANKS], s_own[PPP_MAX_RANKS];
   if (threadIdx.x < PPP_MAX_RANKS) { s_cnt[threadIdx.x] = 0; s_own[threadIdx.x] = 0; }
-  __syncthreads();
+  ex_compute_cuts(V, step, &C, s_cum, s_part);
+  const int world = V.world;
+  if (blockIdx.x == 0) {      // for the scatter kernel and the host's summary
+    if ((int)threadIdx.x <= world) { sc->cutbin[threadIdx.x] = C.cutbin[threadIdx.x]; sc->cutx[threadIdx.x] = C.cutx[threadIdx.x]; }
+    if (threadIdx.x == 0) { sc->gmin = C.gmin; sc->gmax = C.gmax; sc->inv = C.inv; }
+  }
   const int64_t base = (int64_t)blockIdx.x * EX_TILE;
   for (int it = 0; it < EX_TILE / EX_THREADS; it++) {
     const int64_t i = base + (int64_t)it * EX_THREADS + threadIdx.x;
@@ -363,7 +383,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_ex_count(int world, const float*
       float x, y, z;
       ex_load_xyz(raw, i, sf, vec_ok, x, y, z);
       int owner;
-      unsigned m = ex_dest_mask(sc, world, x, y, z, halo, &owner);
+      unsigned m = ex_dest_mask(&C, world, x, y, z, halo, &owner);
       atomicAdd(&s_own[owner], 1);
       while (m) { int d = __ffs(m) - 1; m &= m - 1; atomicAdd(&s_cnt[d], 1); }
     }
@@ -371,40 +391,19 @@ __global__ void __launch_bounds__(EX_THREADS) k_ex_count(int world, const float*
   __syncthreads();
   if ((int)threadIdx.x < world) {
     tilecnt[(size_t)threadIdx.x * ntiles + blockIdx.x] = s_cnt[threadIdx.x];
+    if (s_cnt[threadIdx.x]) atomicAdd(&sc->sendcnt[threadIdx.x], s_cnt[threadIdx.x]);
     if (s_own[threadIdx.x]) atomicAdd(&sc->sendown[threadIdx.x], s_own[threadIdx.x]);
   }
-}
-
-// ---- phase 2c: exclusive scan over the tiles, one block per destination; publish the send counts ----
-__global__ void __launch_bounds__(1024) k_ex_tilescan(ExView V, int32_t* __restrict__ tilecnt, int ntiles, uint32_t step, ExScratch* sc) {
-  __shared__ int s_part[1024];
-  const int d = blockIdx.x;
-  int32_t* a = tilecnt + (size_t)d * ntiles;
-  const int per = (ntiles + 1023) / 1024;
-  const int lo = min(threadIdx.x * per, ntiles), hi = min(lo + per, ntiles);
-  int sum = 0;
-  for (int i = lo; i < hi; i++) sum += a[i];
-  s_part[threadIdx.x] = sum;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    int t = (int)threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
-    __syncthreads();
-    s_part[threadIdx.x] += t;
-    __syncthreads();
-  }
-  int run = s_part[threadIdx.x] - sum;
-  for (int i = lo; i < hi; i++) { int c = a[i]; a[i] = run; run += c; }
-  if (threadIdx.x == 1023) sc->sendcnt[d] = s_part[1023];
   if (!ex_last_block(&sc->ticket[2])) return;
   // last block: this rank's row of the count tables (records, owned) into every arena
-  if ((int)threadIdx.x < V.world * V.world) {
-    const int peer = threadIdx.x / V.world, dst = threadIdx.x % V.world;
+  if ((int)threadIdx.x < world * world) {
+    const int peer = threadIdx.x / world, dst = threadIdx.x % world;
     int32_t* tab = reinterpret_cast<int32_t*>(V.arena[peer] + V.off_cnt);
     tab[V.rank * PPP_MAX_RANKS + dst] = *(volatile int32_t*)&sc->sendcnt[dst];
     tab[PPP_MAX_RANKS * PPP_MAX_RANKS + V.rank * PPP_MAX_RANKS + dst] = *(volatile int32_t*)&sc->sendown[dst];
   }
   __syncthreads();
-  if (threadIdx.x < PPP_MAX_RANKS) sc->sendown[threadIdx.x] = 0;
+  if (threadIdx.x < PPP_MAX_RANKS) { sc->sendown[threadIdx.x] = 0; sc->sendcnt[threadIdx.x] = 0; }
   ex_publish(V, 2, step);
 }
 
@@ -419,17 +418,27 @@ constexpr int EX_WARPS = EX_THREADS / 32;
 
 __global__ void __launch_bounds__(EX_THREADS) k_ex_scatter(ExView V, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
                                                            int64_t global_start, double halo, uint32_t step, ExScratch* sc,
-                                                           const int32_t* __restrict__ tileoff, int ntiles) {
+                                                           const int32_t* __restrict__ tilecnt, int ntiles) {
   __shared__ int s_off[EX_ITERS * EX_WARPS][PPP_MAX_RANKS];
   __shared__ long long s_base[PPP_MAX_RANKS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int world = V.world;
+  // where this tile's records start in every destination: the counts of the lower ranks (count table) plus the
+  // counts of this rank's earlier tiles (summed here: at most a few thousand values, no scan kernel in between)
   if ((int)threadIdx.x < world) {
     const int d = threadIdx.x;
     const int32_t* tab = reinterpret_cast<const int32_t*>(V.arena[V.rank] + V.off_cnt);
     long long b = 0;
     for (int s = 0; s < V.rank; s++) b += *(volatile const int32_t*)(tab + s * PPP_MAX_RANKS + d);
-    s_base[d] = b + tileoff[(size_t)d * ntiles + blockIdx.x];
+    s_base[d] = b;
+  }
+  __syncthreads();
+  for (int d = 0; d < world; d++) {
+    int part = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += EX_THREADS) part += __ldg(tilecnt + (size_t)d * ntiles + t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0 && part) atomicAdd((unsigned long long*)&s_base[d], (unsigned long long)part);
   }
   const int64_t base = (int64_t)blockIdx.x * EX_TILE;
   float x[EX_ITERS], y[EX_ITERS], z[EX_ITERS];
@@ -733,9 +742,7 @@ int ppp_exch_phase(ppp_exch* ex, int phase, const void* chunk_dev, int64_t n, si
       ex->tilecnt_cap = (int64_t)ntiles * ex->world;
     }
     PPP_LAUNCH(ctx, "ex_wait", k_ex_wait, 1, 32, 0, ex->V, 1, ex->step, -1, ex->sc);
-    PPP_LAUNCH(ctx, "ex_cuts", k_ex_cuts, 1, 1024, 0, ex->V, ex->sc);
-    PPP_LAUNCH(ctx, "ex_count", k_ex_count, ntiles, EX_THREADS, 0, ex->world, raw, n, sf, vec_ok, halo, ex->sc, ex->tilecnt, ntiles);
-    PPP_LAUNCH(ctx, "ex_tilescan", k_ex_tilescan, ex->world, 1024, 0, ex->V, ex->tilecnt, ntiles, ex->step, ex->sc);
+    PPP_LAUNCH(ctx, "ex_count", k_ex_count, ntiles, EX_THREADS, 0, ex->V, raw, n, sf, vec_ok, halo, ex->step, ex->sc, ex->tilecnt, ntiles);
     PPP_CHECK_LAUNCH();
   } else {
     PPP_LAUNCH(ctx, "ex_wait", k_ex_wait, 1, 32, 0, ex->V, 2, ex->step, -1, ex->sc);

@@ -441,12 +441,10 @@ constexpr int C_SLOTS = 32;   // keys ordered per network pass
 constexpr int C_STORE = 36;   // storage slots: U spare ones, so a pass is only forced beyond 32 occupied
 
 template <int BD>
-__global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_knn16c(SearchParams P) {
+__device__ __forceinline__ void knn16c_body(const SearchParams& P, const int64_t t, bool valid) {
   extern __shared__ u64 s_keys[];
   constexpr int K = 16;
-  const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
   const GridView& g = P.g;
-  bool valid = t < P.nq;
   float qx = 0.f, qy = 0.f, qz = 0.f;
   int64_t row = 0;
   if (valid) {
@@ -555,8 +553,7 @@ __global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_k
   bool complete = !act || kk == 0;
   if (!complete) complete = store[(kk - 1) * BD] != PPP_KEY_INF;
   if (!complete || ambiguous) {
-    int slot = atomicAdd(P.redo_count, 1);
-    P.redo_list[slot] = (int32_t)t;
+    P.redo_list[atomicAdd(P.redo_count, 1)] = (int32_t)t;
     return;
   }
   const int k = P.cap;
@@ -630,6 +627,12 @@ __global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_k
     else o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
     store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
   }
+}
+
+template <int BD>
+__global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_knn16c(SearchParams P) {
+  const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
+  knn16c_body<BD>(P, t, t < P.nq);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -965,8 +968,12 @@ __device__ __forceinline__ u64 warp_min_u64(u64 v) {
 
 constexpr int WARPQ_WARPS = 4;
 
+constexpr int WQ_SEG_MAX = 128;   // cell ranges of one ring handled in the flattened way (rings up to 31)
+
 __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
   extern __shared__ u64 s_keys[];
+  __shared__ int s_seg[WARPQ_WARPS][WQ_SEG_MAX];
+  __shared__ int s_pre[WARPQ_WARPS][WQ_SEG_MAX + 1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const GridView& g = P.g;
   const int k = P.cap, kk = P.kk;
@@ -996,8 +1003,61 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
   int R = max(P.R0, max(du, dv0));
   int R_prev = -1;
   while (true) {
-    // annulus R_prev < max(|du|,|dv|) <= R, lanes striding over each contiguous cell range
+    // annulus R_prev < max(|du|,|dv|) <= R.  Its cell ranges (one per row, two for the rows that only add the
+    // two outer column strips) are looked up by all lanes at once, then the lanes stride over the CONCATENATION
+    // of the ranges with four candidates in flight each: a query costs a couple of dependent memory latencies
+    // per ring instead of two per row (this kernel is latency-bound: a few hundred queries, one warp each).
     const int v0 = max(cv - R, 0), v1 = min(cv + R, g.nv - 1);
+    const int nseg = 2 * (v1 - v0 + 1);
+    if (nseg > 0 && nseg <= WQ_SEG_MAX) {
+      int* seg_s = s_seg[w];
+      int* seg_p = s_pre[w];
+      for (int sg0 = 0; sg0 < nseg; sg0 += 32) {
+        const int sg = sg0 + lane;
+        int s0 = 0, len = 0;
+        if (sg < nseg) {
+          const int v = v0 + (sg >> 1), part = sg & 1;
+          const bool full = abs(v - cv) > R_prev;
+          int a, b;
+          if (full) { a = max(cu - R, 0); b = part == 0 ? min(cu + R, g.nu - 1) : -1; }
+          else if (part == 0) { a = max(cu - R, 0); b = min(cu - R_prev - 1, g.nu - 1); }
+          else { a = max(cu + R_prev + 1, 0); b = min(cu + R, g.nu - 1); }
+          if (a <= b) {
+            const int32_t* rowp = g.cell_start + (int64_t)v * g.nu;
+            s0 = __ldg(rowp + a);
+            len = __ldg(rowp + b + 1) - s0;
+          }
+        }
+        // exclusive prefix of the lengths (warp scan, carried over the chunks of 32 segments)
+        int inc = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int tt = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += tt; }
+        const int carry = sg0 == 0 ? 0 : seg_p[sg0];
+        if (sg < nseg) { seg_s[sg] = s0; seg_p[sg + 1] = carry + inc; }
+        if (sg0 == 0 && lane == 0) seg_p[0] = 0;
+        __syncwarp();
+      }
+      const int T = seg_p[nseg];
+      for (int base = 0; base < T; base += 128) {
+        float4 c4[4];
+        bool in[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = base + u * 32 + lane;
+          in[u] = i < T;
+          int lo = 0, hi = nseg - 1;           // last segment whose prefix is <= i
+          while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (seg_p[mid] <= i) lo = mid; else hi = mid - 1; }
+          c4[u] = __ldg(g.sorted + (in[u] ? seg_s[lo] + (i - seg_p[lo]) : 0));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (!in[u]) continue;
+          u64 key = make_key(d2_flann(qx, qy, qz, c4[u].x, c4[u].y, c4[u].z), __float_as_int(c4[u].w));
+          // a full lane list only takes keys below its own last entry (list_insert overwrites it)
+          if (key < tau && (cnt < k || key < L[(k - 1) * 32])) list_insert(L, 32, cnt, k, key);
+        }
+      }
+    } else {
     for (int v = v0; v <= v1; v++) {
       const int32_t* rowp = g.cell_start + (int64_t)v * g.nu;
       const bool full = abs(v - cv) > R_prev;
@@ -1015,6 +1075,7 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
           if (key < tau && (cnt < k || key < L[(k - 1) * 32])) list_insert(L, 32, cnt, k, key);
         }
       }
+    }
     }
     __syncwarp();
     // k smallest of the 32 sorted lists
@@ -1411,7 +1472,10 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
   PPP_TRY(prepare_fast(c, P, &redo));
   int st;
   if (P.cap <= 16) {
-    // block size: 96 threads hold 27 warps per SM (24 KB of candidate store per block), 128 hold 24
+    // block size: 96 threads hold 27 warps per SM (24 KB of candidate store per block), 128 hold 24.
+    // (Tried and rejected on measurements: a second pass of this kernel with a 7 x 7 block over the ~0.2 % of
+    // queries the 5 x 5 block cannot finish, before the one-warp-per-query kernel: each extra launch costs the
+    // life time of one block, 30-50 us, whatever the number of queries -- 0.308 ms against 0.266 ms for the stage.)
     int block = 96;
     if (const char* e = getenv("PPP_KNN_BD")) { int v = atoi(e); if (v == 64 || v == 96 || v == 128) block = v; }
     size_t smem = (size_t)C_SLOTS * 8 * block;

@@ -96,13 +96,24 @@ def test_sharded_pipeline_equals_single_cloud(world, stride):
     n, k, halo, S = 120000, 16, 12.0, 24
     cloud = synth.panel(n, seed=23)
     cloud[1234, 1] = np.nan
-    planes = synth.even_planes(cloud, S)
     ctxs, exs, chunks, starts = _ranks(world, cloud, halo, S_cap=S, node_cap=60000, stride=stride)
     ref_ctx = api.Context(0)
-    full = api.Cloud(ref_ctx, cloud)
-    ref_n, ref_i = full.normals_knn(k, stride_floats=stride // 4, return_idx=True)
-    ro, ry, rx, rz = full.slice_contours(planes, "B")
+    full = None
     for step in range(2):
+        if step == 1:
+            # a DIFFERENT cloud through the same exchange objects: nothing of the previous step (flags, counts,
+            # receive buffers, home normals, contour regions) may leak into this one
+            cloud = synth.panel(n, seed=29)
+            cloud[77, 2] = np.inf
+            for r in range(world):
+                chunks[r].copy_(torch.from_numpy(np.ascontiguousarray(cloud[starts[r]:starts[r + 1]])))
+            torch.cuda.synchronize()
+        planes = synth.even_planes(cloud, S)
+        if full is not None:
+            full.close()
+        full = api.Cloud(ref_ctx, cloud)
+        ref_n, ref_i = full.normals_knn(k, stride_floats=stride // 4, return_idx=True)
+        ro, ry, rx, rz = full.slice_contours(planes, "B")
         infos = _run_exchange(exs, chunks, halo, 32)
         clouds, pos, idx = [], [], []
         for r in range(world):

@@ -1,0 +1,3 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_exchange.py -x -q 2>&1 | tail -8
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
