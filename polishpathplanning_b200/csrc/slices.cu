@@ -897,7 +897,9 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     if (S > 0) {
       if ((size_t)smem_cap * 8 > 48 * 1024)
         PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
-      PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, SO_THREADS, (size_t)smem_cap * 8, band_off_dev, band_idx_dev,
+      // short bands: 256 threads sort them with a quarter of the barrier traffic, and more slices share an SM
+      const int so_threads = maxB <= 4096 ? 256 : SO_THREADS;
+      PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, so_threads, (size_t)smem_cap * 8, band_off_dev, band_idx_dev,
                  (const float4*)nullptr, (const u64*)P.keys, (const float*)P.ys, (const float*)P.zs, scratch, smem_cap, ty, tz, n_nodes);
       PPP_CHECK_LAUNCH();
     }
@@ -1022,7 +1024,8 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
     int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(guess, 1024), 24576);  // <= 192 KB of u64
     if ((size_t)smem_cap * 8 > 48 * 1024)
       PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
-    PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, SO_THREADS, (size_t)smem_cap * 8, (const int64_t*)bp.offsets,
+    const int so_threads = smem_cap <= 4608 ? 256 : SO_THREADS;   // short bands (the guess covers the largest one seen so far)
+    PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, so_threads, (size_t)smem_cap * 8, (const int64_t*)bp.offsets,
                (const int32_t*)idx, mp ? (const float4*)nullptr : gs.v.sorted, (const u64*)keys, (const float*)ys, (const float*)zs, scratch, smem_cap, ty, tz, n_nodes);
     PPP_CHECK_LAUNCH();
     if (c->c_S_cap < S + 1) {
