@@ -75,6 +75,11 @@ int ppp_timer_read(ppp_ctx* ctx, int tag, double* total_ms, int64_t* regions, in
  * enabled). names: ';'-separated "name=ms_total:launches" written into buf. */
 int ppp_kernel_profile(ppp_ctx* ctx, int enable);
 int ppp_kernel_profile_read(ppp_ctx* ctx, char* buf, size_t cap, int reset);
+/* Launch trace: while enabled every launch is bracketed by CUDA events on the stream it really runs on
+ * (the overlap of the two working streams is kept, unlike the profile above).  read: ';'-separated
+ * "name=stream:start_ms:end_ms" relative to the moment the trace was enabled; clears the trace. */
+int ppp_kernel_trace(ppp_ctx* ctx, int enable);
+int ppp_kernel_trace_read(ppp_ctx* ctx, char* buf, size_t cap);
 
 /* ------------------------------------------------------------------------------------------ */
 /* cloud = device-resident copy + spatial index.

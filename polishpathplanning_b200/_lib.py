@@ -40,6 +40,8 @@ SIGNATURES = {
     "ppp_timer_read": (C.c_int, [_vp, C.c_int, _f64p, _i64p, C.c_int]),
     "ppp_kernel_profile": (C.c_int, [_vp, C.c_int]),
     "ppp_kernel_profile_read": (C.c_int, [_vp, C.c_char_p, C.c_size_t, C.c_int]),
+    "ppp_kernel_trace": (C.c_int, [_vp, C.c_int]),
+    "ppp_kernel_trace_read": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "ppp_cloud_upload": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.POINTER(_vp)]),
     "ppp_dev_cloud_attach": (C.c_int, [_vp, _vp, C.c_size_t, C.c_size_t, C.POINTER(_vp)]),
     "ppp_cloud_free": (C.c_int, [_vp]),

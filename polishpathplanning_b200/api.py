@@ -77,6 +77,21 @@ class Context:
             out[name] = (float(ms), int(cnt))
         return out
 
+    def kernel_trace(self, enable):
+        check(self.lib.ppp_kernel_trace(self._h, int(bool(enable))))
+
+    def kernel_trace_read(self):
+        """[(name, stream 0 main / 1 auxiliary, start_ms, end_ms)] in launch order; clears the trace."""
+        buf = C.create_string_buffer(1 << 20)
+        check(self.lib.ppp_kernel_trace_read(self._h, buf, len(buf)))
+        out = []
+        for item in buf.value.decode().split(";"):
+            if item:
+                name, _, rest = item.partition("=")
+                aux, t0, t1 = rest.split(":")
+                out.append((name, int(aux), float(t0), float(t1)))
+        return out
+
     # -- buffers the GPUs of other processes can write (CUDA IPC over NVLink / NVSwitch) ------------
     def peer_buffer_alloc(self, nbytes):
         """Owner side: returns (device pointer, 64-byte handle as bytes)."""

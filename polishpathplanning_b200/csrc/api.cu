@@ -65,7 +65,8 @@ int ppp_create(int device, ppp_ctx** out) {
   PPP_CUDA(cudaStreamCreateWithPriority(&ctx->main_stream, cudaStreamNonBlocking, prio_lo));
   PPP_CUDA(cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, prio_hi));
   PPP_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  PPP_CUDA(cudaHostAlloc(&ctx->fetch_host, FETCH_BYTES, cudaHostAllocMapped));
+  PPP_CUDA(cudaHostAlloc(&ctx->fetch_host, FETCH_BYTES + 128, cudaHostAllocMapped));
+  *fetch_flag(ctx) = 0u;
   ctx->stream = ctx->main_stream;
   cudaMemPool_t pool;
   PPP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -88,6 +89,8 @@ void ppp_destroy(ppp_ctx* ctx) {
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->fetch_host) cudaFreeHost(ctx->fetch_host);
+  for (int i = 0; i < 2; i++) if (ctx->scan_state[i]) cudaFree(ctx->scan_state[i]);
+  if (ctx->ingest_dev) cudaFree(ctx->ingest_dev);
   delete ctx;
 }
 
@@ -170,6 +173,39 @@ int ppp_kernel_profile_read(ppp_ctx* ctx, char* buf, size_t cap, int reset) {
     s += line;
   }
   if (reset) ctx->kstats.clear();
+  snprintf(buf, cap, "%s", s.c_str());
+  return PPP_OK;
+}
+
+int ppp_kernel_trace(ppp_ctx* ctx, int enable) {
+  REQUIRE(ctx, "ctx is NULL");
+  LOCK(ctx);
+  ctx->trace = enable != 0;
+  if (ctx->trace) {
+    if (!ctx->trace_base) PPP_CUDA(cudaEventCreate(&ctx->trace_base));
+    PPP_CUDA(cudaEventRecord(ctx->trace_base, ctx->main_stream));
+  }
+  return PPP_OK;
+}
+int ppp_kernel_trace_read(ppp_ctx* ctx, char* buf, size_t cap) {
+  REQUIRE(ctx && buf && cap > 0, "bad arguments");
+  LOCK(ctx);
+  PPP_CUDA(cudaStreamSynchronize(ctx->main_stream));
+  PPP_CUDA(cudaStreamSynchronize(ctx->aux_stream));
+  std::string s;
+  for (auto& r : ctx->trace_recs) {
+    float t0 = 0, t1 = 0;
+    if (ctx->trace_base && cudaEventElapsedTime(&t0, ctx->trace_base, r.a) == cudaSuccess &&
+        cudaEventElapsedTime(&t1, ctx->trace_base, r.b) == cudaSuccess) {
+      char line[256];
+      snprintf(line, sizeof(line), "%s=%d:%.6f:%.6f;", r.name, r.aux, t0, t1);
+      s += line;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  cudaGetLastError();
+  ctx->trace_recs.clear();
   snprintf(buf, cap, "%s", s.c_str());
   return PPP_OK;
 }

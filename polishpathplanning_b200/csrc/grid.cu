@@ -32,9 +32,12 @@ struct BBoxAcc {
   unsigned long long n_finite;
 };
 
+// first use of a context's ingest scratch (later ingests find it reset by k_density_sample's last block);
+// acc is the first member of IngestScratch, the ticket follows it
 __global__ void k_bbox_init(BBoxAcc* acc) {
   for (int d = 0; d < 3; d++) { acc->mn[d] = 0xFFFFFFFFu; acc->mx[d] = 0u; }
   acc->n_finite = 0ull;
+  *(unsigned*)(acc + 1) = 0u;
 }
 
 // Pack stride-`sf` records to float4 (original order) and reduce the bounding box of the finite
@@ -180,10 +183,24 @@ __device__ __forceinline__ float ds_kth_smallest(const float* s) {
   return kth;
 }
 
+// The LAST block to finish (ticket) copies the samples and the bounding box into mapped host memory, puts the
+// scratch back to its initial state for the next cloud and raises the host's flag: no separate init kernel, no
+// device-to-device copy, no fetch kernel on the critical path of an ingest.
+struct IngestScratch {
+  BBoxAcc acc;
+  unsigned ticket;
+  unsigned pad[3];
+  float samples[2 * 128];
+};
+
 __global__ void __launch_bounds__(DS_THREADS) k_density_sample(const float4* __restrict__ xyz4, int64_t n, int64_t stride_s,
-                                                               int64_t stride_m, const BBoxAcc* __restrict__ acc,
-                                                               float* __restrict__ out, int S) {
+                                                               int64_t stride_m, IngestScratch* __restrict__ scr, int S,
+                                                               unsigned* __restrict__ host_out, unsigned* __restrict__ host_flag,
+                                                               unsigned seq) {
   __shared__ float s_d[2 * DS_THREADS], s_p[2 * DS_THREADS];
+  __shared__ bool s_last;
+  const BBoxAcc* acc = &scr->acc;
+  float* out = scr->samples;
   // the axis the primary grid does not span: smallest extent, ties drop z, then y (as cloud_ingest decides)
   int drop = 2;
   {
@@ -220,10 +237,28 @@ __global__ void __launch_bounds__(DS_THREADS) k_density_sample(const float4* __r
   __syncthreads();
   if (threadIdx.x < 32) {
     const float r2 = ds_kth_smallest(s_d);
-    if (threadIdx.x == 0) out[blockIdx.x] = r2;
+    if (threadIdx.x == 0) { out[blockIdx.x] = r2; __threadfence(); }
   } else if (threadIdx.x < 64) {
     const float r2 = ds_kth_smallest(s_p);
-    if ((threadIdx.x & 31) == 0) out[S + blockIdx.x] = r2;
+    if ((threadIdx.x & 31) == 0) { out[S + blockIdx.x] = r2; __threadfence(); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&scr->ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // payload: 2 * S samples, then the bounding-box accumulator (8 words)
+  const volatile unsigned* vs = (const volatile unsigned*)scr->samples;
+  for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) host_out[i] = ((int)(i % S) < (int)gridDim.x) ? vs[i] : 0x7FC00000u;
+  const volatile unsigned* va = (const volatile unsigned*)&scr->acc;
+  if (threadIdx.x < (int)(sizeof(BBoxAcc) / 4)) host_out[2 * S + threadIdx.x] = va[threadIdx.x];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int d = 0; d < 3; d++) { scr->acc.mn[d] = 0xFFFFFFFFu; scr->acc.mx[d] = 0u; }
+    scr->acc.n_finite = 0ull;
+    scr->ticket = 0u;
+    *(volatile unsigned*)host_flag = seq;
   }
 }
 
@@ -277,35 +312,40 @@ int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes) {
   int sf = (int)(stride_bytes / 4);
   int vec_ok = (stride_bytes % 16 == 0) && (((uintptr_t)pts_dev) % 16 == 0);
   PPP_TRY(dev_alloc_keep(ctx, &c->xyz4, (size_t)c->n));
-  BBoxAcc* acc = nullptr;
-  PPP_TRY(dev_alloc(ctx, &acc, 1));
-  PPP_LAUNCH(ctx, "bbox_init", k_bbox_init, 1, 1, 0, acc);
-  PPP_CHECK_LAUNCH();
-  if (c->n > 0) {
-    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((c->n + 1023) / 1024, (int64_t)ctx->sm_count * 16));
-    PPP_LAUNCH(ctx, "pack_bbox", k_pack_bbox, blocks, 256, 0, (const float*)pts_dev, c->n, sf, vec_ok, c->xyz4, acc);
-    PPP_CHECK_LAUNCH();
-  }
-  // surface density + projection quality from a sample (same synchronisation as the bounding box)
   constexpr int DS_SAMPLES = 128;
+  static_assert(offsetof(IngestScratch, ticket) == sizeof(BBoxAcc), "k_bbox_init zeroes the ticket behind the accumulator");
+  BBoxAcc h;
+  std::vector<float> ds_h((size_t)2 * DS_SAMPLES, NAN);
+  for (int d = 0; d < 3; d++) { h.mn[d] = 0xFFFFFFFFu; h.mx[d] = 0u; }
+  h.n_finite = 0ull;
   const int64_t ds_m = std::min<int64_t>(c->n, 16384);                 // subsample every block searches
   const int64_t stride_m = ds_m > 0 ? std::max<int64_t>(1, c->n / ds_m) : 1;
   const int ds_s = (int)std::min<int64_t>(DS_SAMPLES, c->n);
   const int64_t stride_s = ds_s > 0 ? std::max<int64_t>(1, c->n / ds_s) : 1;
-  float* ds_out = nullptr;
-  PPP_TRY(dev_alloc(ctx, &ds_out, (size_t)2 * DS_SAMPLES + sizeof(BBoxAcc) / 4 + 4));
-  if (ds_s > 0) {
-    PPP_LAUNCH(ctx, "density_sample", k_density_sample, ds_s, DS_THREADS, 0, (const float4*)c->xyz4, c->n, stride_s, stride_m,
-               (const BBoxAcc*)acc, ds_out, DS_SAMPLES);
+  if (c->n > 0) {
+    if (!ctx->ingest_dev) {
+      PPP_CUDA(cudaMalloc(&ctx->ingest_dev, sizeof(IngestScratch)));
+      ctx->ingest_clean = false;
+    }
+    IngestScratch* scr = (IngestScratch*)ctx->ingest_dev;
+    if (!ctx->ingest_clean) {
+      PPP_LAUNCH(ctx, "bbox_init", k_bbox_init, 1, 1, 0, &scr->acc);
+      PPP_CHECK_LAUNCH();
+    }
+    ctx->ingest_clean = false;   // until this ingest's last block has reset it
+    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((c->n + 1023) / 1024, (int64_t)ctx->sm_count * 16));
+    PPP_LAUNCH(ctx, "pack_bbox", k_pack_bbox, blocks, 256, 0, (const float*)pts_dev, c->n, sf, vec_ok, c->xyz4, &scr->acc);
     PPP_CHECK_LAUNCH();
+    // surface density + projection quality from a sample; its last block delivers samples + bounding box to the host
+    const unsigned seq = ++ctx->fetch_seq ? ctx->fetch_seq : ++ctx->fetch_seq;
+    PPP_LAUNCH(ctx, "density_sample", k_density_sample, ds_s, DS_THREADS, 0, (const float4*)c->xyz4, c->n, stride_s, stride_m,
+               scr, DS_SAMPLES, (unsigned*)ctx->fetch_host, (unsigned*)fetch_flag(ctx), seq);
+    PPP_CHECK_LAUNCH();
+    PPP_TRY(fetch_wait(ctx, seq));
+    ctx->ingest_clean = true;
+    memcpy(ds_h.data(), ctx->fetch_host, ds_h.size() * sizeof(float));
+    memcpy(&h, (const char*)ctx->fetch_host + ds_h.size() * sizeof(float), sizeof(h));
   }
-  BBoxAcc h;
-  PPP_CUDA(cudaMemcpyAsync(ds_out + 2 * DS_SAMPLES, acc, sizeof(BBoxAcc), cudaMemcpyDeviceToDevice, ctx->stream));
-  std::vector<float> ds_h((size_t)2 * DS_SAMPLES + sizeof(BBoxAcc) / 4);
-  PPP_TRY(fetch_small(ctx, ds_out, ds_h.size() * sizeof(float), ds_h.data()));   // ONE fetch: samples + bounding box
-  memcpy(&h, ds_h.data() + 2 * DS_SAMPLES, sizeof(h));
-  dev_free(ctx, acc);
-  dev_free(ctx, ds_out);
   c->n_finite = (int64_t)h.n_finite;
   for (int d = 0; d < 3; d++) {
     // [upstream] getMinMax3D starts from +/-FLT_MAX; an all-non-finite cloud keeps those.
@@ -409,7 +449,7 @@ int cloud_get_grid_drop(ppp_cloud* c, double h, int drop, GridStore** out) {
   v.slack = (float)(h * (double)(v.nu + v.nv) * 9.5367431640625e-07 + 1e-30);
   v.n_sorted = (int)c->n_finite;
   int64_t ncells = (int64_t)v.nu * v.nv;
-  PPP_TRY(dev_alloc_keep(ctx, &gs.sorted, (size_t)std::max<int64_t>(c->n_finite, 1)));
+  PPP_TRY(dev_alloc_keep(ctx, &gs.sorted, (size_t)std::max<int64_t>(c->n_finite, 1) + PPP_SORTED_PAD));
   PPP_TRY(dev_alloc_keep(ctx, &gs.order, (size_t)std::max<int64_t>(c->n_finite, 1)));
   PPP_TRY(dev_alloc_keep(ctx, &gs.cell_start, (size_t)ncells + 1));
   int32_t* counts = nullptr;
@@ -477,8 +517,31 @@ int cloud_get_mp(ppp_cloud* c, double h, int R0, MPSet** out) {
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void k_fetch_small(const unsigned* __restrict__ src, unsigned* __restrict__ dst, int words) {
+__global__ void k_fetch_small(const unsigned* __restrict__ src, unsigned* __restrict__ dst, int words,
+                              unsigned* __restrict__ flag, unsigned seq) {
   for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *(volatile unsigned*)flag = seq;
+}
+
+int fetch_wait(ppp_ctx* ctx, unsigned seq) {
+  volatile unsigned* flag = fetch_flag(ctx);
+  for (unsigned long spin = 1;; spin++) {
+    if (*flag == seq) return PPP_OK;
+    if ((spin & 0x1FFFul) == 0) {
+      cudaError_t e = cudaStreamQuery(ctx->stream);
+      if (e == cudaSuccess) {
+        if (*flag == seq) return PPP_OK;
+        ppp_set_error("fetch: the stream drained without the kernel signalling (sequence %u)", seq);
+        return PPP_ERR_CUDA;
+      }
+      if (e != cudaErrorNotReady) {
+        ppp_set_error("fetch: %s", cudaGetErrorString(e));
+        return PPP_ERR_CUDA;
+      }
+    }
+  }
 }
 
 int fetch_small(ppp_ctx* ctx, const void* dev_src, size_t bytes, void* host_dst) {
@@ -488,9 +551,11 @@ int fetch_small(ppp_ctx* ctx, const void* dev_src, size_t bytes, void* host_dst)
     PPP_CUDA(cudaStreamSynchronize(ctx->stream));
     return PPP_OK;
   }
-  PPP_LAUNCH(ctx, "fetch_small", k_fetch_small, 1, 256, 0, (const unsigned*)dev_src, (unsigned*)ctx->fetch_host, (int)(bytes / 4));
+  const unsigned seq = ++ctx->fetch_seq ? ctx->fetch_seq : ++ctx->fetch_seq;   // never 0 (the flag's initial value)
+  PPP_LAUNCH(ctx, "fetch_small", k_fetch_small, 1, 256, 0, (const unsigned*)dev_src, (unsigned*)ctx->fetch_host, (int)(bytes / 4),
+             (unsigned*)fetch_flag(ctx), seq);
   PPP_CHECK_LAUNCH();
-  PPP_CUDA(cudaStreamSynchronize(ctx->stream));
+  PPP_TRY(fetch_wait(ctx, seq));
   memcpy(host_dst, ctx->fetch_host, bytes);
   return PPP_OK;
 }

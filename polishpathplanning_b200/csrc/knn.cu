@@ -636,6 +636,232 @@ __global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_k
 }
 
 // ---------------------------------------------------------------------------------------------
+// k <= 16, the cloud's own points as queries: 32-bit FIXED-POINT keys.
+//     key = floor(d2 * scale) << 9 | ordinal          scale = (2^23 - margin) / (ring bound)^2  per query
+// Candidates arrive uniformly in d2 (area), so 23 bits of fixed point over [0, bound^2] resolve the k-th
+// neighbourhood about as finely as the float itself does (1.1e-6 mm^2 at cfg2 against an ulp of 4.8e-7), where a
+// truncated float spends its bits on the nearest neighbours.  The ordinal names the candidate by (row of the
+// block, slot in the row); its sorted position is rebuilt from the row start at the very end, and the exact d2
+// -- needed only if the caller asked for distances -- is recomputed from the gathered record with the same
+// arithmetic.  Consequences against the composite-key kernel above: the per-thread store is 4 bytes per slot
+// instead of 8 (half the shared-memory wave fronts, which with the scattered 128-bit candidate loads made the L1
+// data pipe the busiest unit of that kernel: 69 % under ncu), the sorted words ARE the result (no composite
+// construction, no second gather through the slot number), and from the second flush on slots 0..15 are already
+// in order, so a flush is a 16-input sort of the newcomers, one row of minima and a 16-input bitonic merge.
+// Two candidates whose keys agree in the upper 23 bits (including the best one just dropped) leave the order to
+// the exact hand-over kernel, exactly like the composite keys do.  floor(d2 * scale) is one FFMA.RZ against
+// 2^23 (exact floor of the real product: monotone in d2).
+// ---------------------------------------------------------------------------------------------
+constexpr int F_SLOTS = 32;
+constexpr int F_ROWCAP = 64;    // candidate slots per cell row an ordinal can name (6 bits)
+constexpr int F_MAXR = 3;       // 2R+1 <= 7 rows (3 bits)
+
+template <int BD, int MB>
+__global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
+  extern __shared__ unsigned s_fkeys[];
+  constexpr int K = 16;
+  // A free slot j holds FREE(j): above every key (fixed-point values stop at 8388000 < 0x7FFFE0), and distinct in the
+  // upper 23 bits from every other free slot, so free slots never look like an undecided pair.  Slots fill in
+  // order, a flush keeps the smallest free values FREE(ns..15) exactly where they were: the invariant holds.
+#define F_FREE(j) (((0x7FFFE0u + (unsigned)(j)) << 9) | 511u)
+  constexpr unsigned FREE0 = F_FREE(0);
+  const GridView& g = P.g;
+  const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
+  bool valid = t < P.nq;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  int64_t row = 0;
+  if (valid) {
+    float4 p = __ldg(g.sorted + P.first + t);
+    qx = p.x; qy = p.y; qz = p.z;
+    row = __float_as_int(p.w);
+  }
+  valid = query_is_mine(P, valid, row);
+  if (P.choice && !__any_sync(0xffffffffu, valid)) return;   // none of this warp's points chose this projection
+  const bool fin = valid && finite3(qx, qy, qz);
+  const bool act = fin && g.n_sorted > 0;
+  unsigned* keys = s_fkeys + threadIdx.x;                       // slot j of this thread at keys[j * BD]
+  int* rows = (int*)(s_fkeys + F_SLOTS * BD) + threadIdx.x;     // first sorted position of block row j at rows[j * BD]
+  const unsigned keys_sa = (unsigned)__cvta_generic_to_shared(keys);
+  constexpr unsigned SLOT_B = BD * 4;
+  const int R = P.R0;
+  int cu = 0, cv = 0;
+  float tau = -1.0f, scale = 0.0f;   // inactive lanes accept nothing
+  if (act) {
+    cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
+    cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
+    tau = ring_bound2(g, R, cu, cv);
+    // d2 <= tau  =>  d2 * scale <= 8388000 < 2^23
+    scale = tau > 0.0f ? fminf(__fdiv_rd(8388000.0f, tau), 3.0e38f) : 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < F_SLOTS; i++) keys[i * BD] = F_FREE(i);   // a flush needs no masks
+  int ns = 0;              // next slot to fill
+  bool ambiguous = false, overflow = false;
+  bool in_order = false;   // slots 0..15 are sorted (warp-uniform: flushes are)
+
+  auto flush = [&]() {
+    unsigned a[16], b[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { a[i] = keys[i * BD]; b[i] = keys[(16 + i) * BD]; }
+    if (!in_order) SortNetU32<16>::sort(a);
+    SortNetU32<16>::sort(b);
+    // half-cleaner of the bitonic merge: the 16 smallest end up in a (bitonic), the others in b
+    unsigned drop = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const unsigned lo = min(a[i], b[15 - i]);
+      drop = min(drop, max(a[i], b[15 - i]));
+      a[i] = lo;
+    }
+    SortNetU32<16>::bitonic_merge(a);
+    // equal upper 23 bits among the kept 16 or between the 16th and the best one dropped: the fixed-point key does
+    // not decide their order
+    ambiguous |= (a[15] ^ drop) < 512u;
+#pragma unroll
+    for (int i = 0; i + 1 < 16; i++) ambiguous |= (a[i] ^ a[i + 1]) < 512u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { keys[i * BD] = a[i]; keys[(16 + i) * BD] = F_FREE(16 + i); }
+    // every d2 whose key could still sort at or before the 16th: floor(d2 * scale) <= F  =>  d2 < (F + 1) / scale
+    if (a[15] < FREE0) tau = fminf(tau, __fdiv_ru((float)((a[15] >> 9) + 1u), scale));
+    // newcomers go to slots 16.. from now on, also when fewer than 16 slots hold keys: slots 0..15 (keys, then free
+    // values) stay in order
+    ns = K;
+    in_order = true;
+  };
+
+  constexpr int U = 4;
+#pragma unroll 1
+  for (int j = 0; j <= 2 * R + 1; j++) {
+    const int dv = (j & 1) ? -((j + 1) >> 1) : (j >> 1);  // rows nearest first
+    int s = 0, cnt = 0;
+    const int v = cv + dv;
+    const bool drain = j == 2 * R + 1;
+    if (!drain && act && v >= 0 && v < g.nv) {
+      int a = max(cu - R, 0), b = min(cu + R, g.nu - 1);
+      if (a <= b) {
+        const int32_t* rowp = g.cell_start + (int64_t)v * g.nu;
+        s = __ldg(rowp + a);
+        cnt = __ldg(rowp + b + 1) - s;
+      }
+    }
+    if (!drain) rows[j * BD] = s;
+    if (cnt > F_ROWCAP) { overflow = true; cnt = F_ROWCAP; }   // the ordinal cannot name more: exact path
+    const int e = s + cnt;
+    const int n_it = (__reduce_max_sync(0xffffffffu, cnt) + U - 1) / U + (drain ? 1 : 0);
+    // flush when some lane could run out of slots in the next iteration; the drain row flushes once
+    const int trig = min(F_SLOTS - U, (2 * R + 1 - j) * F_SLOTS - 1);
+    unsigned wsa = keys_sa + (unsigned)ns * SLOT_B;
+    const unsigned trig_sa = keys_sa + (unsigned)trig * SLOT_B;
+    int i0 = s;
+    unsigned ord = (unsigned)j << 6;
+#pragma unroll 1
+    for (int it = 0; it < n_it; it++, i0 += U, ord += U) {
+      float4 c4[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) c4[u] = __ldg(g.sorted + (i0 + u));   // never clamped: see PPP_SORTED_PAD
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const float d2 = d2_flann(qx, qy, qz, c4[u].x, c4[u].y, c4[u].z);
+        if (i0 + u < e && d2 <= tau) {
+          const unsigned key = (__float_as_uint(__fmaf_rz(d2, scale, 8388608.0f)) << 9) | (ord + u);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(wsa), "r"(key) : "memory");
+          wsa += SLOT_B;
+        }
+      }
+      if (__any_sync(0xffffffffu, wsa > trig_sa)) {
+        ns = (int)((wsa - keys_sa) / SLOT_B);
+        flush();
+        wsa = keys_sa + (unsigned)ns * SLOT_B;
+      }
+    }
+    ns = (int)((wsa - keys_sa) / SLOT_B);
+  }
+  if (!valid) return;
+  // slots 0..15 now hold the 16 smallest keys in order (padded with free values)
+  const int kk = P.kk;
+  bool complete = !act || kk == 0;
+  if (!complete) complete = keys[(kk - 1) * BD] < FREE0;
+  if (!complete || ambiguous || overflow) {
+    P.redo_list[atomicAdd(P.redo_count, 1)] = (int32_t)t;
+    return;
+  }
+  const int k = P.cap;
+  int m = 0;  // neighbours found
+#pragma unroll
+  for (int j = 0; j < K; j++) m += (act && j < k && keys[j * BD] < FREE0) ? 1 : 0;
+  int32_t* io = P.idx_out ? P.idx_out + row * (int64_t)k : nullptr;
+  float* dout = (P.idx_out && P.d2_out) ? P.d2_out + row * (int64_t)k : nullptr;
+  const bool al32 = k == K && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 31) == 0;
+  const bool al16 = (k & 3) == 0 && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 15) == 0;
+  const bool want_n = P.normals && fin && m >= 3;
+  const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
+  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float kx = 0.f, ky = 0.f, kz = 0.f;
+  // eight neighbours at a time; ONE gather of the neighbour's sorted record serves the id list, the covariance
+  // and (if asked for) the exact distance
+#pragma unroll
+  for (int jb = 0; jb < K; jb += 8) {
+    if (jb >= k) break;
+    float4 nb[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const unsigned key = keys[(jb + u) * BD];
+      const bool has = jb + u < m;
+      nb[u] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      if (has) nb[u] = __ldg(g.sorted + (rows[((key >> 6) & 7u) * BD] + (int)(key & 63u)));   // a free value names no row
+    }
+    if (io) {
+      float dd[8];
+      if (dout) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) dd[u] = jb + u < m ? d2_flann(qx, qy, qz, nb[u].x, nb[u].y, nb[u].z) : CUDART_INF_F;
+      }
+      if (al32) {
+        // a full row is 64 contiguous, 32-byte aligned bytes: two 256-bit stores instead of sixteen 32-bit ones
+        st_global_256(io + jb, nb[0].w, nb[1].w, nb[2].w, nb[3].w, nb[4].w, nb[5].w, nb[6].w, nb[7].w);
+        if (dout) {
+          reinterpret_cast<float4*>(dout + jb)[0] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+          reinterpret_cast<float4*>(dout + jb)[1] = make_float4(dd[4], dd[5], dd[6], dd[7]);
+        }
+      } else if (al16) {
+        // k = 4, 8, 12: rows are still 16-byte aligned
+        reinterpret_cast<float4*>(io + jb)[0] = make_float4(nb[0].w, nb[1].w, nb[2].w, nb[3].w);
+        if (dout) reinterpret_cast<float4*>(dout + jb)[0] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        if (jb + 4 < k) {
+          reinterpret_cast<float4*>(io + jb)[1] = make_float4(nb[4].w, nb[5].w, nb[6].w, nb[7].w);
+          if (dout) reinterpret_cast<float4*>(dout + jb)[1] = make_float4(dd[4], dd[5], dd[6], dd[7]);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (jb + u < k) {
+            io[jb + u] = __float_as_int(nb[u].w);
+            if (dout) dout[jb + u] = dd[u];
+          }
+        }
+      }
+    }
+    if (want_n) {
+      if (jb == 0 && shifted) { kx = nb[0].x; ky = nb[0].y; kz = nb[0].z; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (jb + u < m) {
+          float x = nb[u].x, y = nb[u].y, z = nb[u].z;
+          if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
+          accumulate_point(acc, x, y, z);
+        }
+      }
+    }
+  }
+  if (P.normals) {
+    float o[4];
+    if (want_n) normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
+    else o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
+    store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // 16 < k <= 32 with the same composite keys and a MERGE instead of a full sort: slots 0..31 of the
 // per-thread store hold the 32 best so far in order, slots 32..47 take up to 16 newly accepted candidates.
 // A flush sorts the 16 new composite keys  (bits(d2) & ~63) | slot  (63 exchanges), folds them into the
@@ -1478,8 +1704,15 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
     // life time of one block, 30-50 us, whatever the number of queries -- 0.308 ms against 0.266 ms for the stage.)
     int block = 96;
     if (const char* e = getenv("PPP_KNN_BD")) { int v = atoi(e); if (v == 64 || v == 96 || v == 128) block = v; }
-    size_t smem = (size_t)C_SLOTS * 8 * block;
-    auto kern = block == 128 ? k_knn16c<128> : (block == 96 ? k_knn16c<96> : k_knn16c<64>);
+    // the cloud's own points (cell order): fixed-point keys; external queries keep the composite-key kernel
+    static const bool old16 = getenv("PPP_KNN16_OLD") != nullptr;   // tuning / comparison aid
+    const bool fixed = !P.q && P.R0 <= F_MAXR && !old16;
+    size_t smem = fixed ? (size_t)(F_SLOTS + 2 * P.R0 + 1) * 4 * block : (size_t)C_SLOTS * 8 * block;
+    static const bool more_regs = getenv("PPP_KNN16_REGS72") != nullptr;   // 72 instead of 64 registers per thread
+    auto kern = fixed ? (block == 128 ? (more_regs ? k_knn16f<128, 7> : k_knn16f<128, 8>)
+                                      : (block == 96 ? (more_regs ? k_knn16f<96, 9> : k_knn16f<96, 10>)
+                                                     : (more_regs ? k_knn16f<64, 14> : k_knn16f<64, 16>)))
+                      : (block == 128 ? k_knn16c<128> : (block == 96 ? k_knn16c<96> : k_knn16c<64>));
     PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned blocks = (unsigned)((P.nq + block - 1) / block);
     PPP_LAUNCH(ctx, P.normals ? "knn_normals" : "knn", kern, blocks, block, smem, P);

@@ -48,7 +48,12 @@ struct ppp_ctx {
   cudaStream_t main_stream = nullptr;  // what ppp_stream() returns; timers and ppp_sync refer to it
   cudaStream_t aux_stream = nullptr;   // high priority: the slicing chain runs here, concurrently with the kNN kernel
   cudaStream_t copy_stream = nullptr;  // device->host result copies that overlap later kernels
-  void* fetch_host = nullptr;          // mapped pinned scratch for fetch_small (FETCH_BYTES)
+  void* fetch_host = nullptr;          // mapped pinned scratch for fetch_small (FETCH_BYTES payload + one flag line)
+  unsigned fetch_seq = 0;              // sequence number the next fetch kernel stores behind its payload
+  void* ingest_dev = nullptr;          // persistent device scratch of cloud_ingest (bounding box, ticket, samples)
+  bool ingest_clean = false;           // ... holds its initial values (the last ingest's kernel reset it)
+  unsigned long long* scan_state[2] = {nullptr, nullptr};   // chained-scan tile words, one array per working stream
+  int64_t scan_state_cap[2] = {0, 0};
   // Temporaries of the API call in progress (ApiScope): whatever an early error return leaves behind
   // is released when the outermost call ends.  Guarded by `mu` like everything else here.
   std::vector<void*> temps;
@@ -56,6 +61,10 @@ struct ppp_ctx {
   std::recursive_mutex mu;
   int64_t launches = 0;
   bool profile = false;
+  bool trace = false;                  // ppp_kernel_trace: per-launch start/end on the real streams (overlap kept)
+  cudaEvent_t trace_base = nullptr;
+  struct TraceRec { const char* name; int aux; cudaEvent_t a, b; };
+  std::vector<TraceRec> trace_recs;
   std::map<std::string, KernelStat> kstats;
   cudaEvent_t t_begin[16] = {}, t_end[16] = {};
   double t_ms[16] = {};
@@ -87,6 +96,11 @@ struct NormalRoute {
   long long start[PPP_MAX_RANKS + 1];
   float* base[PPP_MAX_RANKS];
 };
+
+// Records allocated (not initialised) behind the n_sorted indexed ones: the fixed-point k-nearest kernel reads its
+// candidate rows four records at a time without clamping the position (whatever lies there is rejected by
+// the range test), at most PPP_SORTED_PAD - 1 records beyond the end of a row.
+constexpr int PPP_SORTED_PAD = 96;
 
 struct GridStore {
   GridView v{};
@@ -175,7 +189,7 @@ struct LaunchScope {
   cudaEvent_t a = nullptr, b = nullptr;
   LaunchScope(ppp_ctx* c, const char* n) : ctx(c), name(n) {
     ctx->launches++;
-    if (ctx->profile) {
+    if (ctx->profile || ctx->trace) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
       cudaEventRecord(a, ctx->stream);
@@ -184,7 +198,8 @@ struct LaunchScope {
   ~LaunchScope() {
     if (a) {
       cudaEventRecord(b, ctx->stream);
-      ctx->kstats[name].pending.emplace_back(a, b);
+      if (ctx->trace) ctx->trace_recs.push_back({name, ctx->stream == ctx->aux_stream ? 1 : 0, a, b});
+      else ctx->kstats[name].pending.emplace_back(a, b);
     }
   }
 };
@@ -205,6 +220,12 @@ struct LaunchScope {
 // the slicing path otherwise stall until the normals' 32 MB copy has drained).
 constexpr size_t FETCH_BYTES = 64 * 1024;
 int fetch_small(ppp_ctx* ctx, const void* dev_src, size_t bytes, void* host_dst);
+// The flag word behind the payload area and the host side of the hand-shake: a kernel on ctx->stream stores its
+// payload into ctx->fetch_host, fences (system scope) and stores `seq` into the flag; the host spins on the flag --
+// a few hundred nanoseconds after the store lands, where waking up from cudaStreamSynchronize costs several
+// microseconds -- and looks at the stream's status now and then so that a failed kernel cannot hang it.
+inline volatile unsigned* fetch_flag(ppp_ctx* ctx) { return (volatile unsigned*)((char*)ctx->fetch_host + FETCH_BYTES); }
+int fetch_wait(ppp_ctx* ctx, unsigned seq);
 
 // Stream-ordered device memory.  dev_alloc: a temporary of the current API call (tracked until
 // dev_free, see ApiScope); dev_alloc_keep: memory that outlives the call (cloud, grids, result buffers).
