@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        float d2 = d2_flann(qx, qy, qz, c[u].x, c[u].y, c[u].z);
+        float d2 = d2_flann_x2(pack2(qx, qy), qz, c[u]);
         u64 key = make_key(d2, __float_as_int(c[u].w));
         if (in[u] && key < tau) {
           *wptr = key;
@@ -533,7 +533,7 @@ __device__ __forceinline__ void knn16c_body(const SearchParams& P, const int64_t
       for (int u = 0; u < U; u++) c4[u] = __ldg(g.sorted + min(i0 + u, last));   // clamped: always a valid record
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        float d2 = d2_flann(qx, qy, qz, c4[u].x, c4[u].y, c4[u].z);
+        float d2 = d2_flann_x2(pack2(qx, qy), qz, c4[u]);
         if (i0 + u < e && d2 <= tau) {
           asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(wsa), "r"(i0 + u), "r"(__float_as_uint(d2)) : "memory");
           wsa += SLOT_B;
@@ -695,6 +695,7 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
   }
 #pragma unroll
   for (int i = 0; i < F_SLOTS; i++) keys[i * BD] = F_FREE(i);   // a flush needs no masks
+  const u64 qxy = pack2(qx, qy);
   int ns = 0;              // next slot to fill
   bool ambiguous = false, overflow = false;
   bool in_order = false;   // slots 0..15 are sorted (warp-uniform: flushes are)
@@ -746,24 +747,25 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
     }
     if (!drain) rows[j * BD] = s;
     if (cnt > F_ROWCAP) { overflow = true; cnt = F_ROWCAP; }   // the ordinal cannot name more: exact path
-    const int e = s + cnt;
     const int n_it = (__reduce_max_sync(0xffffffffu, cnt) + U - 1) / U + (drain ? 1 : 0);
     // flush when some lane could run out of slots in the next iteration; the drain row flushes once
     const int trig = min(F_SLOTS - U, (2 * R + 1 - j) * F_SLOTS - 1);
     unsigned wsa = keys_sa + (unsigned)ns * SLOT_B;
     const unsigned trig_sa = keys_sa + (unsigned)trig * SLOT_B;
     int i0 = s;
+    int rem = cnt;   // candidates of this lane's row not yet looked at
     unsigned ord = (unsigned)j << 6;
 #pragma unroll 1
-    for (int it = 0; it < n_it; it++, i0 += U, ord += U) {
+    for (int it = 0; it < n_it; it++, i0 += U, ord += U, rem -= U) {
       float4 c4[U];
 #pragma unroll
       for (int u = 0; u < U; u++) c4[u] = __ldg(g.sorted + (i0 + u));   // never clamped: see PPP_SORTED_PAD
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const float d2 = d2_flann(qx, qy, qz, c4[u].x, c4[u].y, c4[u].z);
-        if (i0 + u < e && d2 <= tau) {
-          const unsigned key = (__float_as_uint(__fmaf_rz(d2, scale, 8388608.0f)) << 9) | (ord + u);
+        const float d2 = d2_flann_x2(qxy, qz, c4[u]);
+        if (u < rem && d2 <= tau) {
+          // (bits << 9) + ordinal: the exponent bits of 2^23 leave at the top; one IMAD (+ an add of u)
+          const unsigned key = __float_as_uint(__fmaf_rz(d2, scale, 8388608.0f)) * 512u + ord + (unsigned)u;
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(wsa), "r"(key) : "memory");
           wsa += SLOT_B;
         }
@@ -786,9 +788,18 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
     return;
   }
   const int k = P.cap;
-  int m = 0;  // neighbours found
-#pragma unroll
-  for (int j = 0; j < K; j++) m += (act && j < k && keys[j * BD] < FREE0) ? 1 : 0;
+  int m = 0;  // neighbours found: keys come first in slots 0..15, so four probes find their number
+  if (act) {
+    if (keys[15 * BD] < FREE0) {
+      m = 16;
+    } else {
+      if (keys[7 * BD] < FREE0) m = 8;
+      if (keys[(m + 3) * BD] < FREE0) m += 4;
+      if (keys[(m + 1) * BD] < FREE0) m += 2;
+      if (keys[m * BD] < FREE0) m += 1;
+    }
+    m = min(m, k);
+  }
   int32_t* io = P.idx_out ? P.idx_out + row * (int64_t)k : nullptr;
   float* dout = (P.idx_out && P.d2_out) ? P.d2_out + row * (int64_t)k : nullptr;
   const bool al32 = k == K && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 31) == 0;
@@ -980,7 +991,7 @@ __global__ void __launch_bounds__(BD, (BD == 64 ? 8 : 4)) k_knn32c(SearchParams 
       for (int u = 0; u < U; u++) c4[u] = __ldg(g.sorted + min(i0 + u, last));
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        float d2 = d2_flann(qx, qy, qz, c4[u].x, c4[u].y, c4[u].z);
+        float d2 = d2_flann_x2(pack2(qx, qy), qz, c4[u]);
         if (i0 + u < e && d2 <= tau) {
           asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(wsa), "r"(i0 + u), "r"(__float_as_uint(d2)) : "memory");
           wsa += SLOT_B;
@@ -1114,7 +1125,7 @@ __global__ void __launch_bounds__(128, 6) k_radius_normals32(SearchParams P) {
       u64* wptr = store + ns * BD;
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        float d2 = d2_flann(qx, qy, qz, c4[u].x, c4[u].y, c4[u].z);
+        float d2 = d2_flann_x2(pack2(qx, qy), qz, c4[u]);
         u64 key = make_key(d2, __float_as_int(c4[u].w));
         if (in[u] && key < tau) {
           *wptr = key;
@@ -1702,11 +1713,11 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
     // (Tried and rejected on measurements: a second pass of this kernel with a 7 x 7 block over the ~0.2 % of
     // queries the 5 x 5 block cannot finish, before the one-warp-per-query kernel: each extra launch costs the
     // life time of one block, 30-50 us, whatever the number of queries -- 0.308 ms against 0.266 ms for the stage.)
-    int block = 96;
-    if (const char* e = getenv("PPP_KNN_BD")) { int v = atoi(e); if (v == 64 || v == 96 || v == 128) block = v; }
     // the cloud's own points (cell order): fixed-point keys; external queries keep the composite-key kernel
     static const bool old16 = getenv("PPP_KNN16_OLD") != nullptr;   // tuning / comparison aid
     const bool fixed = !P.q && P.R0 <= F_MAXR && !old16;
+    int block = fixed ? 128 : 96;   // measured: 0.196 / 0.198 / 0.201 ms with 128 / 64 / 96 threads (fixed-point kernel)
+    if (const char* e = getenv("PPP_KNN_BD")) { int v = atoi(e); if (v == 64 || v == 96 || v == 128) block = v; }
     size_t smem = fixed ? (size_t)(F_SLOTS + 2 * P.R0 + 1) * 4 * block : (size_t)C_SLOTS * 8 * block;
     static const bool more_regs = getenv("PPP_KNN16_REGS72") != nullptr;   // 72 instead of 64 registers per thread
     auto kern = fixed ? (block == 128 ? (more_regs ? k_knn16f<128, 7> : k_knn16f<128, 8>)
