@@ -1065,6 +1065,216 @@ __global__ void __launch_bounds__(BD, (BD == 64 ? 8 : 4)) k_knn32c(SearchParams 
 }
 
 // ---------------------------------------------------------------------------------------------
+// 16 < k <= 64, the cloud's own points as queries: the fixed-point keys of k_knn16f with the merge scheme of
+// k_knn32c.  Slots 0..K-1 hold the K best so far in order (free values behind the keys), slots K..K+NEW-1 take the
+// newcomers; a flush sorts the newcomers, folds them into the kept K with one row of minima and a K-input bitonic
+// merge and writes the K words back: no composite construction, no gather of 64-bit keys through the slot number,
+// 4 bytes of shared memory per slot instead of 8.  K = 32: 16 newcomers (63 + 80 exchanges per flush), ordinals of
+// 3 + 6 bits, 23 bits of d2.  K = 64: 32 newcomers (191 + 192 exchanges), ordinals of 3 + 7 bits (rows of up to 128
+// candidates), 22 bits of d2 -- the list lives in 96 registers during a flush where the 64-bit-key kernel it
+// replaces (k_knn_fast<64,16>) needed 198.
+// ---------------------------------------------------------------------------------------------
+template <int K, int NEW, int RB, int BD, int MB>
+__global__ void __launch_bounds__(BD, MB) k_knnf(SearchParams P) {
+  extern __shared__ unsigned s_fkeys[];
+  constexpr int SLOTS = K + NEW;
+  constexpr int SH = 3 + RB;                        // ordinal bits: row of the block, slot in the row
+  constexpr unsigned OMASK = (1u << SH) - 1u;
+  constexpr unsigned FIXTOP = 1u << (32 - SH);      // fixed-point values stay below FIXTOP - 608
+  constexpr int ROWCAP = 1 << RB;
+  static_assert(SLOTS <= 128, "free values are FIXTOP - 128 + slot");
+#define F32_FREE(j) (((FIXTOP - 128u + (unsigned)(j)) << SH) | OMASK)
+  constexpr unsigned FREE0 = F32_FREE(0);
+  const GridView& g = P.g;
+  const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
+  bool valid = t < P.nq;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  int64_t row = 0;
+  if (valid) {
+    float4 p = __ldg(g.sorted + P.first + t);
+    qx = p.x; qy = p.y; qz = p.z;
+    row = __float_as_int(p.w);
+  }
+  valid = query_is_mine(P, valid, row);
+  if (P.choice && !__any_sync(0xffffffffu, valid)) return;   // none of this warp's points chose this projection
+  const bool fin = valid && finite3(qx, qy, qz);
+  const bool act = fin && g.n_sorted > 0;
+  unsigned* keys = s_fkeys + threadIdx.x;                     // slot j of this thread at keys[j * BD]
+  int* rows = (int*)(s_fkeys + SLOTS * BD) + threadIdx.x;     // first sorted position of block row j at rows[j * BD]
+  const unsigned keys_sa = (unsigned)__cvta_generic_to_shared(keys);
+  constexpr unsigned SLOT_B = BD * 4;
+  const int R = P.R0;
+  const int kk = P.kk;       // neighbours wanted (<= K)
+  int cu = 0, cv = 0;
+  float tau = -1.0f, scale = 0.0f;   // inactive lanes accept nothing
+  if (act) {
+    cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
+    cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
+    tau = ring_bound2(g, R, cu, cv);
+    scale = tau > 0.0f ? fminf(__fdiv_rd((float)(FIXTOP - 608u), tau), 3.0e38f) : 0.0f;   // d2 <= tau  =>  d2 * scale < FIXTOP - 608
+  }
+#pragma unroll
+  for (int i = 0; i < SLOTS; i++) keys[i * BD] = F32_FREE(i);   // ascending: slots 0..K-1 are "in order" from the start
+  const u64 qxy = pack2(qx, qy);
+  bool ambiguous = false, overflow = false;
+  unsigned wsa = keys_sa + (unsigned)K * SLOT_B;     // cursor in the newcomers' region
+
+  auto flush = [&]() {
+    unsigned b[NEW];
+#pragma unroll
+    for (int i = 0; i < NEW; i++) b[i] = keys[(K + i) * BD];
+    SortNetU32<NEW>::sort(b);
+    unsigned a[K];
+#pragma unroll
+    for (int i = 0; i < K; i++) a[i] = keys[i * BD];
+    // kept (ascending) ++ newcomers (descending) is bitonic: the half-cleaner leaves the K smallest in a[]; the
+    // smallest of what it discards is the (K+1)-th of the union
+    unsigned next = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = K - NEW; i < K; i++) {
+      const unsigned o = b[K - 1 - i];
+      next = min(next, max(a[i], o));
+      a[i] = min(a[i], o);
+    }
+    SortNetU32<K>::bitonic_merge(a);
+    // equal fixed-point bits: the order of the two is left to the exact kernel (free values differ from each other and
+    // from every key there)
+    ambiguous |= (a[K - 1] ^ next) <= OMASK;
+#pragma unroll
+    for (int i = 0; i + 1 < K; i++) ambiguous |= (a[i] ^ a[i + 1]) <= OMASK;
+#pragma unroll
+    for (int i = 0; i < K; i++) keys[i * BD] = a[i];
+#pragma unroll
+    for (int i = 0; i < NEW; i++) keys[(K + i) * BD] = F32_FREE(K + i);
+    wsa = keys_sa + (unsigned)K * SLOT_B;
+    if (kk > 0) {
+      const unsigned kth = keys[(kk - 1) * BD];
+      if (kth < FREE0) tau = fminf(tau, __fdiv_ru((float)((kth >> SH) + 1u), scale));
+    }
+  };
+
+  constexpr int U = 4;
+  const unsigned trig_sa = keys_sa + (unsigned)(K + NEW - U) * SLOT_B;   // room for one more iteration?
+#pragma unroll 1
+  for (int j = 0; j <= 2 * R + 1; j++) {
+    const int dv = (j & 1) ? -((j + 1) >> 1) : (j >> 1);  // rows nearest first
+    int s = 0, cnt = 0;
+    const int v = cv + dv;
+    const bool drain = j == 2 * R + 1;
+    if (!drain && act && v >= 0 && v < g.nv) {
+      int a0 = max(cu - R, 0), b0 = min(cu + R, g.nu - 1);
+      if (a0 <= b0) {
+        const int32_t* rowp = g.cell_start + (int64_t)v * g.nu;
+        s = __ldg(rowp + a0);
+        cnt = __ldg(rowp + b0 + 1) - s;
+      }
+    }
+    if (!drain) rows[j * BD] = s;
+    if (cnt > ROWCAP) { overflow = true; cnt = ROWCAP; }   // the ordinal cannot name more: exact path
+    // the drain pseudo-row runs one empty iteration whose flush is unconditional
+    const int n_it = (__reduce_max_sync(0xffffffffu, cnt) + U - 1) / U + (drain ? 1 : 0);
+    const unsigned trig = drain ? 0u : trig_sa;
+    int i0 = s;
+    int rem = cnt;
+    unsigned ord = (unsigned)j << RB;
+#pragma unroll 1
+    for (int it = 0; it < n_it; it++, i0 += U, ord += U, rem -= U) {
+      float4 c4[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) c4[u] = __ldg(g.sorted + (i0 + u));   // never clamped: see PPP_SORTED_PAD
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const float d2 = d2_flann_x2(qxy, qz, c4[u]);
+        if (u < rem && d2 <= tau) {
+          // floor(d2 * scale) sits in the low mantissa bits of the sum; the multiplication shifts the exponent out
+          const unsigned key = __float_as_uint(__fmaf_rz(d2, scale, 8388608.0f)) * (1u << SH) + ord + (unsigned)u;
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(wsa), "r"(key) : "memory");
+          wsa += SLOT_B;
+        }
+      }
+      if (__any_sync(0xffffffffu, wsa > trig)) flush();
+    }
+  }
+  if (!valid) return;
+  bool complete = !act || kk == 0;
+  if (!complete) complete = keys[(kk - 1) * BD] < FREE0;
+  if (!complete || ambiguous || overflow) {
+    P.redo_list[atomicAdd(P.redo_count, 1)] = (int32_t)t;
+    return;
+  }
+  const int k = P.cap;
+  int m = 0;   // neighbours found: keys come first in slots 0..K-1
+  if (act) {
+    if (keys[(K - 1) * BD] < FREE0) {
+      m = K;
+    } else {
+#pragma unroll
+      for (int step = K / 2; step >= 1; step >>= 1)
+        if (keys[(m + step - 1) * BD] < FREE0) m += step;
+    }
+    m = min(m, k);
+  }
+  int32_t* io = P.idx_out ? P.idx_out + row * (int64_t)k : nullptr;
+  float* dout = (P.idx_out && P.d2_out) ? P.d2_out + row * (int64_t)k : nullptr;
+  const bool al32 = (k & 7) == 0 && (((uintptr_t)P.idx_out | (uintptr_t)P.d2_out) & 31) == 0;
+  const bool want_n = P.normals && fin && m >= 3;
+  const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
+  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float kx = 0.f, ky = 0.f, kz = 0.f;
+#pragma unroll 1
+  for (int jb = 0; jb < k; jb += 8) {
+    float4 nb[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      nb[u] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+      if (jb + u < m) {
+        const unsigned key = keys[(jb + u) * BD];
+        nb[u] = __ldg(g.sorted + (rows[((key >> RB) & 7u) * BD] + (int)(key & (unsigned)(ROWCAP - 1))));
+      }
+    }
+    if (io) {
+      float dd[8];
+      if (dout) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) dd[u] = jb + u < m ? d2_flann(qx, qy, qz, nb[u].x, nb[u].y, nb[u].z) : CUDART_INF_F;
+      }
+      if (al32) {
+        st_global_256(io + jb, nb[0].w, nb[1].w, nb[2].w, nb[3].w, nb[4].w, nb[5].w, nb[6].w, nb[7].w);
+        if (dout) {
+          reinterpret_cast<float4*>(dout + jb)[0] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+          reinterpret_cast<float4*>(dout + jb)[1] = make_float4(dd[4], dd[5], dd[6], dd[7]);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          if (jb + u < k) {
+            io[jb + u] = __float_as_int(nb[u].w);
+            if (dout) dout[jb + u] = dd[u];
+          }
+        }
+      }
+    }
+    if (want_n) {
+      if (jb == 0 && shifted) { kx = nb[0].x; ky = nb[0].y; kz = nb[0].z; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (jb + u < m) {
+          float x = nb[u].x, y = nb[u].y, z = nb[u].z;
+          if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }
+          accumulate_point(acc, x, y, z);
+        }
+      }
+    }
+  }
+  if (P.normals) {
+    float o[4];
+    if (want_n) normal_from_accumulators(acc, m, qx, qy, qz, P.vpx, P.vpy, P.vpz, o);
+    else o[0] = o[1] = o[2] = o[3] = CUDART_NAN_F;
+    store_normal(P.normals, P.nmap, row, P.nsf, o, P.route);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Fixed-radius normals (NormalEstimation::setRadiusSearch, the reference's default r = 2.5) with
 // the same composite-key idea: every candidate with d2 < r2 is parked in one of 32 slots, ONE
 // 32-input network on 32-bit composite keys orders them at the end, and the covariance is
@@ -1730,7 +1940,33 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
     PPP_CHECK_LAUNCH();
     st = PPP_OK;
   }
-  else if (P.cap <= 32 && !getenv("PPP_KNN32_OLD")) {
+  else if (P.cap <= 32 && !P.q && P.R0 <= F_MAXR && !getenv("PPP_KNN32_OLD")) {
+    // measured (1M points, k = 32, ms): 128 threads x 6 blocks (80 registers) 0.351, x 5 (93) 0.359, 64 threads x 12 / 10 / 8: 0.354 / 0.365 / 0.359
+    int block = 128;
+    if (const char* e = getenv("PPP_KNN_BD")) { int v = atoi(e); if (v == 64 || v == 128) block = v; }
+    size_t smem = (size_t)(32 + 16 + 2 * P.R0 + 1) * 4 * block;
+    static const int regs = getenv("PPP_KNNF_REGS") ? atoi(getenv("PPP_KNNF_REGS")) : 0;   // tuning aid: +1 more registers, fewer blocks
+    auto kern = block == 128 ? (regs > 0 ? k_knnf<32, 16, 6, 128, 5> : k_knnf<32, 16, 6, 128, 6>)
+                             : (regs > 0 ? k_knnf<32, 16, 6, 64, 10> : k_knnf<32, 16, 6, 64, 12>);
+    unsigned blocks = (unsigned)((P.nq + block - 1) / block);
+    PPP_LAUNCH(ctx, P.normals ? "knn_normals" : "knn", kern, blocks, block, smem, P);
+    PPP_CHECK_LAUNCH();
+    st = PPP_OK;
+  }
+  else if (P.cap > 32 && P.cap <= 64 && !P.q && P.R0 <= F_MAXR && !getenv("PPP_KNN64_OLD")) {
+    int block = 128;   // measured (1M points, k = 64): 0.789 ms with 128 threads x 4 blocks, 0.829 with 64 x 8
+    if (const char* e = getenv("PPP_KNN_BD")) { int v = atoi(e); if (v == 64 || v == 128) block = v; }
+    size_t smem = (size_t)(64 + 32 + 2 * P.R0 + 1) * 4 * block;
+    static const int regs = getenv("PPP_KNNF_REGS") ? atoi(getenv("PPP_KNNF_REGS")) : 0;
+    auto kern = block == 128 ? (regs > 0 ? k_knnf<64, 32, 7, 128, 3> : k_knnf<64, 32, 7, 128, 4>)
+                             : (regs > 0 ? k_knnf<64, 32, 7, 64, 6> : k_knnf<64, 32, 7, 64, 8>);
+    PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned blocks = (unsigned)((P.nq + block - 1) / block);
+    PPP_LAUNCH(ctx, P.normals ? "knn_normals" : "knn", kern, blocks, block, smem, P);
+    PPP_CHECK_LAUNCH();
+    st = PPP_OK;
+  }
+  else if (P.cap <= 32 && !getenv("PPP_KNN32_OLD2")) {
     const int block = 64;
     size_t smem = (size_t)48 * 8 * block;
     auto kern = k_knn32c<64>;

@@ -114,25 +114,52 @@ __global__ void __launch_bounds__(256) k_band_fill(BandSet b, const float4* __re
   }
 }
 
-// Sorting network on a (possibly non power-of-two) array with virtual +inf padding: every
+// Bitonic sorting network on a (possibly non power-of-two) array with virtual +inf padding: every
 // compare-exchange puts the minimum at the lower index, partners beyond n are skipped.
+// One thread per COMPARATOR (no idle half), and a warp owns 64 consecutive elements through every step whose
+// span fits in them -- whole stages up to k = 64 and the j <= 32 tail of every later stage --, so those steps are
+// separated by __syncwarp only: 21 block-wide barriers for 2048 elements instead of 66.
+template <typename T>
+__device__ __forceinline__ void cta_sort_ce(T* a, int i, int l, int n) {
+  if (l < n) { T x = a[i], y = a[l]; if (y < x) { a[i] = y; a[l] = x; } }
+}
 template <typename T>
 __device__ void cta_sort(T* a, int n) {
-  int np2 = 1;
+  if (n <= 1) return;   // uniform over the block
+  int np2 = 2;
   while (np2 < n) np2 <<= 1;
-  for (int k = 2; k <= np2; k <<= 1) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      int l = i ^ (k - 1);
-      if (l > i && l < n) { T x = a[i], y = a[l]; if (y < x) { a[i] = y; a[l] = x; } }
-    }
-    __syncthreads();
-    for (int j = k >> 2; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int l = i ^ j;
-        if (l > i && l < n) { T x = a[i], y = a[l]; if (y < x) { a[i] = y; a[l] = x; } }
+  const int half = np2 >> 1;                       // comparators per step
+  const int nt = blockDim.x;                       // a multiple of 32
+  // stages k = 2 .. 64: warp-local throughout
+  for (int c0 = threadIdx.x; c0 - (int)(threadIdx.x & 31) < half; c0 += nt) {   // warp-uniform trip count
+    const int c = c0;
+    for (int k = 2; k <= min(np2, 64); k <<= 1) {
+      const int hk = k >> 1;
+      if (c < half) { const int b = c / hk, o = c - b * hk; cta_sort_ce(a, b * k + o, b * k + (k - 1 - o), n); }
+      __syncwarp();
+      for (int j = k >> 2; j > 0; j >>= 1) {
+        if (c < half) { const int i = 2 * c - (c & (j - 1)); cta_sort_ce(a, i, i + j, n); }
+        __syncwarp();
       }
+    }
+  }
+  __syncthreads();
+  for (int k = 128; k <= np2; k <<= 1) {
+    const int hk = k >> 1;
+    for (int c = threadIdx.x; c < half; c += nt) { const int b = c / hk, o = c - b * hk; cta_sort_ce(a, b * k + o, b * k + (k - 1 - o), n); }
+    __syncthreads();
+    for (int j = k >> 2; j > 32; j >>= 1) {
+      for (int c = threadIdx.x; c < half; c += nt) { const int i = 2 * c - (c & (j - 1)); cta_sort_ce(a, i, i + j, n); }
       __syncthreads();
     }
+    for (int c0 = threadIdx.x; c0 - (int)(threadIdx.x & 31) < half; c0 += nt) {
+      const int c = c0;
+      for (int j = 32; j > 0; j >>= 1) {
+        if (c < half) { const int i = 2 * c - (c & (j - 1)); cta_sort_ce(a, i, i + j, n); }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
   }
 }
 
