@@ -153,6 +153,7 @@ __device__ __forceinline__ void ex_load_xyz(const float* __restrict__ raw, int64
 
 // ---- waits ------------------------------------------------------------------------------------
 __global__ void k_ex_wait(ExView V, int phase, uint32_t step, int only_src, ExScratch* sc) {
+  pdl_prologue();
   const int src = threadIdx.x;
   if (src >= V.world || (only_src >= 0 && src != only_src)) return;
   const uint32_t* f = ex_flag(V, V.rank, phase, src);
@@ -166,11 +167,13 @@ __global__ void k_ex_wait(ExView V, int phase, uint32_t step, int only_src, ExSc
 // Raise this rank's flag of `phase` everywhere: closes a phase whose stores were issued by earlier
 // kernels of the stream (the search kernels' normal records, the contour compaction).
 __global__ void k_ex_signal(ExView V, int phase, uint32_t step) {
+  pdl_prologue();
   __threadfence_system();
   if ((int)threadIdx.x < V.world) st_release_sys(ex_flag(V, threadIdx.x, phase, V.rank), step);
 }
 
 __global__ void k_ex_reset(ExScratch* sc) {
+  pdl_prologue();
   sc->mn = 0xFFFFFFFFu; sc->mx = 0u; sc->n_fin = 0ull;
   for (int i = 0; i < 4; i++) sc->ticket[i] = 0;
   for (int i = threadIdx.x; i < EX_BINS; i += blockDim.x) sc->hist[i] = 0;
@@ -180,6 +183,7 @@ __global__ void k_ex_reset(ExScratch* sc) {
 // ---- phase 0: x-range of the chunk --------------------------------------------------------------
 __global__ void __launch_bounds__(EX_THREADS) k_ex_minmax(ExView V, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
                                                           uint32_t step, ExScratch* sc) {
+  pdl_prologue();
   float mn = CUDART_INF_F, mx = -CUDART_INF_F;
   unsigned cnt = 0;
   constexpr int PPT = 4;   // independent loads in flight per thread
@@ -249,6 +253,7 @@ __device__ __forceinline__ int ex_bin(float x, double gmin, double inv) {
 // ---- phase 1: histogram of x over the global range -----------------------------------------------
 __global__ void __launch_bounds__(1024) k_ex_hist(ExView V, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
                                                         uint32_t step, ExScratch* sc) {
+  pdl_prologue();
   __shared__ int32_t s_hist[EX_BINS];
   for (int i = threadIdx.x; i < EX_BINS; i += blockDim.x) s_hist[i] = 0;
   double gmin, gmax;
@@ -365,6 +370,7 @@ __device__ __forceinline__ unsigned ex_dest_mask(const CUTS* sc, int world, floa
 __global__ void __launch_bounds__(EX_THREADS) k_ex_count(ExView V, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
                                                          double halo, uint32_t step, ExScratch* sc, int32_t* __restrict__ tilecnt,
                                                          int ntiles) {
+  pdl_prologue();
   __shared__ long long s_cum[EX_BINS];
   __shared__ long long s_part[EX_THREADS];
   __shared__ ExCuts C;
@@ -419,6 +425,7 @@ constexpr int EX_WARPS = EX_THREADS / 32;
 __global__ void __launch_bounds__(EX_THREADS) k_ex_scatter(ExView V, const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
                                                            int64_t global_start, double halo, uint32_t step, ExScratch* sc,
                                                            const int32_t* __restrict__ tilecnt, int ntiles) {
+  pdl_prologue();
   __shared__ int s_off[EX_ITERS * EX_WARPS][PPP_MAX_RANKS];
   __shared__ long long s_base[PPP_MAX_RANKS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -489,6 +496,7 @@ __global__ void __launch_bounds__(EX_THREADS) k_ex_scatter(ExView V, const float
 
 // After the records have landed: local row -> global index (-1 for halo copies), and the summary.
 __global__ void __launch_bounds__(256) k_ex_rowmap(ExView V, ExScratch* sc, int32_t* __restrict__ rowmap) {
+  pdl_prologue();
   __shared__ long long s_n[2];
   if (threadIdx.x == 0) {
     const int32_t* tab = reinterpret_cast<const int32_t*>(V.arena[V.rank] + V.off_cnt);

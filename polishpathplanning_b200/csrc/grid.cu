@@ -35,6 +35,7 @@ struct BBoxAcc {
 // first use of a context's ingest scratch (later ingests find it reset by k_density_sample's last block);
 // acc is the first member of IngestScratch, the ticket follows it
 __global__ void k_bbox_init(BBoxAcc* acc) {
+  pdl_prologue();
   for (int d = 0; d < 3; d++) { acc->mn[d] = 0xFFFFFFFFu; acc->mx[d] = 0u; }
   acc->n_finite = 0ull;
   *(unsigned*)(acc + 1) = 0u;
@@ -44,6 +45,7 @@ __global__ void k_bbox_init(BBoxAcc* acc) {
 // points.  One pass over the raw cloud: 12 useful bytes of each record in, 16 out.
 __global__ void __launch_bounds__(256) k_pack_bbox(const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
                                                    float4* __restrict__ xyz4, BBoxAcc* __restrict__ acc) {
+  pdl_prologue();
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
   float mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
   unsigned cnt = 0;
@@ -124,6 +126,7 @@ __device__ __forceinline__ int cell_of(const GridView& g, float x, float y, floa
 
 __global__ void __launch_bounds__(256) k_cell_count(GridView g, const float4* __restrict__ xyz4, int64_t n,
                                                     int32_t* __restrict__ counts) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = __ldg(xyz4 + i);
@@ -135,6 +138,7 @@ __global__ void __launch_bounds__(256) k_cell_count(GridView g, const float4* __
 __global__ void __launch_bounds__(256) k_cell_scatter(GridView g, const float4* __restrict__ xyz4, int64_t n,
                                                       int32_t* __restrict__ counts, const int32_t* __restrict__ start,
                                                       float4* __restrict__ sorted, int32_t* __restrict__ order) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = __ldg(xyz4 + i);
@@ -197,6 +201,7 @@ __global__ void __launch_bounds__(DS_THREADS) k_density_sample(const float4* __r
                                                                int64_t stride_m, IngestScratch* __restrict__ scr, int S,
                                                                unsigned* __restrict__ host_out, unsigned* __restrict__ host_flag,
                                                                unsigned seq) {
+  pdl_prologue();
   __shared__ float s_d[2 * DS_THREADS], s_p[2 * DS_THREADS];
   __shared__ bool s_last;
   const BBoxAcc* acc = &scr->acc;
@@ -283,6 +288,7 @@ __device__ __forceinline__ int block_population(const GridView& g, float x, floa
 // block is simply the one with the fewest points that are NOT neighbours.  hist[p]: how many points chose p.
 __global__ void __launch_bounds__(256) k_mp_choose(G3 G, const float4* __restrict__ xyz4, int64_t n, int R,
                                                    unsigned char* __restrict__ choice, unsigned long long* __restrict__ hist) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int pick = -1;
   if (i < n) {
@@ -519,6 +525,7 @@ int cloud_get_mp(ppp_cloud* c, double h, int R0, MPSet** out) {
 // ---------------------------------------------------------------------------------------------
 __global__ void k_fetch_small(const unsigned* __restrict__ src, unsigned* __restrict__ dst, int words,
                               unsigned* __restrict__ flag, unsigned seq) {
+  pdl_prologue();
   for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
   __threadfence_system();
   __syncthreads();

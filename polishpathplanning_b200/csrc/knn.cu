@@ -65,6 +65,7 @@ __device__ __forceinline__ void list_insert(u64* L, int BD, int& cnt, int cap, u
 }
 
 __global__ void __launch_bounds__(128) k_search(SearchParams P) {
+  pdl_prologue();
   extern __shared__ u64 s_keys[];
   const int BD = blockDim.x;
   int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(128) k_search(SearchParams P) {
 // d2 < r2 is wanted; a query with more than K of them is handed over to the generic kernel.
 template <int K, int PB, bool RADIUS>
 __global__ void __launch_bounds__(128, (K <= 16 ? 6 : (K <= 32 ? 3 : 2))) k_knn_fast(SearchParams P) {
+  pdl_prologue();
   extern __shared__ u64 s_keys[];
   constexpr int BD = 128;  // launch block size (immediate shared-memory offsets)
   const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
@@ -631,15 +633,16 @@ __device__ __forceinline__ void knn16c_body(const SearchParams& P, const int64_t
 
 template <int BD>
 __global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_knn16c(SearchParams P) {
+  pdl_prologue();
   const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
   knn16c_body<BD>(P, t, t < P.nq);
 }
 
 // ---------------------------------------------------------------------------------------------
 // k <= 16, the cloud's own points as queries: 32-bit FIXED-POINT keys.
-//     key = floor(d2 * scale) << 9 | ordinal          scale = (2^23 - margin) / (ring bound)^2  per query
-// Candidates arrive uniformly in d2 (area), so 23 bits of fixed point over [0, bound^2] resolve the k-th
-// neighbourhood about as finely as the float itself does (1.1e-6 mm^2 at cfg2 against an ulp of 4.8e-7), where a
+//     key = floor(d2 * scale) << 10 | ordinal         scale = (2^22 - margin) / (ring bound)^2  per query
+// Candidates arrive uniformly in d2 (area), so 22 bits of fixed point over [0, bound^2] resolve the k-th
+// neighbourhood nearly as finely as the float itself does (2.2e-6 mm^2 at cfg2 against an ulp of 4.8e-7), where a
 // truncated float spends its bits on the nearest neighbours.  The ordinal names the candidate by (row of the
 // block, slot in the row); its sorted position is rebuilt from the row start at the very end, and the exact d2
 // -- needed only if the caller asked for distances -- is recomputed from the gathered record with the same
@@ -648,22 +651,28 @@ __global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_k
 // data pipe the busiest unit of that kernel: 69 % under ncu), the sorted words ARE the result (no composite
 // construction, no second gather through the slot number), and from the second flush on slots 0..15 are already
 // in order, so a flush is a 16-input sort of the newcomers, one row of minima and a 16-input bitonic merge.
-// Two candidates whose keys agree in the upper 23 bits (including the best one just dropped) leave the order to
+// Two candidates whose keys agree in the upper 22 bits (including the best one just dropped) leave the order to
 // the exact hand-over kernel, exactly like the composite keys do.  floor(d2 * scale) is one FFMA.RZ against
 // 2^23 (exact floor of the real product: monotone in d2).
 // ---------------------------------------------------------------------------------------------
 constexpr int F_SLOTS = 32;
-constexpr int F_ROWCAP = 64;    // candidate slots per cell row an ordinal can name (6 bits)
-constexpr int F_MAXR = 3;       // 2R+1 <= 7 rows (3 bits)
+constexpr int F_RB = 7;                  // ordinal: 3 bits of block row (2R+1 <= 7), F_RB bits of slot in the row
+constexpr int F_ROWCAP = 1 << F_RB;      // candidates per cell row an ordinal can name; denser rows take the exact path
+constexpr int F_SH = 3 + F_RB;
+constexpr unsigned F_OMASK = (1u << F_SH) - 1u;
+constexpr unsigned F_FIXTOP = 1u << (32 - F_SH);   // fixed-point values stay below F_FIXTOP - 608
+constexpr int F_MAXR = 3;
+static_assert(F_ROWCAP + 4 <= PPP_SORTED_PAD, "unclamped candidate loads run up to F_ROWCAP + 3 records past a row");
 
 template <int BD, int MB>
 __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
-  extern __shared__ unsigned s_fkeys[];
+  pdl_prologue();
+  extern __shared__ __align__(128) unsigned s_fkeys[];
   constexpr int K = 16;
-  // A free slot j holds FREE(j): above every key (fixed-point values stop at 8388000 < 0x7FFFE0), and distinct in the
-  // upper 23 bits from every other free slot, so free slots never look like an undecided pair.  Slots fill in
+  // A free slot j holds FREE(j): above every key (fixed-point values stop 608 below F_FIXTOP), and distinct in the
+  // fixed-point bits from every other free slot, so free slots never look like an undecided pair.  Slots fill in
   // order, a flush keeps the smallest free values FREE(ns..15) exactly where they were: the invariant holds.
-#define F_FREE(j) (((0x7FFFE0u + (unsigned)(j)) << 9) | 511u)
+#define F_FREE(j) (((F_FIXTOP - 128u + (unsigned)(j)) << F_SH) | F_OMASK)
   constexpr unsigned FREE0 = F_FREE(0);
   const GridView& g = P.g;
   const int64_t t = (int64_t)blockIdx.x * BD + threadIdx.x;
@@ -690,8 +699,8 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
     cu = cell_coord_raw(axis_of(qx, qy, qz, g.au), g.min_u, g.inv_h);
     cv = cell_coord_raw(axis_of(qx, qy, qz, g.av), g.min_v, g.inv_h);
     tau = ring_bound2(g, R, cu, cv);
-    // d2 <= tau  =>  d2 * scale <= 8388000 < 2^23
-    scale = tau > 0.0f ? fminf(__fdiv_rd(8388000.0f, tau), 3.0e38f) : 0.0f;
+    // d2 <= tau  =>  d2 * scale < F_FIXTOP - 608
+    scale = tau > 0.0f ? fminf(__fdiv_rd((float)(F_FIXTOP - 608u), tau), 3.0e38f) : 0.0f;
   }
 #pragma unroll
   for (int i = 0; i < F_SLOTS; i++) keys[i * BD] = F_FREE(i);   // a flush needs no masks
@@ -717,13 +726,13 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
     SortNetU32<16>::bitonic_merge(a);
     // equal upper 23 bits among the kept 16 or between the 16th and the best one dropped: the fixed-point key does
     // not decide their order
-    ambiguous |= (a[15] ^ drop) < 512u;
+    ambiguous |= (a[15] ^ drop) <= F_OMASK;
 #pragma unroll
-    for (int i = 0; i + 1 < 16; i++) ambiguous |= (a[i] ^ a[i + 1]) < 512u;
+    for (int i = 0; i + 1 < 16; i++) ambiguous |= (a[i] ^ a[i + 1]) <= F_OMASK;
 #pragma unroll
     for (int i = 0; i < 16; i++) { keys[i * BD] = a[i]; keys[(16 + i) * BD] = F_FREE(16 + i); }
     // every d2 whose key could still sort at or before the 16th: floor(d2 * scale) <= F  =>  d2 < (F + 1) / scale
-    if (a[15] < FREE0) tau = fminf(tau, __fdiv_ru((float)((a[15] >> 9) + 1u), scale));
+    if (a[15] < FREE0) tau = fminf(tau, __fdiv_ru((float)((a[15] >> F_SH) + 1u), scale));
     // newcomers go to slots 16.. from now on, also when fewer than 16 slots hold keys: slots 0..15 (keys, then free
     // values) stay in order
     ns = K;
@@ -754,7 +763,7 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
     const unsigned trig_sa = keys_sa + (unsigned)trig * SLOT_B;
     int i0 = s;
     int rem = cnt;   // candidates of this lane's row not yet looked at
-    unsigned ord = (unsigned)j << 6;
+    unsigned ord = (unsigned)j << F_RB;
 #pragma unroll 1
     for (int it = 0; it < n_it; it++, i0 += U, ord += U, rem -= U) {
       float4 c4[U];
@@ -764,8 +773,8 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
       for (int u = 0; u < U; u++) {
         const float d2 = d2_flann_x2(qxy, qz, c4[u]);
         if (u < rem && d2 <= tau) {
-          // (bits << 9) + ordinal: the exponent bits of 2^23 leave at the top; one IMAD (+ an add of u)
-          const unsigned key = __float_as_uint(__fmaf_rz(d2, scale, 8388608.0f)) * 512u + ord + (unsigned)u;
+          // (bits << F_SH) + ordinal: the exponent bits of 2^23 leave at the top; one IMAD (+ an add of u)
+          const unsigned key = __float_as_uint(__fmaf_rz(d2, scale, 8388608.0f)) * (1u << F_SH) + ord + (unsigned)u;
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(wsa), "r"(key) : "memory");
           wsa += SLOT_B;
         }
@@ -819,7 +828,7 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
       const unsigned key = keys[(jb + u) * BD];
       const bool has = jb + u < m;
       nb[u] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-      if (has) nb[u] = __ldg(g.sorted + (rows[((key >> 6) & 7u) * BD] + (int)(key & 63u)));   // a free value names no row
+      if (has) nb[u] = __ldg(g.sorted + (rows[((key >> F_RB) & 7u) * BD] + (int)(key & (unsigned)(F_ROWCAP - 1))));   // a free value names no row
     }
     if (io) {
       float dd[8];
@@ -885,6 +894,7 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
 // ---------------------------------------------------------------------------------------------
 template <int BD>
 __global__ void __launch_bounds__(BD, (BD == 64 ? 8 : 4)) k_knn32c(SearchParams P) {
+  pdl_prologue();
   extern __shared__ u64 s_keys[];
   constexpr int K = 32, NEW = 16, SLOTS = K + NEW;
   constexpr unsigned SMASK = 63u;   // slot bits of a composite key
@@ -1076,12 +1086,14 @@ __global__ void __launch_bounds__(BD, (BD == 64 ? 8 : 4)) k_knn32c(SearchParams 
 // ---------------------------------------------------------------------------------------------
 template <int K, int NEW, int RB, int BD, int MB>
 __global__ void __launch_bounds__(BD, MB) k_knnf(SearchParams P) {
-  extern __shared__ unsigned s_fkeys[];
+  pdl_prologue();
+  extern __shared__ __align__(128) unsigned s_fkeys[];
   constexpr int SLOTS = K + NEW;
   constexpr int SH = 3 + RB;                        // ordinal bits: row of the block, slot in the row
   constexpr unsigned OMASK = (1u << SH) - 1u;
   constexpr unsigned FIXTOP = 1u << (32 - SH);      // fixed-point values stay below FIXTOP - 608
   constexpr int ROWCAP = 1 << RB;
+  static_assert(ROWCAP + 4 <= PPP_SORTED_PAD, "unclamped candidate loads run up to ROWCAP + 3 records past a row");
   static_assert(SLOTS <= 128, "free values are FIXTOP - 128 + slot");
 #define F32_FREE(j) (((FIXTOP - 128u + (unsigned)(j)) << SH) | OMASK)
   constexpr unsigned FREE0 = F32_FREE(0);
@@ -1282,6 +1294,7 @@ __global__ void __launch_bounds__(BD, MB) k_knnf(SearchParams P) {
 // neighbours whose d2 agree in the upper 27 bits, goes to the generic kernel (exact for any count).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 6) k_radius_normals32(SearchParams P) {
+  pdl_prologue();
   extern __shared__ u64 s_keys[];
   constexpr int BD = 128;
   constexpr int U = 4;
@@ -1418,6 +1431,7 @@ constexpr int WARPQ_WARPS = 4;
 constexpr int WQ_SEG_MAX = 128;   // cell ranges of one ring handled in the flattened way (rings up to 31)
 
 __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
+  pdl_prologue();
   extern __shared__ u64 s_keys[];
   __shared__ int s_seg[WARPQ_WARPS][WQ_SEG_MAX];
   __shared__ int s_pre[WARPQ_WARPS][WQ_SEG_MAX + 1];
@@ -1593,6 +1607,7 @@ constexpr int RW_CAPL = 16;  // keys per lane: up to 512 neighbours per query if
 
 __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_radius_warp(SearchParams P, int32_t* __restrict__ redo2_count,
                                                                   int32_t* __restrict__ redo2_list) {
+  pdl_prologue();
   __shared__ u64 s_l[WARPQ_WARPS * 32 * RW_CAPL];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const GridView& g = P.g;
@@ -1654,6 +1669,7 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_radius_warp(SearchParams P
 }
 
 __global__ void __launch_bounds__(128) k_radius_count(SearchParams P, int32_t* __restrict__ counts, int32_t* __restrict__ max_count) {
+  pdl_prologue();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int cnt = 0;
   bool have = t < P.nq;
@@ -1702,6 +1718,7 @@ __global__ void __launch_bounds__(128) k_radius_count(SearchParams P, int32_t* _
 __global__ void __launch_bounds__(128) k_principal_curvatures(const int32_t* __restrict__ idx, int64_t nq, int k,
                                                               const float* __restrict__ normals, int nsf,
                                                               float* __restrict__ out, int32_t* __restrict__ nn0) {
+  pdl_prologue();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nq) return;
   const int32_t* nb = idx + t * (int64_t)k;
@@ -1777,6 +1794,7 @@ __global__ void __launch_bounds__(128) k_principal_curvatures(const int32_t* __r
 // its coverage flag set.  No ordering is needed, so candidates are marked as they are scanned.
 __global__ void __launch_bounds__(128) k_coverage_mark(SearchParams P, unsigned char* __restrict__ flags,
                                                        const float* __restrict__ r2_per_query) {
+  pdl_prologue();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= P.nq) return;
   const GridView& g = P.g;
@@ -1799,6 +1817,7 @@ __global__ void __launch_bounds__(128) k_coverage_mark(SearchParams P, unsigned 
 __global__ void __launch_bounds__(256) k_sor_mean(const float4* __restrict__ xyz4, const float* __restrict__ d2, int64_t n,
                                                   int k, int sqrt_float, float* __restrict__ dist,
                                                   unsigned long long* __restrict__ n_valid) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool ok = false;
   if (i < n) {
@@ -1821,6 +1840,7 @@ __global__ void __launch_bounds__(256) k_sor_mean(const float4* __restrict__ xyz
 }
 
 __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -1830,6 +1850,7 @@ __global__ void k_fill_i32(int32_t* p, int64_t n, int32_t v) {
 __global__ void k_default_rows(const float4* __restrict__ xyz4, int64_t n, int cap, int32_t* idx_out, float* d2_out,
                                float* normals, int nsf, const int32_t* __restrict__ nmap,
                                const NormalRoute* __restrict__ route) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = __ldg(xyz4 + i);

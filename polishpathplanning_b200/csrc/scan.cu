@@ -47,6 +47,7 @@ __device__ __forceinline__ T block_excl_scan(T v, T* total) {
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const TI* __restrict__ in, int64_t n, TO* __restrict__ tile_sums) {
+  pdl_prologue();
   int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
   TO s = 0;
 #pragma unroll
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const TI* __res
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const TI* __restrict__ in, int64_t n, const TO* __restrict__ tile_base,
                                                              TO* __restrict__ out, int write_total) {
+  pdl_prologue();
   int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   TO v[SCAN_ITEMS];
   TO s = 0;
@@ -88,7 +90,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const TI* __restric
 }
 
 template <typename T>
-__global__ void k_scan_zero_total(T* out) { out[0] = 0; }
+__global__ void k_scan_zero_total(T* out) {
+  pdl_prologue(); out[0] = 0; }
 
 // Single-pass exclusive scan (chained tiles with decoupled look-back).  A tile takes its number from a ticket
 // counter -- so every tile it may wait for is already running --, scans its 4096 items, publishes
@@ -98,6 +101,7 @@ __global__ void k_scan_zero_total(T* out) { out[0] = 0; }
 // words and the ticket for the next call: no memset between calls.
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chained(const int32_t* __restrict__ in, int64_t n, int32_t* __restrict__ out,
                                                                unsigned long long* __restrict__ state, int tiles) {
+  pdl_prologue();
   __shared__ int s_tile;
   __shared__ int32_t s_prefix;
   if (threadIdx.x == 0) s_tile = (int)atomicAdd(state, 1ull);
@@ -209,4 +213,9 @@ int scan_exclusive_i32(ppp_ctx* ctx, const int32_t* in, int32_t* out, int64_t n)
 }
 int scan_exclusive_i32_to_i64(ppp_ctx* ctx, const int32_t* in, int64_t* out, int64_t n) {
   return scan_impl<int32_t, long long>(ctx, in, (long long*)out, n, 1);
+}
+
+bool ppp_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("PPP_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }

@@ -57,6 +57,7 @@ __device__ __forceinline__ void for_memberships(const BandSet& b, float x, F&& f
 
 __global__ void __launch_bounds__(256) k_band_count(BandSet b, const float4* __restrict__ xyz4, int64_t n, int64_t chunk,
                                                     int use_smem, int w_is_flag, int32_t* __restrict__ counts) {
+  pdl_prologue();
   extern __shared__ int32_t s_cnt[];
   if (use_smem) {
     for (int t = threadIdx.x; t < b.S; t += blockDim.x) s_cnt[t] = 0;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) k_band_count(BandSet b, const float4* __r
 __global__ void __launch_bounds__(256) k_band_fill(BandSet b, const float4* __restrict__ xyz4, int64_t n, int64_t chunk,
                                                    int use_smem, int w_is_flag, int32_t* __restrict__ cursor,
                                                    const int64_t* __restrict__ offsets, int32_t* __restrict__ idx_out) {
+  pdl_prologue();
   extern __shared__ int32_t s_mem[];
   int32_t* s_cnt = s_mem;
   int32_t* s_base = s_mem + b.S;
@@ -164,6 +166,7 @@ __device__ void cta_sort(T* a, int n) {
 }
 
 __global__ void __launch_bounds__(1024) k_band_sort(const int64_t* __restrict__ offsets, int32_t* __restrict__ idx, int smem_cap) {
+  pdl_prologue();
   extern __shared__ int32_t s_idx[];
   int s = blockIdx.x;
   int64_t o = offsets[s];
@@ -349,6 +352,7 @@ __device__ __forceinline__ int lower_pos(const int32_t* a, int n, int v) {
 // at shared-memory latency; larger bands use the global scratch arrays with the same code.
 template <bool MEMBER>
 __global__ void __launch_bounds__(1024) k_contour(ContourParams P, int smem_cap) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ int s_warp[32];
   __shared__ int s_npairs, s_nl, s_nr;
@@ -522,6 +526,7 @@ constexpr int PAIR_WARPS = 4;
 
 template <bool MEMBER>
 __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
+  pdl_prologue();
   __shared__ int64_t s_m[PAIR_WARPS][64];
   __shared__ int s_s[PAIR_WARPS][64];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -599,6 +604,7 @@ __global__ void __launch_bounds__(SO_THREADS) k_slice_order(const int64_t* __res
                                                            const float* __restrict__ zs, u64* __restrict__ scratch,
                                                            int smem_cap, double* __restrict__ ty, double* __restrict__ tz,
                                                            int32_t* __restrict__ n_nodes) {
+  pdl_prologue();
   extern __shared__ u64 s_keys64[];
   __shared__ int s_warp[32];
   __shared__ int s_valid;
@@ -649,6 +655,7 @@ __global__ void __launch_bounds__(SO_THREADS) k_slice_order(const int64_t* __res
 }
 
 __global__ void k_set_member_bits(const int32_t* __restrict__ idx, int64_t m, uint32_t* __restrict__ bits) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) atomicOr(bits + (idx[i] >> 5), 1u << (idx[i] & 31));
 }
@@ -657,6 +664,7 @@ __global__ void __launch_bounds__(256) k_compact_nodes(const int64_t* __restrict
                                                       const float* __restrict__ planes, const double* __restrict__ ty,
                                                       const double* __restrict__ tz, double* __restrict__ y,
                                                       double* __restrict__ x, double* __restrict__ z) {
+  pdl_prologue();
   int s = blockIdx.x;
   int64_t so = band_off[s], d = node_off[s];
   int n = (int)(node_off[s + 1] - d);
@@ -680,6 +688,7 @@ struct NodeDest {
 __global__ void __launch_bounds__(256) k_compact_nodes_auto(const int64_t* __restrict__ band_off, const int64_t* __restrict__ node_off,
                                                            int S, const float* __restrict__ planes, const double* __restrict__ ty,
                                                            const double* __restrict__ tz, NodeDest D, int64_t* __restrict__ summary) {
+  pdl_prologue();
   const int s = blockIdx.x;
   const int64_t total = node_off[S];
   const bool ext = D.ey && total <= D.ecap;
