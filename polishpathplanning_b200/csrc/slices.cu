@@ -9,7 +9,11 @@
 #include <cmath>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "ppp_device.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -125,6 +129,24 @@ template <typename T>
 __device__ __forceinline__ void cta_sort_ce(T* a, int i, int l, int n) {
   if (l < n) { T x = a[i], y = a[l]; if (y < x) { a[i] = y; a[l] = x; } }
 }
+// Steps j0, j0 / 2, .., 1 of a merge over a[0 .. 2 * half) (n valid elements in front); ends with a block barrier.
+template <typename T>
+__device__ void cta_jsteps(T* a, int n, int half, int j0) {
+  const int nt = blockDim.x;
+  for (int j = j0; j > 32; j >>= 1) {
+    for (int c = threadIdx.x; c < half; c += nt) { const int i = 2 * c - (c & (j - 1)); cta_sort_ce(a, i, i + j, n); }
+    __syncthreads();
+  }
+  for (int c0 = threadIdx.x; c0 - (int)(threadIdx.x & 31) < half; c0 += nt) {   // warp-uniform trip count
+    const int c = c0;
+    for (int j = min(j0, 32); j > 0; j >>= 1) {
+      if (c < half) { const int i = 2 * c - (c & (j - 1)); cta_sort_ce(a, i, i + j, n); }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+}
+
 template <typename T>
 __device__ void cta_sort(T* a, int n) {
   if (n <= 1) return;   // uniform over the block
@@ -150,18 +172,7 @@ __device__ void cta_sort(T* a, int n) {
     const int hk = k >> 1;
     for (int c = threadIdx.x; c < half; c += nt) { const int b = c / hk, o = c - b * hk; cta_sort_ce(a, b * k + o, b * k + (k - 1 - o), n); }
     __syncthreads();
-    for (int j = k >> 2; j > 32; j >>= 1) {
-      for (int c = threadIdx.x; c < half; c += nt) { const int i = 2 * c - (c & (j - 1)); cta_sort_ce(a, i, i + j, n); }
-      __syncthreads();
-    }
-    for (int c0 = threadIdx.x; c0 - (int)(threadIdx.x & 31) < half; c0 += nt) {
-      const int c = c0;
-      for (int j = 32; j > 0; j >>= 1) {
-        if (c < half) { const int i = 2 * c - (c & (j - 1)); cta_sort_ce(a, i, i + j, n); }
-        __syncwarp();
-      }
-    }
-    __syncthreads();
+    cta_jsteps(a, n, half, k >> 2);
   }
 }
 
@@ -598,29 +609,25 @@ __global__ void __launch_bounds__(PAIR_WARPS * 32) k_pair_nodes(PairParams P) {
 // matters for -0.0 / +0.0) and the value of the LAST insertion (highest left index).
 constexpr int SO_THREADS = 1024;
 
-__global__ void __launch_bounds__(SO_THREADS) k_slice_order(const int64_t* __restrict__ band_off, const int32_t* __restrict__ band_idx,
-                                                           const float4* __restrict__ sorted_if_pos,
-                                                           const u64* __restrict__ keys_g, const float* __restrict__ ys,
-                                                           const float* __restrict__ zs, u64* __restrict__ scratch,
-                                                           int smem_cap, double* __restrict__ ty, double* __restrict__ tz,
-                                                           int32_t* __restrict__ n_nodes) {
-  pdl_prologue();
-  extern __shared__ u64 s_keys64[];
-  __shared__ int s_warp[32];
-  __shared__ int s_valid;
-  const int s = blockIdx.x;
+__device__ void slice_order_single(const int64_t* __restrict__ band_off, const int32_t* __restrict__ band_idx,
+                                   const float4* __restrict__ sorted_if_pos, const u64* __restrict__ keys_g,
+                                   const float* __restrict__ ys, const float* __restrict__ zs, u64* __restrict__ scratch,
+                                   u64* s_keys64, int smem_cap, int skip_big, double* __restrict__ ty, double* __restrict__ tz,
+                                   int32_t* __restrict__ n_nodes, int s, int* s_warp, int* s_valid_p) {
   const int64_t o = band_off[s];
   const int B = (int)(band_off[s + 1] - o);
+  if (skip_big && B > smem_cap) return;   // left to the cluster kernel that follows (uniform over the block)
   u64* k = (B <= smem_cap) ? s_keys64 : (scratch + o);
-  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) *s_valid_p = 0;
   __syncthreads();
   // keep only the node keys (left members that found a pair); their order does not matter yet
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
     u64 key = keys_g[o + i];
-    if (key != PPP_KEY_INF) k[atomicAdd(&s_valid, 1)] = key;
+    if (key != PPP_KEY_INF) k[atomicAdd(s_valid_p, 1)] = key;
   }
   __syncthreads();
-  const int nv = s_valid;
+  const int nv = *s_valid_p;
   cta_sort(k, nv);
   int nodes = 0;
   for (int base = 0; base < nv; base += blockDim.x) {
@@ -652,6 +659,156 @@ __global__ void __launch_bounds__(SO_THREADS) k_slice_order(const int64_t* __res
     }
   }
   if (threadIdx.x == 0) n_nodes[s] = nodes;
+}
+
+__global__ void __launch_bounds__(SO_THREADS) k_slice_order(const int64_t* __restrict__ band_off, const int32_t* __restrict__ band_idx,
+                                                           const float4* __restrict__ sorted_if_pos,
+                                                           const u64* __restrict__ keys_g, const float* __restrict__ ys,
+                                                           const float* __restrict__ zs, u64* __restrict__ scratch,
+                                                           int smem_cap, int skip_big, double* __restrict__ ty, double* __restrict__ tz,
+                                                           int32_t* __restrict__ n_nodes) {
+  pdl_prologue();
+  extern __shared__ u64 s_keys64[];
+  __shared__ int s_warp[32];
+  __shared__ int s_valid;
+  slice_order_single(band_off, band_idx, sorted_if_pos, keys_g, ys, zs, scratch, s_keys64, smem_cap, skip_big, ty, tz, n_nodes,
+                     (int)blockIdx.x, s_warp, &s_valid);
+}
+
+// ---- the same, one thread-block CLUSTER per slice ------------------------------------------------------------
+// For slices whose node keys do not fit one CTA's shared memory (the silhouette bands of a closed workpiece hold tens
+// of thousands of members) and for sweeps with fewer slices than SMs (a rank's share of the planes at 8 GPUs): the C
+// CTAs of a cluster each filter 1/C of the band, the keys go -- by distributed-shared-memory stores -- into ONE
+// array spread over the C shared memories (chunk = np2 / C keys per CTA), and the bitonic network runs on it: every
+// stage up to k = chunk and the j < chunk tail of the later stages stay inside a CTA (cta_sort / cta_jsteps), the
+// few remaining steps exchange across CTAs through DSMEM with a cluster barrier each (C = 4: 3 + 2 + 1 of them).
+// The map-order pass reads its left neighbour and the tail of equal-y runs across the CTA boundary the same way.
+// A slice too large even for C x SOC_CHUNK_MAX keys is sorted by CTA 0 in global scratch like before.
+constexpr int SOC_CHUNK_MAX = 16384;   // keys per CTA: 128 KB
+
+template <int C>
+__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(SO_THREADS, 1)
+k_slice_order_cl(const int64_t* __restrict__ band_off, const int32_t* __restrict__ band_idx, const float4* __restrict__ sorted_if_pos,
+                 const u64* __restrict__ keys_g, const float* __restrict__ ys, const float* __restrict__ zs, u64* __restrict__ scratch,
+                 int chunk_cap, int S, int min_B, int max_B, double* __restrict__ ty, double* __restrict__ tz,
+                 int32_t* __restrict__ n_nodes) {
+  pdl_prologue();
+  extern __shared__ u64 s_arr[];     // this CTA's chunk of the slice's distributed key array
+  __shared__ int s_warp[32];
+  __shared__ int s_cnt, s_fill, s_first;
+  cg::cluster_group cl = cg::this_cluster();
+  const int r = (int)cl.block_rank();
+  const int nt = blockDim.x;
+  // the clusters of the grid share the slices whose band size lies in (min_B, max_B]; every test below that decides
+  // the control flow depends on the slice alone, so the CTAs of a cluster stay together
+  for (int s = blockIdx.x / C; s < S; s += gridDim.x / C) {
+  const int64_t o = band_off[s];
+  const int B = (int)(band_off[s + 1] - o);
+  if (B <= min_B || B > max_B) continue;
+  const int seg = (B + C - 1) / C;
+  const int b0 = min(r * seg, B), b1 = min(b0 + seg, B);   // my part of the band
+  if (threadIdx.x == 0) { s_cnt = 0; s_fill = 0; s_first = 0; }
+  __syncthreads();
+  int mine = 0;
+  for (int i = b0 + threadIdx.x; i < b1; i += nt) mine += keys_g[o + i] != PPP_KEY_INF ? 1 : 0;
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_cnt, mine);
+  cl.sync();
+  int nv = 0, before = 0;
+#pragma unroll
+  for (int q = 0; q < C; q++) {
+    const int cq = *cl.map_shared_rank(&s_cnt, q);
+    if (q < r) before += cq;
+    nv += cq;
+  }
+  int np2 = 2;
+  while (np2 < nv) np2 <<= 1;
+  const int chunk = max(np2 / C, 64);    // keys per CTA, a power of two
+  if (chunk > chunk_cap) {               // uniform over the cluster: CTA 0 takes the slice alone, in global scratch
+    cl.sync();                           // ... once nobody reads this CTA's counters any more
+    if (r == 0) slice_order_single(band_off, band_idx, sorted_if_pos, keys_g, ys, zs, scratch, s_arr, 0, 0, ty, tz, n_nodes, s, s_warp, &s_cnt);
+    continue;                            // (the others wait for it at the next slice's first cluster barrier)
+  }
+  const int csh = 31 - __clz(chunk);
+  auto elem = [&](int g) -> u64* { return cl.map_shared_rank(s_arr, g >> csh) + (g & (chunk - 1)); };
+  // the node keys (left members that found a pair) -> their place in the distributed array; order inside is arbitrary
+  for (int i = b0 + threadIdx.x; i < b1; i += nt) {
+    const u64 key = keys_g[o + i];
+    if (key != PPP_KEY_INF) *elem(before + atomicAdd(&s_fill, 1)) = key;
+  }
+  cl.sync();
+  const int base = r * chunk;
+  const int n_loc = max(0, min(nv - base, chunk));
+  cta_sort(s_arr, n_loc);
+  cl.sync();
+  const int half = np2 >> 1;
+  const int c_lo = r * (chunk >> 1), c_hi = min((r + 1) * (chunk >> 1), half);   // this CTA's comparators of a cross step
+  for (int k = 2 * chunk; k <= np2; k <<= 1) {
+    const int hk = k >> 1;
+    for (int c = c_lo + threadIdx.x; c < c_hi; c += nt) {
+      const int b = c / hk, oo = c - b * hk, i = b * k + oo, l = b * k + (k - 1 - oo);
+      if (l < nv) { u64* pi = elem(i); u64* pl = elem(l); const u64 x = *pi, y = *pl; if (y < x) { *pi = y; *pl = x; } }
+    }
+    cl.sync();
+    for (int j = k >> 2; j >= chunk; j >>= 1) {
+      for (int c = c_lo + threadIdx.x; c < c_hi; c += nt) {
+        const int i = 2 * c - (c & (j - 1)), l = i + j;
+        if (l < nv) { u64* pi = elem(i); u64* pl = elem(l); const u64 x = *pi, y = *pl; if (y < x) { *pi = y; *pl = x; } }
+      }
+      cl.sync();
+    }
+    cta_jsteps(s_arr, n_loc, chunk >> 1, chunk >> 1);
+    cl.sync();
+  }
+  // std::map order: one node per distinct y, key of the first insertion, value of the last (see k_slice_order)
+  int firsts = 0;
+  for (int il = threadIdx.x; il < n_loc; il += nt) {
+    const int g = base + il;
+    firsts += (g == 0 || ((*elem(g - 1)) >> 32) != (s_arr[il] >> 32)) ? 1 : 0;
+  }
+  firsts = __reduce_add_sync(0xffffffffu, firsts);
+  if ((threadIdx.x & 31) == 0 && firsts) atomicAdd(&s_first, firsts);
+  cl.sync();
+  int nodes = 0, total = 0;
+#pragma unroll
+  for (int q = 0; q < C; q++) {
+    const int fq = *cl.map_shared_rank(&s_first, q);
+    if (q < r) nodes += fq;
+    total += fq;
+  }
+  for (int bt = 0; bt < n_loc; bt += nt) {
+    const int il = bt + threadIdx.x;
+    const int g = base + il;
+    bool first = false;
+    u64 key = 0;
+    if (il < n_loc) {
+      key = s_arr[il];
+      first = g == 0 || ((*elem(g - 1)) >> 32) != (key >> 32);
+    }
+    const int rnk = cta_flag_rank(first, s_warp, nodes);
+    if (first) {
+      const int slot = (int)(uint32_t)(key & 0xFFFFFFFFull);
+      auto id_of = [&](int sl) {
+        const int e = __ldg(band_idx + o + sl);
+        return sorted_if_pos ? __float_as_int(__ldg(&sorted_if_pos[e].w)) : e;
+      };
+      int lo_idx = -1, hi_idx = -1, lo_slot = slot, hi_slot = slot;
+      for (int j = g + 1; j < nv; j++) {
+        const u64 kj = *elem(j);
+        if ((kj >> 32) != (key >> 32)) break;
+        if (lo_idx < 0) lo_idx = hi_idx = id_of(slot);   // ids are only needed when a y value repeats
+        const int sl = (int)(uint32_t)(kj & 0xFFFFFFFFull);
+        const int id = id_of(sl);
+        if (id < lo_idx) { lo_idx = id; lo_slot = sl; }
+        if (id > hi_idx) { hi_idx = id; hi_slot = sl; }
+      }
+      ty[o + rnk] = (double)ys[o + lo_slot];
+      tz[o + rnk] = (double)zs[o + hi_slot];
+    }
+  }
+  if (r == 0 && threadIdx.x == 0) n_nodes[s] = total;
+  cl.sync();   // no CTA leaves (or starts the next slice) while a neighbour may still read its shared memory
+  }
 }
 
 __global__ void k_set_member_bits(const int32_t* __restrict__ idx, int64_t m, uint32_t* __restrict__ bits) {
@@ -737,6 +894,7 @@ struct BandPrep {
   unsigned blocks = 1;
   int64_t chunk = 0;
   int max_depth = 0;          // most bands any single x can belong to
+  float max_width = 0.f;      // widest band (hi - lo)
   const float4* src = nullptr;  // records the bands are drawn from: the packed cloud (entries = original indices) ...
   int64_t n_src = 0;            // ... or the cell-major sorted array of a grid (entries = sorted positions)
   int w_is_flag = 1;
@@ -771,7 +929,7 @@ static int bands_prepare(ppp_cloud* c, const float* plane_x_host, int S, float h
   }
   for (int t = 0; t < S; t++) {
     int s = perm[t];
-    if (!std::isnan(lo[s])) Sv = t + 1;
+    if (!std::isnan(lo[s])) { Sv = t + 1; bp->max_width = std::max(bp->max_width, hi[s] - lo[s]); }
     stage[3 * S + t] = lo[s];
     stage[4 * S + t] = hi[s];
   }
@@ -859,6 +1017,70 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
   return PPP_OK;
 }
 
+// Orders the nodes of every slice, in two launches that split the slices by band size:
+//   1. one CTA per slice (k_slice_order) -- or, when a sweep has fewer slices than the GPU has SMs, a cluster of 2 / 4
+//      CTAs per slice -- for the bands up to cap1 members, sized from `band_est`;
+//   2. a few persistent clusters of 8 CTAs (k_slice_order_cl<8>, 128 KB of keys per CTA) for the bands beyond cap1:
+//      the silhouette bands of a closed workpiece, a flat face parallel to the planes.  Only launched when such bands
+//      are to be expected (`expect_big`, or an estimate beyond cap1); otherwise the first launch sorts a band that
+//      does exceed cap1 after all in `scratch` (slow, but an empty second launch costs every sweep ~5 us).
+// `scratch` (M keys) also takes what even a cluster cannot hold (> 131072 node keys in one slice).
+static int launch_slice_order(ppp_ctx* ctx, int S, int64_t band_est, bool expect_big, const int64_t* band_off, const int32_t* band_idx,
+                              const float4* sorted_if_pos, const u64* keys, const float* ys, const float* zs, u64* scratch,
+                              double* ty, double* tz, int32_t* n_nodes) {
+  if (S <= 0) return PPP_OK;
+  band_est = std::max<int64_t>(band_est, 1);
+  int C = 1;
+  if (band_est >= 4096 && band_est <= 4 * (int64_t)SOC_CHUNK_MAX) C = S * 2 <= ctx->sm_count ? 4 : (S <= ctx->sm_count ? 2 : 1);
+  if (const char* e = getenv("PPP_SLICE_CLUSTER")) {   // tuning / test aid: first launch with clusters of 1 / 2 / 4 / 8
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4 || v == 8) C = v;
+  }
+  int64_t np2 = 1;
+  while (np2 < band_est) np2 <<= 1;
+  const int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(band_est, 1024), 24576);  // C == 1: <= 192 KB of u64
+  const int chunk_cap = (int)std::min<int64_t>(std::max<int64_t>(np2 / C, 1024), SOC_CHUNK_MAX);
+  const int64_t cap1 = C == 1 ? (int64_t)smem_cap : (int64_t)chunk_cap * C;
+  const bool big = expect_big || band_est > cap1;   // a second launch takes the bands beyond cap1
+  if (C == 1) {
+    if ((size_t)smem_cap * 8 > 48 * 1024)
+      PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
+    // short bands: 256 threads sort them with a quarter of the barrier traffic, and more slices share an SM
+    const int so_threads = smem_cap <= 4608 ? 256 : SO_THREADS;
+    PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, so_threads, (size_t)smem_cap * 8, band_off, band_idx, sorted_if_pos,
+               keys, ys, zs, scratch, smem_cap, big ? 1 : 0, ty, tz, n_nodes);
+    PPP_CHECK_LAUNCH();
+  } else {
+    const int max_B = big ? (int)cap1 : 2147483647;
+    const size_t smem = (size_t)chunk_cap * 8;
+    const unsigned grid = (unsigned)S * (unsigned)C;
+    if (C == 2) {
+      auto kern = k_slice_order_cl<2>;
+      if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PPP_LAUNCH(ctx, "slice_order", kern, grid, SO_THREADS, smem, band_off, band_idx, sorted_if_pos, keys, ys, zs, scratch, chunk_cap, S, -1, max_B, ty, tz, n_nodes);
+    } else if (C == 4) {
+      auto kern = k_slice_order_cl<4>;
+      if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PPP_LAUNCH(ctx, "slice_order", kern, grid, SO_THREADS, smem, band_off, band_idx, sorted_if_pos, keys, ys, zs, scratch, chunk_cap, S, -1, max_B, ty, tz, n_nodes);
+    } else {
+      auto kern = k_slice_order_cl<8>;
+      if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PPP_LAUNCH(ctx, "slice_order", kern, grid, SO_THREADS, smem, band_off, band_idx, sorted_if_pos, keys, ys, zs, scratch, chunk_cap, S, -1, max_B, ty, tz, n_nodes);
+    }
+    PPP_CHECK_LAUNCH();
+  }
+  if (!big) return PPP_OK;
+  // the bands beyond cap1
+  auto kern = k_slice_order_cl<8>;
+  const size_t smem = (size_t)SOC_CHUNK_MAX * 8;
+  PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned clusters = (unsigned)std::min(S, 16);
+  PPP_LAUNCH(ctx, "slice_order_big", kern, clusters * 8u, SO_THREADS, smem, band_off, band_idx, sorted_if_pos, keys, ys, zs, scratch,
+             SOC_CHUNK_MAX, S, (int)cap1, 2147483647, ty, tz, n_nodes);
+  PPP_CHECK_LAUNCH();
+  return PPP_OK;
+}
+
 static int finish_nodes(ppp_cloud* c, int S, const int64_t* band_off_dev, const float* planes_dev, const int32_t* n_nodes,
                         const double* ty, const double* tz, int64_t* total_nodes_out) {
   ppp_ctx* ctx = c->ctx;
@@ -927,18 +1149,10 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
     }
     int64_t maxB = 0;
     for (int s = 0; s < S; s++) maxB = std::max(maxB, band_off_host[s + 1] - band_off_host[s]);
-    int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(maxB, 1), 24576);  // <= 192 KB of u64
     u64* scratch = nullptr;
-    if (maxB > smem_cap) PPP_TRY(dev_alloc(ctx, &scratch, M));
-    if (S > 0) {
-      if ((size_t)smem_cap * 8 > 48 * 1024)
-        PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
-      // short bands: 256 threads sort them with a quarter of the barrier traffic, and more slices share an SM
-      const int so_threads = maxB <= 4096 ? 256 : SO_THREADS;
-      PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, so_threads, (size_t)smem_cap * 8, band_off_dev, band_idx_dev,
-                 (const float4*)nullptr, (const u64*)P.keys, (const float*)P.ys, (const float*)P.zs, scratch, smem_cap, ty, tz, n_nodes);
-      PPP_CHECK_LAUNCH();
-    }
+    if (maxB > 24576) PPP_TRY(dev_alloc(ctx, &scratch, M));   // slices beyond every shared-memory path
+    PPP_TRY(launch_slice_order(ctx, S, maxB, false, band_off_dev, band_idx_dev, (const float4*)nullptr, (const u64*)P.keys, (const float*)P.ys,
+                               (const float*)P.zs, scratch, ty, tz, n_nodes));
     st = finish_nodes(c, S, band_off_dev, planes_dev, n_nodes, ty, tz, total_nodes_out);
     dev_free(ctx, P.keys); dev_free(ctx, P.ys); dev_free(ctx, P.zs); dev_free(ctx, scratch);
   } else {
@@ -1056,14 +1270,14 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
     PPP_CHECK_LAUNCH();
     // shared-memory capacity of the per-slice sort: the largest band of the previous call on this
     // cloud, else an estimate from the mean population of a band; larger bands sort in `scratch`
-    int64_t guess = c->max_band_hint > 0 ? c->max_band_hint + c->max_band_hint / 4 : 2 * (Mb / std::max(S, 1)) + 1024;
-    int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(guess, 1024), 24576);  // <= 192 KB of u64
-    if ((size_t)smem_cap * 8 > 48 * 1024)
-      PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
-    const int so_threads = smem_cap <= 4608 ? 256 : SO_THREADS;   // short bands (the guess covers the largest one seen so far)
-    PPP_LAUNCH(ctx, "slice_order", k_slice_order, (unsigned)S, so_threads, (size_t)smem_cap * 8, (const int64_t*)bp.offsets,
-               (const int32_t*)idx, mp ? (const float4*)nullptr : gs.v.sorted, (const u64*)keys, (const float*)ys, (const float*)zs, scratch, smem_cap, ty, tz, n_nodes);
-    PPP_CHECK_LAUNCH();
+    // size of the largest band: that of the previous call on this cloud, else what a uniform spread of the points along
+    // x would put into the widest band (+50 %); whatever turns out larger goes to the cluster launch
+    const double ext_x = std::max((double)c->bmax[0] - (double)c->bmin[0], 1e-6);
+    const int64_t uniform = (int64_t)std::min((double)Mb, 1.5 * (double)c->n_finite * std::min(1.0, (double)bp.max_width / ext_x)) + 512;
+    int64_t guess = c->max_band_hint > 0 ? c->max_band_hint + c->max_band_hint / 4 : uniform;
+    // closed / steep workpieces (multi-projection index) have silhouette bands many times the mean
+    PPP_TRY(launch_slice_order(ctx, S, guess, mp != nullptr, (const int64_t*)bp.offsets, (const int32_t*)idx, mp ? (const float4*)nullptr : gs.v.sorted,
+                               (const u64*)keys, (const float*)ys, (const float*)zs, scratch, ty, tz, n_nodes));
     if (c->c_S_cap < S + 1) {
       dev_free(ctx, c->c_node_off);
       PPP_TRY(dev_alloc_keep(ctx, &c->c_node_off, (size_t)S + 1));

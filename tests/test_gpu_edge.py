@@ -620,3 +620,26 @@ def test_sync_free_slicing_corner_cases(ctx):
     o = o2.slice_contours(planes, "B")
     assert all(np.array_equal(a, b) for a, b in zip(g, o))
     g2.close()
+
+
+@pytest.mark.parametrize("cluster", [2, 4, 8])
+def test_slice_order_thread_block_clusters(ctx, cluster, monkeypatch):
+    """The cluster variant of the per-slice ordering (k_slice_order_cl: the node keys of a slice spread over the
+    shared memories of 2, 4 or 8 CTAs, cross-CTA compare-exchange steps through distributed shared memory):
+    short bands (all keys land in CTA 0's chunk), medium ones, bands beyond one CTA's shared memory, bands beyond the
+    cluster's capacity (CTA 0 alone, in global scratch), empty slices and equal-y runs -- identical to the oracle."""
+    monkeypatch.setenv("PPP_SLICE_CLUSTER", str(cluster))
+    c = synth.panel(200000, 51)
+    c[::7, 1] = np.round(c[::7, 1])          # repeated y values -> equal-y runs in the node keys
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    mn, mx = oc.minmax()
+    for planes, hw in ((synth.even_planes(c, 40), 2.0),                                               # ~1.8k members
+                       (np.array([mn[0] - 30.0, mn[0] + 60.0, mx[0] - 45.0], np.float32), 12.0),      # ~11k members, one empty slice
+                       (np.array([0.5 * (mn[0] + mx[0])], np.float32), 40.0),                         # ~36k members
+                       (np.array([0.5 * (mn[0] + mx[0]), mn[0] + 150.0], np.float32), 150.0)):        # ~135k members
+        for _ in range(2):                       # the second call sizes the launch from the first one's largest band
+            g = gc.slice_contours(planes, "B", half_width=hw)
+            o = oc.slice_contours(planes, "B", half_width=hw)
+            assert all(np.array_equal(a, b) for a, b in zip(g, o)), (cluster, hw)
+    gc.close()
