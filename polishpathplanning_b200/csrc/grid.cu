@@ -44,8 +44,10 @@ __global__ void k_bbox_init(BBoxAcc* acc) {
 // Pack stride-`sf` records to float4 (original order) and reduce the bounding box of the finite
 // points.  One pass over the raw cloud: 12 useful bytes of each record in, 16 out.
 __global__ void __launch_bounds__(256) k_pack_bbox(const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
-                                                   float4* __restrict__ xyz4, BBoxAcc* __restrict__ acc) {
+                                                   float4* __restrict__ xyz4, BBoxAcc* __restrict__ acc,
+                                                   float4* __restrict__ sub, int sub_shift) {
   pdl_prologue();
+  const int64_t sub_mask = ((int64_t)1 << sub_shift) - 1;   // every 2^sub_shift-th point also goes to the compact subsample
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
   float mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
   unsigned cnt = 0;
@@ -71,7 +73,9 @@ __global__ void __launch_bounds__(256) k_pack_bbox(const float* __restrict__ raw
       int64_t i = base + (int64_t)j * blockDim.x + threadIdx.x;
       if (i >= n) continue;
       bool fin = finite3(x[j], y[j], z[j]);
-      xyz4[i] = make_float4(x[j], y[j], z[j], fin ? 0.0f : CUDART_NAN_F);
+      const float4 rec = make_float4(x[j], y[j], z[j], fin ? 0.0f : CUDART_NAN_F);
+      xyz4[i] = rec;
+      if (sub && (i & sub_mask) == 0) sub[i >> sub_shift] = rec;
       if (fin) {
         cnt++;
         mn[0] = fminf(mn[0], x[j]); mx[0] = fmaxf(mx[0], x[j]);
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(GridView g, const float4* 
 }
 
 // Surface density around a sample of the points: block b takes point b * stride_s of the cloud and looks at
-// every stride_m-th point.  Each thread keeps the two smallest squared distances it meets -- in space, and in
+// every 2^shift-th point (the compact subsample k_pack_bbox wrote on its way through the cloud).  Each thread keeps the two smallest squared distances it meets -- in space, and in
 // projection onto the two axes of largest extent (the primary column grid); the 8th smallest of the block's 512
 // values of either kind is (almost always exactly) the 8th nearest point of the subsample.  The 3-D value gives
 // the surface density whatever the shape; the ratio of the two says how the surface projects: ~1 for a height
@@ -198,7 +202,7 @@ struct IngestScratch {
 };
 
 __global__ void __launch_bounds__(DS_THREADS) k_density_sample(const float4* __restrict__ xyz4, int64_t n, int64_t stride_s,
-                                                               int64_t stride_m, IngestScratch* __restrict__ scr, int S,
+                                                               const float4* __restrict__ sub, int m, IngestScratch* __restrict__ scr, int S,
                                                                unsigned* __restrict__ host_out, unsigned* __restrict__ host_flag,
                                                                unsigned seq) {
   pdl_prologue();
@@ -218,13 +222,13 @@ __global__ void __launch_bounds__(DS_THREADS) k_density_sample(const float4* __r
   const bool qfin = q.w == q.w;
   float d0 = CUDART_INF_F, d1 = CUDART_INF_F, p0 = CUDART_INF_F, p1 = CUDART_INF_F;
   if (qfin) {
-    constexpr int PPT = 4;   // independent (scattered) loads in flight per thread
-    for (int64_t j0 = (int64_t)threadIdx.x * stride_m; j0 < n; j0 += (int64_t)DS_THREADS * PPT * stride_m) {
+    constexpr int PPT = 8;   // independent loads in flight per thread (the subsample is compact: coalesced lines from L2)
+    for (int j0 = (int)threadIdx.x; j0 < m; j0 += DS_THREADS * PPT) {
       float4 p[PPT];
 #pragma unroll
       for (int u = 0; u < PPT; u++) {
-        const int64_t j = j0 + (int64_t)u * DS_THREADS * stride_m;
-        p[u] = j < n ? __ldg(xyz4 + j) : make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        const int j = j0 + u * DS_THREADS;
+        p[u] = j < m ? __ldg(sub + j) : make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
       }
 #pragma unroll
       for (int u = 0; u < PPT; u++) {
@@ -324,27 +328,32 @@ int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes) {
   std::vector<float> ds_h((size_t)2 * DS_SAMPLES, NAN);
   for (int d = 0; d < 3; d++) { h.mn[d] = 0xFFFFFFFFu; h.mx[d] = 0u; }
   h.n_finite = 0ull;
-  const int64_t ds_m = std::min<int64_t>(c->n, 16384);                 // subsample every block searches
-  const int64_t stride_m = ds_m > 0 ? std::max<int64_t>(1, c->n / ds_m) : 1;
+  // subsample every block searches: every 2^shift-th point, 8192 .. 16383 of them (all points of a smaller cloud)
+  int sub_shift = 0;
+  while ((c->n >> sub_shift) >= 16384) sub_shift++;
+  const int64_t stride_m = (int64_t)1 << sub_shift;
+  const int sub_m = (int)((c->n + stride_m - 1) >> sub_shift);
   const int ds_s = (int)std::min<int64_t>(DS_SAMPLES, c->n);
   const int64_t stride_s = ds_s > 0 ? std::max<int64_t>(1, c->n / ds_s) : 1;
   if (c->n > 0) {
+    constexpr size_t SUB_BYTES = (size_t)16384 * sizeof(float4);
     if (!ctx->ingest_dev) {
-      PPP_CUDA(cudaMalloc(&ctx->ingest_dev, sizeof(IngestScratch)));
+      PPP_CUDA(cudaMalloc(&ctx->ingest_dev, SUB_BYTES + sizeof(IngestScratch)));   // [subsample][scratch]
       ctx->ingest_clean = false;
     }
-    IngestScratch* scr = (IngestScratch*)ctx->ingest_dev;
+    float4* sub = (float4*)ctx->ingest_dev;
+    IngestScratch* scr = (IngestScratch*)((char*)ctx->ingest_dev + SUB_BYTES);
     if (!ctx->ingest_clean) {
       PPP_LAUNCH(ctx, "bbox_init", k_bbox_init, 1, 1, 0, &scr->acc);
       PPP_CHECK_LAUNCH();
     }
     ctx->ingest_clean = false;   // until this ingest's last block has reset it
     int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((c->n + 1023) / 1024, (int64_t)ctx->sm_count * 16));
-    PPP_LAUNCH(ctx, "pack_bbox", k_pack_bbox, blocks, 256, 0, (const float*)pts_dev, c->n, sf, vec_ok, c->xyz4, &scr->acc);
+    PPP_LAUNCH(ctx, "pack_bbox", k_pack_bbox, blocks, 256, 0, (const float*)pts_dev, c->n, sf, vec_ok, c->xyz4, &scr->acc, sub, sub_shift);
     PPP_CHECK_LAUNCH();
     // surface density + projection quality from a sample; its last block delivers samples + bounding box to the host
     const unsigned seq = ++ctx->fetch_seq ? ctx->fetch_seq : ++ctx->fetch_seq;
-    PPP_LAUNCH(ctx, "density_sample", k_density_sample, ds_s, DS_THREADS, 0, (const float4*)c->xyz4, c->n, stride_s, stride_m,
+    PPP_LAUNCH(ctx, "density_sample", k_density_sample, ds_s, DS_THREADS, 0, (const float4*)c->xyz4, c->n, stride_s, (const float4*)sub, sub_m,
                scr, DS_SAMPLES, (unsigned*)ctx->fetch_host, (unsigned*)fetch_flag(ctx), seq);
     PPP_CHECK_LAUNCH();
     PPP_TRY(fetch_wait(ctx, seq));

@@ -27,6 +27,11 @@ struct BandSet {
   const float* hi;      // same order
   const int32_t* slice; // original slice number of sorted entry
   int S;
+  // A sweep with constant pitch (the usual case): lo[t] ~ lo0 + t * pitch and hi[t] ~ hi0 + t * pitch to within a
+  // quarter pitch (checked on the host).  The slices that can contain x then follow from two multiplications
+  // instead of two binary searches of log2(S) dependent loads each; the exact limits are re-tested either way.
+  int regular;
+  float lo0, hi0, inv_pitch;
 };
 
 // slices containing x form the contiguous sorted range [first hi >= x, first lo > x)
@@ -51,7 +56,16 @@ constexpr int BAND_SMEM_BINS = 12288;  // 48 KB of int32
 template <typename F>
 __device__ __forceinline__ void for_memberships(const BandSet& b, float x, F&& f) {
   int first, last;
-  band_range(b, x, first, last);
+  if (b.regular) {
+    // t with hi[t] >= x: t >= (x - hi0) / pitch;  t with lo[t] <= x: t <= (x - lo0) / pitch;  one slice of margin
+    // on either side covers the quarter-pitch tolerance and the rounding (non-finite x: empty range)
+    const float a = (x - b.hi0) * b.inv_pitch, c = (x - b.lo0) * b.inv_pitch;
+    if (!(a == a) || !(c == c)) return;
+    first = max((int)fminf(fmaxf(ceilf(a) - 1.0f, 0.0f), 2.0e9f), 0);
+    last = min((int)fminf(fmaxf(floorf(c) + 2.0f, 0.0f), 2.0e9f), b.S);
+  } else {
+    band_range(b, x, first, last);
+  }
   for (int t = first; t < last; t++) {
     // lo/hi are sorted together only when all bands have one width; re-test to stay exact otherwise
     if (x < __ldg(b.lo + t) || x > __ldg(b.hi + t)) continue;
@@ -954,7 +968,18 @@ static int bands_prepare(ppp_cloud* c, const float* plane_x_host, int S, float h
     PPP_CUDA(cudaMemcpyAsync(bp->fdev, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     PPP_CUDA(cudaMemcpyAsync(bp->pdev, perm.data(), (size_t)S * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
   }
-  bp->b = BandSet{bp->fdev + 3 * (size_t)S, bp->fdev + 4 * (size_t)S, bp->pdev, Sv};
+  bp->b = BandSet{bp->fdev + 3 * (size_t)S, bp->fdev + 4 * (size_t)S, bp->pdev, Sv, 0, 0.f, 0.f, 0.f};
+  if (Sv >= 8 && !getenv("PPP_BANDS_SEARCH")) {   // constant pitch?  (PPP_BANDS_SEARCH: always the binary searches)
+    const float* slo = stage.data() + 3 * (size_t)S;
+    const float* shi = stage.data() + 4 * (size_t)S;
+    const double pitch = ((double)slo[Sv - 1] - (double)slo[0]) / (double)(Sv - 1);
+    bool ok = pitch > 0 && std::isfinite(pitch);
+    for (int t = 0; ok && t < Sv; t++) {
+      ok = std::fabs((double)slo[t] - ((double)slo[0] + t * pitch)) <= 0.25 * pitch &&
+           std::fabs((double)shi[t] - ((double)shi[0] + t * pitch)) <= 0.25 * pitch;
+    }
+    if (ok) { bp->b.regular = 1; bp->b.lo0 = slo[0]; bp->b.hi0 = shi[0]; bp->b.inv_pitch = (float)(1.0 / pitch); }
+  }
   bp->Sv = Sv;
   bp->use_smem = Sv <= BAND_SMEM_BINS / 2;  // fill needs two arrays
   bp->blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((bp->n_src + 1023) / 1024, (int64_t)ctx->sm_count * 8));

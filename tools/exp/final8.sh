@@ -1,0 +1,16 @@
+set -x
+T=r02f
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+nvidia-smi -L | head -8
+PPP_CHECK_N=400000 timeout 300 $TR --nproc-per-node 8 --master-port 29601 tools/multi_gpu_check.py > gpurun_out/${T}_check8.log 2>&1; tail -3 gpurun_out/${T}_check8.log
+PPP_CHECK_N=400000 PPP_CHECK_K=32 timeout 300 $TR --nproc-per-node 4 --master-port 29602 tools/multi_gpu_check.py > gpurun_out/${T}_check4_k32.log 2>&1; tail -3 gpurun_out/${T}_check4_k32.log
+PPP_BENCH_VERBOSE=1 timeout 600 $TR --nproc-per-node 8 --master-port 29603 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/${T}_bench_8gpu.json 2> gpurun_out/${T}_bench_8gpu.err; grep "rank" gpurun_out/${T}_bench_8gpu.err | tail -16
+timeout 300 $TR --nproc-per-node 8 --master-port 29604 bench.py --impl reference --gpus 8 --steps 3 --warmup 1 > gpurun_out/${T}_bench_8gpu_ref.json 2>/dev/null
+PPP_BENCH_VERBOSE=1 timeout 400 $TR --nproc-per-node 4 --master-port 29605 bench.py --gpus 4 --steps 20 --warmup 5 --no-cfg3 > gpurun_out/${T}_bench_4gpu.json 2> gpurun_out/${T}_bench_4gpu.err
+PPP_BENCH_VERBOSE=1 timeout 400 $TR --nproc-per-node 2 --master-port 29606 bench.py --gpus 2 --steps 20 --warmup 5 --no-cfg3 > gpurun_out/${T}_bench_2gpu.json 2> gpurun_out/${T}_bench_2gpu.err
+timeout 600 $TR --nproc-per-node 8 --master-port 29607 tools/sweep_multi.py all > gpurun_out/${T}_sweep_8gpu.jsonl 2> gpurun_out/${T}_sweep_8gpu.err
+CUDA_VISIBLE_DEVICES=0,1,2,3 timeout 500 $TR --nproc-per-node 4 --master-port 29608 tools/sweep_multi.py cfg4 > gpurun_out/${T}_sweep_4gpu.jsonl 2> gpurun_out/${T}_sweep_4gpu.err &
+CUDA_VISIBLE_DEVICES=4,5 timeout 500 $TR --nproc-per-node 2 --master-port 29609 tools/sweep_multi.py cfg4 > gpurun_out/${T}_sweep_2gpu.jsonl 2> gpurun_out/${T}_sweep_2gpu.err &
+CUDA_VISIBLE_DEVICES=6 timeout 500 python tools/sweep_multi.py all > gpurun_out/${T}_sweep_1gpu.jsonl 2> gpurun_out/${T}_sweep_1gpu.err &
+wait
+wc -l gpurun_out/${T}_sweep_*.jsonl
