@@ -479,13 +479,12 @@ def measure_multi(env, cfg, steps, warmup, verify=True, e2e=True):
         t_s = time.perf_counter()
         ctx.timer_begin(1)
         ex.exchange(chunk_d.data_ptr(), n_r, 32, HALO_MM)
-        info = ex.finish()                                             # one synchronisation: slab size, cuts, x-range
+        # ONE synchronisation for the exchange AND the ingest of the received slab: slab size, cuts, x-range, bounding box
+        info, c = ex.finish_attach(to_rank0=not to_host)
         ctx.timer_end(1)
-        t_s = mark("exchange", t_s)
+        t_s = mark("exchange+attach", t_s)
         planes = make_planes(np.float32(info["x_range"][0]), np.float32(info["x_range"][1]), S)   # getMinMax3D -> sweep
         pos = parallel.owned_planes(planes, info["cuts"], rank)
-        c = ex.attach(to_rank0=not to_host)
-        t_s = mark("attach", t_s)
         if to_host:     # contour nodes + per-slice offsets straight into this rank's region of the host result
             base = dst.dev_base + region_host
             c.dev_set_contour_offsets_buffer(base, S + 1)

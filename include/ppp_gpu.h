@@ -274,6 +274,10 @@ void* ppp_exch_home_normals(ppp_exch* ex);        /* device: normal records of t
 /* The slab as a cloud whose normal estimators deliver each owned row's record to its home rank; with
  * to_rank0 != 0 ppp_dev_slice_contours also writes its nodes + per-slice offsets to rank 0's region.   */
 int ppp_exch_attach(ppp_exch* ex, int to_rank0, ppp_cloud** out);
+/* ppp_exch_finish followed by ppp_exch_attach, with one host synchronisation instead of two (the slab is ingested
+ * straight behind the exchange kernels; its size reaches the host together with the bounding box). */
+int ppp_exch_finish_attach(ppp_exch* ex, int to_rank0, int64_t* n_local, int64_t* n_owned, double* cuts, double x_range[2],
+                           ppp_cloud** out);
 int ppp_exch_nodes_region(ppp_exch* ex, int r, const int64_t** offsets_dev, const double** y_dev, const double** x_dev,
                           const double** z_dev);   /* rank 0: device pointers of rank r's contour region */
 /* what: PPP_EXCH_NORMALS / PPP_EXCH_CONTOURS.  signal: the results of that kind this rank has enqueued so

@@ -89,6 +89,7 @@ SIGNATURES = {
     "ppp_exch_row_map": (_vp, [_vp]),
     "ppp_exch_home_normals": (_vp, [_vp]),
     "ppp_exch_attach": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "ppp_exch_finish_attach": (C.c_int, [_vp, C.c_int, _i64p, _i64p, _f64p, _f64p, C.POINTER(_vp)]),
     "ppp_exch_nodes_region": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "ppp_exch_results_signal": (C.c_int, [_vp, C.c_int]),
     "ppp_exch_results_wait": (C.c_int, [_vp, C.c_int]),

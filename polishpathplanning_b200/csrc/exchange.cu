@@ -823,6 +823,60 @@ int ppp_exch_attach(ppp_exch* ex, int to_rank0, ppp_cloud** out) {
   return PPP_OK;
 }
 
+// ppp_exch_finish + ppp_exch_attach with ONE host synchronisation: the slab is ingested (pack, bounding box, density
+// sample) straight behind the exchange kernels, the kernels take its size from device memory, and the exchange summary
+// travels to the host with the ingest results.
+int ppp_exch_finish_attach(ppp_exch* ex, int to_rank0, int64_t* n_local, int64_t* n_owned, double* cuts, double x_range[2],
+                           ppp_cloud** out) {
+  if (!ex || !out) { ppp_set_error("ppp_exch_finish_attach: NULL argument"); return PPP_ERR_INVALID; }
+  ppp_ctx* ctx = ex->ctx;
+  EX_LOCK(ex);
+  PPP_CUDA(cudaSetDevice(ctx->device));
+  PPP_LAUNCH(ctx, "ex_wait", k_ex_wait, 1, 32, 0, ex->V, 3, ex->step, -1, ex->sc);
+  const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((ex->cap_recv + 255) / 256, (int64_t)ctx->sm_count * 8));
+  PPP_LAUNCH(ctx, "ex_rowmap", k_ex_rowmap, blocks, 256, 0, ex->V, ex->sc, ex->rowmap);
+  PPP_CHECK_LAUNCH();
+  struct Summary {
+    double cutx[PPP_MAX_RANKS + 1];
+    double gmin, gmax, inv;
+    int32_t sendcnt[PPP_MAX_RANKS], sendown[PPP_MAX_RANKS];
+    long long n_local, n_owned;
+    int32_t err, pad;
+  } sum;
+  static_assert(offsetof(ExScratch, pad) + sizeof(int32_t) - offsetof(ExScratch, cutx) == sizeof(Summary), "summary mirrors the scratch tail");
+  ppp_cloud* c = new ppp_cloud();
+  c->ctx = ctx;
+  c->n = 0;
+  c->grids.reserve(48);
+  c->mps.reserve(16);
+  int st = cloud_ingest_ex(c, ex->arena + ex->L.recv, 16, ex->cap_recv, &ex->sc->n_local, (const char*)ex->sc + offsetof(ExScratch, cutx),
+                           sizeof(sum), &sum);
+  if (st == PPP_OK && sum.err) {
+    ppp_set_error(sum.err == 1 ? "ppp_exch_finish_attach: timed out waiting for a peer rank"
+                               : "ppp_exch_finish_attach: receive buffer too small (cap_recv %lld)", (long long)ex->cap_recv);
+    cudaMemsetAsync((char*)ex->sc + offsetof(ExScratch, err), 0, sizeof(int32_t), ctx->stream);
+    st = sum.err == 1 ? PPP_ERR_CUDA : PPP_ERR_CAPACITY;
+  }
+  if (st != PPP_OK) { ppp_cloud_free(c); return st; }
+  ex->n_local = sum.n_local;
+  if (n_local) *n_local = sum.n_local;
+  if (n_owned) *n_owned = sum.n_owned;
+  if (cuts) for (int r = 0; r <= ex->world; r++) cuts[r] = sum.cutx[r];
+  if (x_range) { x_range[0] = sum.gmin; x_range[1] = sum.gmax; }
+  c->nmap = ex->rowmap;
+  c->route = ex->route;
+  if (to_rank0) {
+    unsigned char* reg = ex->peer[0] + ex->L.nodes + (size_t)ex->rank * ex->L.node_region;
+    st = ppp_dev_set_contour_offsets_buffer(c, (int64_t*)reg, (int64_t)ex->S_cap + 1);
+    if (st == PPP_OK && ex->node_cap > 0)
+      st = ppp_dev_set_contour_buffers(c, (double*)(reg + ex->L.node_off_bytes), (double*)(reg + ex->L.node_off_bytes + ex->L.node_arr_bytes),
+                                       (double*)(reg + ex->L.node_off_bytes + 2 * ex->L.node_arr_bytes), ex->node_cap);
+    if (st != PPP_OK) { ppp_cloud_free(c); return st; }
+  }
+  *out = c;
+  return PPP_OK;
+}
+
 // Rank 0's view of rank r's contour region (device pointers into the own arena).
 int ppp_exch_nodes_region(ppp_exch* ex, int r, const int64_t** offsets, const double** y, const double** x, const double** z) {
   if (!ex || r < 0 || r >= ex->world) { ppp_set_error("ppp_exch_nodes_region: bad argument"); return PPP_ERR_INVALID; }

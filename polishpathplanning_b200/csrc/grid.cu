@@ -26,6 +26,13 @@ inline float ord2f(uint32_t u) {
   return f;
 }
 
+// Subsample of the density estimate: every 2^shift-th point, 8192 .. 16383 of them (all points of a smaller cloud).
+__host__ __device__ inline int ds_sub_shift(long long n) {
+  int sh = 0;
+  while ((n >> sh) >= 16384) sh++;
+  return sh;
+}
+
 struct BBoxAcc {
   uint32_t mn[3];
   uint32_t mx[3];
@@ -45,8 +52,13 @@ __global__ void k_bbox_init(BBoxAcc* acc) {
 // points.  One pass over the raw cloud: 12 useful bytes of each record in, 16 out.
 __global__ void __launch_bounds__(256) k_pack_bbox(const float* __restrict__ raw, int64_t n, int sf, int vec_ok,
                                                    float4* __restrict__ xyz4, BBoxAcc* __restrict__ acc,
-                                                   float4* __restrict__ sub, int sub_shift) {
+                                                   float4* __restrict__ sub, int sub_shift,
+                                                   const long long* __restrict__ n_dev) {
   pdl_prologue();
+  if (n_dev) {   // the point count is only known on the device (a slab the exchange has just received)
+    n = *n_dev;
+    sub_shift = ds_sub_shift(n);
+  }
   const int64_t sub_mask = ((int64_t)1 << sub_shift) - 1;   // every 2^sub_shift-th point also goes to the compact subsample
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
   float mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
@@ -204,10 +216,18 @@ struct IngestScratch {
 __global__ void __launch_bounds__(DS_THREADS) k_density_sample(const float4* __restrict__ xyz4, int64_t n, int64_t stride_s,
                                                                const float4* __restrict__ sub, int m, IngestScratch* __restrict__ scr, int S,
                                                                unsigned* __restrict__ host_out, unsigned* __restrict__ host_flag,
-                                                               unsigned seq) {
+                                                               unsigned seq, const long long* __restrict__ n_dev,
+                                                               const unsigned* __restrict__ extra_src, int extra_words) {
   pdl_prologue();
   __shared__ float s_d[2 * DS_THREADS], s_p[2 * DS_THREADS];
   __shared__ bool s_last;
+  if (n_dev) {   // point count known on the device only: the same choices cloud_ingest makes on the host
+    n = *n_dev;
+    const long long ds_s = n < (long long)gridDim.x ? n : (long long)gridDim.x;
+    stride_s = ds_s > 0 ? (n / ds_s > 1 ? n / ds_s : 1) : 1;
+    const int sh = ds_sub_shift(n);
+    m = (int)((n + ((long long)1 << sh) - 1) >> sh);
+  }
   const BBoxAcc* acc = &scr->acc;
   float* out = scr->samples;
   // the axis the primary grid does not span: smallest extent, ties drop z, then y (as cloud_ingest decides)
@@ -218,7 +238,8 @@ __global__ void __launch_bounds__(DS_THREADS) k_density_sample(const float4* __r
     if (ext[1] < ext[drop]) drop = 1;
     if (ext[0] < ext[drop]) drop = 0;
   }
-  const float4 q = __ldg(xyz4 + (int64_t)blockIdx.x * stride_s);
+  const bool has_q = (int64_t)blockIdx.x * stride_s < n;
+  const float4 q = has_q ? __ldg(xyz4 + (int64_t)blockIdx.x * stride_s) : make_float4(0.f, 0.f, 0.f, CUDART_NAN_F);
   const bool qfin = q.w == q.w;
   float d0 = CUDART_INF_F, d1 = CUDART_INF_F, p0 = CUDART_INF_F, p1 = CUDART_INF_F;
   if (qfin) {
@@ -261,6 +282,9 @@ __global__ void __launch_bounds__(DS_THREADS) k_density_sample(const float4* __r
   for (int i = threadIdx.x; i < 2 * S; i += blockDim.x) host_out[i] = ((int)(i % S) < (int)gridDim.x) ? vs[i] : 0x7FC00000u;
   const volatile unsigned* va = (const volatile unsigned*)&scr->acc;
   if (threadIdx.x < (int)(sizeof(BBoxAcc) / 4)) host_out[2 * S + threadIdx.x] = va[threadIdx.x];
+  // ... the point count, and whatever else the caller wants with the same hand-shake (the exchange's summary)
+  if (threadIdx.x == 0) { host_out[2 * S + 8] = (unsigned)((unsigned long long)n & 0xFFFFFFFFull); host_out[2 * S + 9] = (unsigned)((unsigned long long)n >> 32); }
+  for (int i = threadIdx.x; i < extra_words; i += blockDim.x) host_out[2 * S + 10 + i] = ((const volatile unsigned*)extra_src)[i];
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -318,24 +342,30 @@ __global__ void __launch_bounds__(256) k_mp_choose(G3 G, const float4* __restric
 }  // namespace
 
 int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes) {
+  return cloud_ingest_ex(c, pts_dev, stride_bytes, c->n, nullptr, nullptr, 0, nullptr);
+}
+
+// n_dev != nullptr: the point count lies in device memory (*n_dev <= n_cap, written by earlier work of the stream) and
+// reaches the host together with the ingest results -- c->n is set from it; `extra_bytes` of device memory at
+// extra_src travel with the same hand-shake into extra_out (multiples of 4).
+int cloud_ingest_ex(ppp_cloud* c, const void* pts_dev, size_t stride_bytes, int64_t n_cap, const long long* n_dev,
+                    const void* extra_src, size_t extra_bytes, void* extra_out) {
   ppp_ctx* ctx = c->ctx;
   int sf = (int)(stride_bytes / 4);
   int vec_ok = (stride_bytes % 16 == 0) && (((uintptr_t)pts_dev) % 16 == 0);
-  PPP_TRY(dev_alloc_keep(ctx, &c->xyz4, (size_t)c->n));
+  if (!n_dev) n_cap = c->n;
+  PPP_TRY(dev_alloc_keep(ctx, &c->xyz4, (size_t)n_cap));
   constexpr int DS_SAMPLES = 128;
   static_assert(offsetof(IngestScratch, ticket) == sizeof(BBoxAcc), "k_bbox_init zeroes the ticket behind the accumulator");
   BBoxAcc h;
   std::vector<float> ds_h((size_t)2 * DS_SAMPLES, NAN);
   for (int d = 0; d < 3; d++) { h.mn[d] = 0xFFFFFFFFu; h.mx[d] = 0u; }
   h.n_finite = 0ull;
-  // subsample every block searches: every 2^shift-th point, 8192 .. 16383 of them (all points of a smaller cloud)
-  int sub_shift = 0;
-  while ((c->n >> sub_shift) >= 16384) sub_shift++;
-  const int64_t stride_m = (int64_t)1 << sub_shift;
-  const int sub_m = (int)((c->n + stride_m - 1) >> sub_shift);
-  const int ds_s = (int)std::min<int64_t>(DS_SAMPLES, c->n);
-  const int64_t stride_s = ds_s > 0 ? std::max<int64_t>(1, c->n / ds_s) : 1;
-  if (c->n > 0) {
+  if (n_cap > 0) {
+    const int sub_shift = ds_sub_shift(n_cap);
+    const int sub_m = (int)((n_cap + ((int64_t)1 << sub_shift) - 1) >> sub_shift);
+    const int ds_blocks = (int)std::min<int64_t>(DS_SAMPLES, n_cap);
+    const int64_t stride_s0 = std::max<int64_t>(1, n_cap / ds_blocks);
     constexpr size_t SUB_BYTES = (size_t)16384 * sizeof(float4);
     if (!ctx->ingest_dev) {
       PPP_CUDA(cudaMalloc(&ctx->ingest_dev, SUB_BYTES + sizeof(IngestScratch)));   // [subsample][scratch]
@@ -348,19 +378,34 @@ int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes) {
       PPP_CHECK_LAUNCH();
     }
     ctx->ingest_clean = false;   // until this ingest's last block has reset it
-    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((c->n + 1023) / 1024, (int64_t)ctx->sm_count * 16));
-    PPP_LAUNCH(ctx, "pack_bbox", k_pack_bbox, blocks, 256, 0, (const float*)pts_dev, c->n, sf, vec_ok, c->xyz4, &scr->acc, sub, sub_shift);
+    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_cap + 1023) / 1024, (int64_t)ctx->sm_count * 16));
+    PPP_LAUNCH(ctx, "pack_bbox", k_pack_bbox, blocks, 256, 0, (const float*)pts_dev, n_cap, sf, vec_ok, c->xyz4, &scr->acc, sub, sub_shift, n_dev);
     PPP_CHECK_LAUNCH();
     // surface density + projection quality from a sample; its last block delivers samples + bounding box to the host
     const unsigned seq = ++ctx->fetch_seq ? ctx->fetch_seq : ++ctx->fetch_seq;
-    PPP_LAUNCH(ctx, "density_sample", k_density_sample, ds_s, DS_THREADS, 0, (const float4*)c->xyz4, c->n, stride_s, (const float4*)sub, sub_m,
-               scr, DS_SAMPLES, (unsigned*)ctx->fetch_host, (unsigned*)fetch_flag(ctx), seq);
+    const int extra_words = (int)(extra_bytes / 4);
+    PPP_LAUNCH(ctx, "density_sample", k_density_sample, ds_blocks, DS_THREADS, 0, (const float4*)c->xyz4, n_cap, stride_s0, (const float4*)sub, sub_m,
+               scr, DS_SAMPLES, (unsigned*)ctx->fetch_host, (unsigned*)fetch_flag(ctx), seq, n_dev, (const unsigned*)extra_src, extra_words);
     PPP_CHECK_LAUNCH();
     PPP_TRY(fetch_wait(ctx, seq));
     ctx->ingest_clean = true;
-    memcpy(ds_h.data(), ctx->fetch_host, ds_h.size() * sizeof(float));
-    memcpy(&h, (const char*)ctx->fetch_host + ds_h.size() * sizeof(float), sizeof(h));
+    const char* pay = (const char*)ctx->fetch_host;
+    memcpy(ds_h.data(), pay, ds_h.size() * sizeof(float));
+    memcpy(&h, pay + ds_h.size() * sizeof(float), sizeof(h));
+    if (n_dev) {
+      long long n_real = 0;
+      memcpy(&n_real, pay + ds_h.size() * sizeof(float) + sizeof(h), sizeof(n_real));
+      c->n = std::min<int64_t>(std::max<long long>(n_real, 0), n_cap);
+    }
+    if (extra_out && extra_bytes) memcpy(extra_out, pay + ds_h.size() * sizeof(float) + sizeof(h) + 8, extra_bytes);
+  } else if (n_dev) {
+    c->n = 0;
+    if (extra_out && extra_bytes) PPP_TRY(fetch_small(ctx, extra_src, extra_bytes, extra_out));
   }
+  // the choices the kernels made from the point count
+  const int sub_shift = ds_sub_shift(c->n);
+  const int64_t stride_m = (int64_t)1 << sub_shift;
+  const int ds_s = (int)std::min<int64_t>(DS_SAMPLES, c->n);
   c->n_finite = (int64_t)h.n_finite;
   for (int d = 0; d < 3; d++) {
     // [upstream] getMinMax3D starts from +/-FLT_MAX; an all-non-finite cloud keeps those.

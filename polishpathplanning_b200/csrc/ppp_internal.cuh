@@ -304,6 +304,8 @@ int scan_exclusive_i32_to_i64(ppp_ctx* ctx, const int32_t* in, int64_t* out, int
 
 // grid.cu
 int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes);
+int cloud_ingest_ex(ppp_cloud* c, const void* pts_dev, size_t stride_bytes, int64_t n_cap, const long long* n_dev,
+                    const void* extra_src, size_t extra_bytes, void* extra_out);
 int cloud_get_grid(ppp_cloud* c, double h, GridStore** out);               // primary projection
 int cloud_get_grid_drop(ppp_cloud* c, double h, int drop, GridStore** out);
 // Decides (once per cloud, one synchronisation) whether the primary column grid `g` piles points up; afterwards

@@ -1043,8 +1043,8 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
 }
 
 // Orders the nodes of every slice, in two launches that split the slices by band size:
-//   1. one CTA per slice (k_slice_order) -- or, when a sweep has fewer slices than the GPU has SMs, a cluster of 2 / 4
-//      CTAs per slice -- for the bands up to cap1 members, sized from `band_est`;
+//   1. one CTA per slice (k_slice_order) -- or, when a sweep has at most half as many slices as the GPU has SMs, a
+//      cluster of 2 / 4 / 8 CTAs per slice -- for the bands up to cap1 members, sized from `band_est`;
 //   2. a few persistent clusters of 8 CTAs (k_slice_order_cl<8>, 128 KB of keys per CTA) for the bands beyond cap1:
 //      the silhouette bands of a closed workpiece, a flat face parallel to the planes.  Only launched when such bands
 //      are to be expected (`expect_big`, or an estimate beyond cap1); otherwise the first launch sorts a band that
@@ -1056,7 +1056,10 @@ static int launch_slice_order(ppp_ctx* ctx, int S, int64_t band_est, bool expect
   if (S <= 0) return PPP_OK;
   band_est = std::max<int64_t>(band_est, 1);
   int C = 1;
-  if (band_est >= 4096 && band_est <= 4 * (int64_t)SOC_CHUNK_MAX) C = S * 2 <= ctx->sm_count ? 4 : (S <= ctx->sm_count ? 2 : 1);
+  // clusters pay while all of them fit the GPU at once (measured, slices x members -> best C: 25 x 4k -> 4, 71 x 11k -> 2,
+  // 100 x 5.6k -> 1, 141 x 5.6k -> 1): the largest C with S * C CTAs on the SMs in one wave
+  if (band_est >= 4096 && band_est <= 4 * (int64_t)SOC_CHUNK_MAX)
+    while (C < 8 && S * C * 2 <= ctx->sm_count) C *= 2;
   if (const char* e = getenv("PPP_SLICE_CLUSTER")) {   // tuning / test aid: first launch with clusters of 1 / 2 / 4 / 8
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4 || v == 8) C = v;

@@ -232,6 +232,17 @@ class Exchange:
         self._api.check(self.lib.ppp_exch_attach(self._h, int(bool(to_rank0)), C.byref(h)))
         return self._api.Cloud(self.ctx, handle=h)
 
+    def finish_attach(self, to_rank0=True):
+        """finish() + attach() with one host synchronisation; returns (info, cloud)."""
+        nl, no = C.c_int64(0), C.c_int64(0)
+        cuts = np.zeros(self.world + 1, np.float64)
+        xr = np.zeros(2, np.float64)
+        h = C.c_void_p()
+        self._api.check(self.lib.ppp_exch_finish_attach(self._h, int(bool(to_rank0)), C.byref(nl), C.byref(no),
+                                                        cuts.ctypes.data_as(C.POINTER(C.c_double)),
+                                                        xr.ctypes.data_as(C.POINTER(C.c_double)), C.byref(h)))
+        return ({"n_local": nl.value, "n_owned": no.value, "cuts": cuts, "x_range": xr}, self._api.Cloud(self.ctx, handle=h))
+
     NORMALS, CONTOURS = 0, 1
 
     def results_signal(self, what):

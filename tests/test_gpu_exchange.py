@@ -87,10 +87,12 @@ def test_exchange_receive_overflow_is_reported():
         c.close()
 
 
-@pytest.mark.parametrize("world,stride", [(3, 32), (4, 16)])
-def test_sharded_pipeline_equals_single_cloud(world, stride):
+@pytest.mark.parametrize("world,stride,combined", [(3, 32, False), (4, 16, False), (3, 32, True), (2, 16, True)])
+def test_sharded_pipeline_equals_single_cloud(world, stride, combined):
     """Exchange -> per-slab kNN + normals (records delivered to their home rank) -> contours of the owned
-    planes (delivered to rank 0's regions) == the same calls on the whole cloud, bit for bit."""
+    planes (delivered to rank 0's regions) == the same calls on the whole cloud, bit for bit.  combined: the
+    one-synchronisation ppp_exch_finish_attach (slab size read from device memory by the ingest kernels) instead of
+    ppp_exch_finish + ppp_exch_attach."""
     import torch
     from polishpathplanning_b200 import api, parallel, synth
     n, k, halo, S = 120000, 16, 12.0, 24
@@ -114,10 +116,17 @@ def test_sharded_pipeline_equals_single_cloud(world, stride):
         full = api.Cloud(ref_ctx, cloud)
         ref_n, ref_i = full.normals_knn(k, stride_floats=stride // 4, return_idx=True)
         ro, ry, rx, rz = full.slice_contours(planes, "B")
-        infos = _run_exchange(exs, chunks, halo, 32)
+        if combined:
+            for p in range(4):                          # several ranks in one process: phase by phase
+                for ex, ch in zip(exs, chunks):
+                    ex.phase(p, ch.data_ptr(), ch.shape[0], 32, halo)
+            both = [ex.finish_attach(to_rank0=True) for ex in exs]
+            infos = [b[0] for b in both]
+        else:
+            infos = _run_exchange(exs, chunks, halo, 32)
         clouds, pos, idx = [], [], []
         for r in range(world):
-            c = exs[r].attach(to_rank0=True)
+            c = both[r][1] if combined else exs[r].attach(to_rank0=True)
             clouds.append(c)
             idx.append(torch.empty((infos[r]["n_local"], k), dtype=torch.int32, device="cuda:0"))
             c.dev_normals_knn(k, exs[r].home_normals_ptr, stride, idx_ptr=idx[r].data_ptr())

@@ -37,8 +37,7 @@ def main():
         chunk = torch.from_numpy(cloud[a:b].copy()).to(dev)
         torch.cuda.synchronize()
         ex.exchange(chunk.data_ptr(), b - a, 32, halo)
-        info = ex.finish()
-        c = ex.attach(to_rank0=True)
+        info, c = ex.finish_attach(to_rank0=True)
         nl = info["n_local"]
         idx = torch.empty((nl, k), dtype=torch.int32, device=dev)
         d2 = torch.empty((nl, k), dtype=torch.float32, device=dev)

@@ -28,9 +28,13 @@ def main(path):
         for k in KEYS:
             if k in d:
                 print("  %-70s %14s %s" % (k, d[k][1], d[k][0]))
-        rd = float(d["dram__bytes_read.sum"][1]) if "dram__bytes_read.sum" in d else 0
-        wr = float(d["dram__bytes_write.sum"][1]) if "dram__bytes_write.sum" in d else 0
-        print("  %-70s %14.3f %s" % ("dram traffic (read+write)", rd + wr, d["dram__bytes_read.sum"][0]))
+        def mbytes(key):
+            if key not in d:
+                return 0.0
+            unit, val = d[key]
+            scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(unit, 1.0)
+            return float(val) * scale
+        print("  %-70s %14.3f %s" % ("dram traffic (read+write)", mbytes("dram__bytes_read.sum") + mbytes("dram__bytes_write.sum"), "Mbyte"))
         stalls = sorted(((float(v[1] or 0), k) for k, v in d.items()
                          if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("per_issue_active.ratio")), reverse=True)
         print("  top stalls (warps stalled per issue): " + ", ".join(
