@@ -1577,11 +1577,17 @@ __global__ void __launch_bounds__(WARPQ_WARPS * 32) k_knn_warp(SearchParams P) {
       float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       const bool shifted = (P.flags & PPP_COV_SHIFTED) != 0;
       float kx = 0.f, ky = 0.f, kz = 0.f;
-      const int my_idx = mine != PPP_KEY_INF ? key_idx(mine) : 0;
-      const int my_idx2 = mine2 != PPP_KEY_INF ? key_idx(mine2) : 0;
+      // every lane fetches ITS neighbour's record (one memory latency for all of them); the accumulation then walks
+      // the list through shuffles -- sixteen dependent loads in a row were a third of this latency-bound kernel
+      float4 rec = make_float4(0.f, 0.f, 0.f, 0.f), rec2 = rec;
+      if (mine != PPP_KEY_INF) rec = __ldg(P.xyz4 + key_idx(mine));
+      if (mine2 != PPP_KEY_INF) rec2 = __ldg(P.xyz4 + key_idx(mine2));
       for (int j = 0; j < have; j++) {
-        int idx = __shfl_sync(0xffffffffu, j < 32 ? my_idx : my_idx2, j & 31);
-        float4 a = __ldg(P.xyz4 + idx);
+        const bool lo32 = j < 32;
+        float4 a;
+        a.x = __shfl_sync(0xffffffffu, lo32 ? rec.x : rec2.x, j & 31);
+        a.y = __shfl_sync(0xffffffffu, lo32 ? rec.y : rec2.y, j & 31);
+        a.z = __shfl_sync(0xffffffffu, lo32 ? rec.z : rec2.z, j & 31);
         if (shifted && j == 0) { kx = a.x; ky = a.y; kz = a.z; }
         float x = a.x, y = a.y, z = a.z;
         if (shifted) { x = __fsub_rn(x, kx); y = __fsub_rn(y, ky); z = __fsub_rn(z, kz); }

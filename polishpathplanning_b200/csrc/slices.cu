@@ -858,8 +858,10 @@ struct NodeDest {
 
 __global__ void __launch_bounds__(256) k_compact_nodes_auto(const int64_t* __restrict__ band_off, const int64_t* __restrict__ node_off,
                                                            int S, const float* __restrict__ planes, const double* __restrict__ ty,
-                                                           const double* __restrict__ tz, NodeDest D, int64_t* __restrict__ summary) {
+                                                           const double* __restrict__ tz, NodeDest D, int64_t* __restrict__ summary,
+                                                           unsigned* __restrict__ host_out, unsigned* __restrict__ host_flag, unsigned seq) {
   pdl_prologue();
+  __shared__ bool s_last;
   const int s = blockIdx.x;
   const int64_t total = node_off[S];
   const bool ext = D.ey && total <= D.ecap;
@@ -880,6 +882,19 @@ __global__ void __launch_bounds__(256) k_compact_nodes_auto(const int64_t* __res
     atomicMax((unsigned long long*)(summary + 2), (unsigned long long)(band_off[s + 1] - so));
     if (s == 0) { summary[0] = total; summary[1] = band_off[S]; summary[3] = ext ? 1 : 0; }
   }
+  if (!host_out) return;
+  // The last block to finish hands the summary to the host itself (mapped memory + flag, as cloud_ingest does): no
+  // fetch kernel at the end of the chain.  Node stores may go to page-locked host memory: system-scope fence in every block.
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd((unsigned long long*)(summary + 4), 1ull) == (unsigned long long)gridDim.x - 1ull;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < 8) host_out[threadIdx.x] = ((const volatile unsigned*)summary)[threadIdx.x];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) *(volatile unsigned*)host_flag = seq;
 }
 
 }  // namespace
@@ -1285,8 +1300,8 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
     PPP_TRY(dev_alloc(ctx, &n_nodes, (size_t)S));
     PPP_TRY(dev_alloc(ctx, &keys, M)); PPP_TRY(dev_alloc(ctx, &ys, M)); PPP_TRY(dev_alloc(ctx, &zs, M));
     PPP_TRY(dev_alloc(ctx, &scratch, M));
-    PPP_TRY(dev_alloc(ctx, &summary, 4));
-    PPP_CUDA(cudaMemsetAsync(summary, 0, 4 * sizeof(int64_t), ctx->stream));
+    PPP_TRY(dev_alloc(ctx, &summary, 5));   // {nodes, members, largest band, used caller's buffers, ticket}
+    PPP_CUDA(cudaMemsetAsync(summary, 0, 5 * sizeof(int64_t), ctx->stream));
     const float* planes_dev = bp.fdev;
     PairParams P{};
     set_grids(P, gs, mp); P.xyz4 = c->xyz4;
@@ -1319,11 +1334,14 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
       c->c_cap = Mb;
     }
     NodeDest D{c->ext_y, c->ext_x, c->ext_z, c->ext_y ? c->ext_cap : 0, c->c_y, c->c_x, c->c_z, c->ext_off, c->ext_off_cap};
+    const unsigned seq = ++ctx->fetch_seq ? ctx->fetch_seq : ++ctx->fetch_seq;
     PPP_LAUNCH(ctx, "compact_nodes", k_compact_nodes_auto, (unsigned)S, 256, 0, (const int64_t*)bp.offsets,
-               (const int64_t*)c->c_node_off, S, planes_dev, (const double*)ty, (const double*)tz, D, summary);
+               (const int64_t*)c->c_node_off, S, planes_dev, (const double*)ty, (const double*)tz, D, summary,
+               (unsigned*)ctx->fetch_host, (unsigned*)fetch_flag(ctx), seq);
     PPP_CHECK_LAUNCH();
     int64_t h[4] = {0, 0, 0, 0};
-    PPP_TRY(fetch_small(ctx, summary, sizeof(h), h));   // the one synchronisation of the chain
+    PPP_TRY(fetch_wait(ctx, seq));                       // the one synchronisation of the chain
+    memcpy(h, ctx->fetch_host, sizeof(h));
     const bool ext = h[3] != 0;
     c->out_y = ext ? c->ext_y : c->c_y;
     c->out_x = ext ? c->ext_x : c->c_x;
