@@ -404,6 +404,9 @@ int ppp_dev_download(ppp_ctx* ctx, void* host_dst, const void* dev_src, size_t b
 
 const int32_t* ppp_dev_sorted_order(ppp_cloud* c) {
   if (!c || c->grids.empty()) return nullptr;
+  ApiScope scope(c->ctx);
+  if (cudaSetDevice(c->ctx->device) != cudaSuccess) return nullptr;
+  if (grid_sorted_order(c, c->grids.back()) != PPP_OK) return nullptr;
   return c->grids.back().order;
 }
 

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) k_cell_count(GridView g, const float4* __
 // counts[] still holds the histogram; each point claims slot start[c] + (--counts[c]).
 __global__ void __launch_bounds__(256) k_cell_scatter(GridView g, const float4* __restrict__ xyz4, int64_t n,
                                                       int32_t* __restrict__ counts, const int32_t* __restrict__ start,
-                                                      float4* __restrict__ sorted, int32_t* __restrict__ order) {
+                                                      float4* __restrict__ sorted) {
   pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -162,7 +162,14 @@ __global__ void __launch_bounds__(256) k_cell_scatter(GridView g, const float4* 
   int c = cell_of(g, p.x, p.y, p.z);
   int slot = __ldg(start + c) + atomicSub(counts + c, 1) - 1;
   sorted[slot] = make_float4(p.x, p.y, p.z, __int_as_float((int)i));
-  order[slot] = (int)i;
+}
+
+// original index per sorted position as a plain array (ppp_dev_sorted_order; built on request only: the record's w
+// carries the same number, and a second scattered store per point cost the index build 10 %)
+__global__ void __launch_bounds__(256) k_extract_order(const float4* __restrict__ sorted, int64_t n, int32_t* __restrict__ order) {
+  pdl_prologue();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) order[i] = __float_as_int(__ldg(&sorted[i].w));
 }
 
 // Surface density around a sample of the points: block b takes point b * stride_s of the cloud and looks at
@@ -510,7 +517,6 @@ int cloud_get_grid_drop(ppp_cloud* c, double h, int drop, GridStore** out) {
   v.n_sorted = (int)c->n_finite;
   int64_t ncells = (int64_t)v.nu * v.nv;
   PPP_TRY(dev_alloc_keep(ctx, &gs.sorted, (size_t)std::max<int64_t>(c->n_finite, 1) + PPP_SORTED_PAD));
-  PPP_TRY(dev_alloc_keep(ctx, &gs.order, (size_t)std::max<int64_t>(c->n_finite, 1)));
   PPP_TRY(dev_alloc_keep(ctx, &gs.cell_start, (size_t)ncells + 1));
   int32_t* counts = nullptr;
   PPP_TRY(dev_alloc(ctx, &counts, (size_t)ncells));
@@ -526,7 +532,7 @@ int cloud_get_grid_drop(ppp_cloud* c, double h, int drop, GridStore** out) {
   if (c->n > 0) {
     unsigned blocks = (unsigned)((c->n + 255) / 256);
     PPP_LAUNCH(ctx, "cell_scatter", k_cell_scatter, blocks, 256, 0, v, (const float4*)c->xyz4, c->n, counts,
-               (const int32_t*)gs.cell_start, gs.sorted, gs.order);
+               (const int32_t*)gs.cell_start, gs.sorted);
     PPP_CHECK_LAUNCH();
   }
   dev_free(ctx, counts);
@@ -573,6 +579,18 @@ int cloud_get_mp(ppp_cloud* c, double h, int R0, MPSet** out) {
   PPP_CUDA(cudaEventRecord(m.ready, ctx->stream));
   c->mps.push_back(m);
   *out = &c->mps.back();
+  return PPP_OK;
+}
+
+int grid_sorted_order(ppp_cloud* c, GridStore& gs) {
+  if (gs.order) return PPP_OK;
+  ppp_ctx* ctx = c->ctx;
+  const int64_t n = gs.v.n_sorted;
+  PPP_TRY(dev_alloc_keep(ctx, &gs.order, (size_t)std::max<int64_t>(n, 1)));
+  if (n > 0) {
+    PPP_LAUNCH(ctx, "extract_order", k_extract_order, (unsigned)((n + 255) / 256), 256, 0, (const float4*)gs.sorted, n, gs.order);
+    PPP_CHECK_LAUNCH();
+  }
   return PPP_OK;
 }
 

@@ -107,7 +107,7 @@ struct GridStore {
   int drop = 2;              // the axis this grid does NOT span (2: cells over x, y)
   float4* sorted = nullptr;
   int32_t* cell_start = nullptr;
-  int32_t* order = nullptr;  // original index per sorted position
+  int32_t* order = nullptr;  // original index per sorted position (built on request: grid_sorted_order)
   double h = 0;
   cudaEvent_t ready = nullptr;  // recorded after the build: consumers on other streams wait on it
 };
@@ -307,6 +307,7 @@ int cloud_ingest(ppp_cloud* c, const void* pts_dev, size_t stride_bytes);
 int cloud_ingest_ex(ppp_cloud* c, const void* pts_dev, size_t stride_bytes, int64_t n_cap, const long long* n_dev,
                     const void* extra_src, size_t extra_bytes, void* extra_out);
 int cloud_get_grid(ppp_cloud* c, double h, GridStore** out);               // primary projection
+int grid_sorted_order(ppp_cloud* c, GridStore& gs);                        // builds gs.order on first request
 int cloud_get_grid_drop(ppp_cloud* c, double h, int drop, GridStore** out);
 // Decides (once per cloud, one synchronisation) whether the primary column grid `g` piles points up; afterwards
 // c->mp_state is 0 or 1.
