@@ -126,20 +126,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chained(const int32_t* __
   }
   int32_t tot;
   const int32_t ex = block_excl_scan<int32_t>(s, &tot);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // the first warp walks back over the predecessors' words 32 at a time: lane l looks at tile (base - l), the walk
+    // ends at the nearest inclusive prefix (a tile before the first counts as inclusive 0)
+    const int lane = threadIdx.x;
     int32_t prefix = 0;
     if (tile > 0) {
-      words[tile] = (1ull << 32) | (unsigned long long)(uint32_t)tot;
-      __threadfence();
-      for (int p = tile - 1; p >= 0; p--) {
-        unsigned long long w;
-        do { w = words[p]; } while ((w >> 32) == 0ull);
-        prefix += (int32_t)(uint32_t)w;
-        if ((w >> 32) == 2ull) break;
+      if (lane == 0) words[tile] = (1ull << 32) | (unsigned long long)(uint32_t)tot;
+      for (int base = tile - 1;; base -= 32) {
+        const int p = base - lane;
+        unsigned long long w = 2ull << 32;
+        if (p >= 0) { do { w = words[p]; } while ((w >> 32) == 0ull); }
+        const unsigned incl = __ballot_sync(0xffffffffu, (w >> 32) == 2ull);
+        const int stop = incl ? __ffs(incl) - 1 : 31;            // nearest inclusive prefix in this window
+        prefix += __reduce_add_sync(0xffffffffu, lane <= stop ? (int32_t)(uint32_t)w : 0);
+        if (incl) break;
       }
     }
-    words[tile] = (2ull << 32) | (unsigned long long)(uint32_t)(prefix + tot);
-    s_prefix = prefix;
+    if (lane == 0) {
+      words[tile] = (2ull << 32) | (unsigned long long)(uint32_t)(prefix + tot);
+      s_prefix = prefix;
+    }
   }
   __syncthreads();
   int32_t run = ex + s_prefix;
