@@ -46,6 +46,7 @@ METRIC = "points/sec kNN(k=16)+normals+slicing"
 UNIT = "points/s"
 HALF_WIDTH = 2.0
 HALO_MM = 12.0
+SETTLE_STEPS = 10         # untimed steps in front of the W warm-up steps (see timed_device_steps)
 PAIRING = "B"             # SectPath::insert_point (src/contour_alg.cpp:165-237)
 CPU_SAMPLE_MAX = 2_000_000   # --impl reference: points of the workload one CPU step processes
 
@@ -280,6 +281,10 @@ class Env:
 def timed_device_steps(env, step, steps, warmup):
     """W warm-up + K timed steps, each behind an L2 flush; CUDA events on the library's stream."""
     ctx = env.ctx
+    # settle first: the first steps of a process see one-off costs (memory pools growing to their working size, lazy
+    # module loads, clocks leaving idle) that have shown up as single steps of tens of milliseconds; then the W warm-ups
+    for _ in range(SETTLE_STEPS):
+        step()
     for _ in range(warmup):
         env.flush_l2(); step()
     env.sync_all()
@@ -404,7 +409,7 @@ def measure_single(env, cfg, steps, warmup, e2e=True):
         e2e_bytes["d2h"] = pin_normals.nbytes + off.nbytes + 3 * y.nbytes
         c.close()
 
-    for _ in range(min(warmup, 3)):
+    for _ in range(SETTLE_STEPS // 2 + min(warmup, 3)):
         host_step()
     env.sync_all()
     t0 = time.perf_counter()

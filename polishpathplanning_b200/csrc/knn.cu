@@ -656,19 +656,20 @@ __global__ void __launch_bounds__(BD, (BD == 128 ? 7 : (BD == 96 ? 9 : 13))) k_k
 // 2^23 (exact floor of the real product: monotone in d2).
 // ---------------------------------------------------------------------------------------------
 constexpr int F_SLOTS = 32;
-constexpr int F_RB = 7;                  // ordinal: 3 bits of block row (2R+1 <= 7), F_RB bits of slot in the row
-constexpr int F_ROWCAP = 1 << F_RB;      // candidates per cell row an ordinal can name; denser rows take the exact path
-constexpr int F_SH = 3 + F_RB;
-constexpr unsigned F_OMASK = (1u << F_SH) - 1u;
-constexpr unsigned F_FIXTOP = 1u << (32 - F_SH);   // fixed-point values stay below F_FIXTOP - 608
 constexpr int F_MAXR = 3;
-static_assert(F_ROWCAP + 4 <= PPP_SORTED_PAD, "unclamped candidate loads run up to F_ROWCAP + 3 records past a row");
+// RB (template parameter of k_knn16f): bits of the ordinal that name the slot inside a cell row (3 more name the row,
+// 2R+1 <= 7).  RB = 7: rows of up to 128 candidates, 22 bits of d2.
 
-template <int BD, int MB>
+template <int BD, int MB, int F_RB>
 __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
   pdl_prologue();
   extern __shared__ __align__(128) unsigned s_fkeys[];
   constexpr int K = 16;
+  constexpr int F_ROWCAP = 1 << F_RB;      // candidates per cell row an ordinal can name; denser rows take the exact path
+  constexpr int F_SH = 3 + F_RB;
+  constexpr unsigned F_OMASK = (1u << F_SH) - 1u;
+  constexpr unsigned F_FIXTOP = 1u << (32 - F_SH);   // fixed-point values stay below F_FIXTOP - 608
+  static_assert(F_ROWCAP + 4 <= PPP_SORTED_PAD, "unclamped candidate loads run up to F_ROWCAP + 3 records past a row");
   // A free slot j holds FREE(j): above every key (fixed-point values stop 608 below F_FIXTOP), and distinct in the
   // fixed-point bits from every other free slot, so free slots never look like an undecided pair.  Slots fill in
   // order, a flush keeps the smallest free values FREE(ns..15) exactly where they were: the invariant holds.
@@ -1957,9 +1958,12 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
     if (const char* e = getenv("PPP_KNN_BD")) { int v = atoi(e); if (v == 64 || v == 96 || v == 128) block = v; }
     size_t smem = fixed ? (size_t)(F_SLOTS + 2 * P.R0 + 1) * 4 * block : (size_t)C_SLOTS * 8 * block;
     static const bool more_regs = getenv("PPP_KNN16_REGS72") != nullptr;   // 72 instead of 64 registers per thread
-    auto kern = fixed ? (block == 128 ? (more_regs ? k_knn16f<128, 7> : k_knn16f<128, 8>)
-                                      : (block == 96 ? (more_regs ? k_knn16f<96, 9> : k_knn16f<96, 10>)
-                                                     : (more_regs ? k_knn16f<64, 14> : k_knn16f<64, 16>)))
+    // (RB = 9 -- rows of up to 512 candidates -- for workpieces with walls was measured and rejected: box with walls
+    // search 0.41 -> 0.72 ms for a hand-over kernel that only went 0.73 -> 0.53 ms: the warp-uniform row loops of the
+    // thread-per-query kernel pay for the longest row of 32 queries.)
+    auto kern = fixed ? (block == 128 ? (more_regs ? k_knn16f<128, 7, 7> : k_knn16f<128, 8, 7>)
+                                      : (block == 96 ? (more_regs ? k_knn16f<96, 9, 7> : k_knn16f<96, 10, 7>)
+                                                     : (more_regs ? k_knn16f<64, 14, 7> : k_knn16f<64, 16, 7>)))
                       : (block == 128 ? k_knn16c<128> : (block == 96 ? k_knn16c<96> : k_knn16c<64>));
     PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned blocks = (unsigned)((P.nq + block - 1) / block);
