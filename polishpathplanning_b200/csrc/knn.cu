@@ -1997,7 +1997,7 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
     PPP_CHECK_LAUNCH();
     st = PPP_OK;
   }
-  else if (P.cap <= 32 && !getenv("PPP_KNN32_OLD2")) {
+  else if (P.cap <= 32) {   // external query arrays (not in cell order), or PPP_KNN32_OLD: composite keys
     const int block = 64;
     size_t smem = (size_t)48 * 8 * block;
     auto kern = k_knn32c<64>;
@@ -2006,8 +2006,7 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
     PPP_CHECK_LAUNCH();
     st = PPP_OK;
   }
-  else if (P.cap <= 32) st = launch_knn_fast_k<32, 16, false>(c, P);
-  else st = launch_knn_fast_k<64, 16, false>(c, P);
+  else st = launch_knn_fast_k<64, 16, false>(c, P);   // external query arrays with 32 < k <= 64, or PPP_KNN64_OLD: 64-bit keys
   if (st == PPP_OK) {
     // hand-over queries: one warp each, persistent warps (their number is only known on the device)
     P.use_redo = 1;
