@@ -113,11 +113,12 @@ def load():
     """Load libppp_gpu.so; raises if it has not been built (python -m polishpathplanning_b200.build)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("PPP_GPU_LIB") or LIB_PATH   # PPP_GPU_LIB: the bounds-checked build (tests/test_gpu_bounds.py)
+        if not os.path.exists(path):
             raise ImportError(
                 "libppp_gpu.so is missing at %s. Build it with `python -m polishpathplanning_b200.build` "
-                "(nvcc, sm_100a). The hot path has no CPU / PyTorch fallback." % LIB_PATH)
-        L = C.CDLL(LIB_PATH)
+                "(nvcc, sm_100a). The hot path has no CPU / PyTorch fallback." % path)
+        L = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)  # AttributeError if the symbol is not exported
             fn.restype = res

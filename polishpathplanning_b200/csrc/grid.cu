@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(256) k_pack_bbox(const float* __restrict__ raw
       bool fin = finite3(x[j], y[j], z[j]);
       const float4 rec = make_float4(x[j], y[j], z[j], fin ? 0.0f : CUDART_NAN_F);
       xyz4[i] = rec;
+      PPP_DEV_ASSERT(!sub || (i >> sub_shift) < 16384);
       if (sub && (i & sub_mask) == 0) sub[i >> sub_shift] = rec;
       if (fin) {
         cnt++;
@@ -147,7 +148,9 @@ __global__ void __launch_bounds__(256) k_cell_count(GridView g, const float4* __
   if (i >= n) return;
   float4 p = __ldg(xyz4 + i);
   if (p.w != p.w) return;  // non-finite point: not indexed
-  atomicAdd(counts + cell_of(g, p.x, p.y, p.z), 1);
+  const int cell = cell_of(g, p.x, p.y, p.z);
+  PPP_DEV_ASSERT(cell >= 0 && cell < g.nu * g.nv);
+  atomicAdd(counts + cell, 1);
 }
 
 // counts[] still holds the histogram; each point claims slot start[c] + (--counts[c]).
@@ -161,6 +164,7 @@ __global__ void __launch_bounds__(256) k_cell_scatter(GridView g, const float4* 
   if (p.w != p.w) return;
   int c = cell_of(g, p.x, p.y, p.z);
   int slot = __ldg(start + c) + atomicSub(counts + c, 1) - 1;
+  PPP_DEV_ASSERT(c >= 0 && c < g.nu * g.nv && slot >= 0 && slot < g.n_sorted);
   sorted[slot] = make_float4(p.x, p.y, p.z, __int_as_float((int)i));
 }
 

@@ -665,6 +665,7 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
   pdl_prologue();
   extern __shared__ __align__(128) unsigned s_fkeys[];
   constexpr int K = 16;
+  constexpr int PPP_ASSERT_SLOTS = F_SLOTS;
   constexpr int F_ROWCAP = 1 << F_RB;      // candidates per cell row an ordinal can name; denser rows take the exact path
   constexpr int F_SH = 3 + F_RB;
   constexpr unsigned F_OMASK = (1u << F_SH) - 1u;
@@ -768,6 +769,7 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
 #pragma unroll 1
     for (int it = 0; it < n_it; it++, i0 += U, ord += U, rem -= U) {
       float4 c4[U];
+      PPP_DEV_ASSERT(i0 >= 0 && i0 + U - 1 < g.n_sorted + PPP_SORTED_PAD);
 #pragma unroll
       for (int u = 0; u < U; u++) c4[u] = __ldg(g.sorted + (i0 + u));   // never clamped: see PPP_SORTED_PAD
 #pragma unroll
@@ -776,6 +778,7 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
         if (u < rem && d2 <= tau) {
           // (bits << F_SH) + ordinal: the exponent bits of 2^23 leave at the top; one IMAD (+ an add of u)
           const unsigned key = __float_as_uint(__fmaf_rz(d2, scale, 8388608.0f)) * (1u << F_SH) + ord + (unsigned)u;
+          PPP_DEV_ASSERT(wsa >= keys_sa && wsa < keys_sa + (unsigned)(PPP_ASSERT_SLOTS) * SLOT_B);
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(wsa), "r"(key) : "memory");
           wsa += SLOT_B;
         }
@@ -829,7 +832,11 @@ __global__ void __launch_bounds__(BD, MB) k_knn16f(SearchParams P) {
       const unsigned key = keys[(jb + u) * BD];
       const bool has = jb + u < m;
       nb[u] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-      if (has) nb[u] = __ldg(g.sorted + (rows[((key >> F_RB) & 7u) * BD] + (int)(key & (unsigned)(F_ROWCAP - 1))));   // a free value names no row
+      if (has) {   // a free value names no row
+        const int rj = (int)((key >> F_RB) & 7u), pos = rows[rj * BD] + (int)(key & (unsigned)(F_ROWCAP - 1));
+        PPP_DEV_ASSERT(rj <= 2 * R && pos >= 0 && pos < g.n_sorted);
+        nb[u] = __ldg(g.sorted + pos);
+      }
     }
     if (io) {
       float dd[8];
@@ -1090,6 +1097,7 @@ __global__ void __launch_bounds__(BD, MB) k_knnf(SearchParams P) {
   pdl_prologue();
   extern __shared__ __align__(128) unsigned s_fkeys[];
   constexpr int SLOTS = K + NEW;
+  constexpr int PPP_ASSERT_SLOTS = SLOTS;
   constexpr int SH = 3 + RB;                        // ordinal bits: row of the block, slot in the row
   constexpr unsigned OMASK = (1u << SH) - 1u;
   constexpr unsigned FIXTOP = 1u << (32 - SH);      // fixed-point values stay below FIXTOP - 608
@@ -1193,6 +1201,7 @@ __global__ void __launch_bounds__(BD, MB) k_knnf(SearchParams P) {
 #pragma unroll 1
     for (int it = 0; it < n_it; it++, i0 += U, ord += U, rem -= U) {
       float4 c4[U];
+      PPP_DEV_ASSERT(i0 >= 0 && i0 + U - 1 < g.n_sorted + PPP_SORTED_PAD);
 #pragma unroll
       for (int u = 0; u < U; u++) c4[u] = __ldg(g.sorted + (i0 + u));   // never clamped: see PPP_SORTED_PAD
 #pragma unroll
@@ -1201,6 +1210,7 @@ __global__ void __launch_bounds__(BD, MB) k_knnf(SearchParams P) {
         if (u < rem && d2 <= tau) {
           // floor(d2 * scale) sits in the low mantissa bits of the sum; the multiplication shifts the exponent out
           const unsigned key = __float_as_uint(__fmaf_rz(d2, scale, 8388608.0f)) * (1u << SH) + ord + (unsigned)u;
+          PPP_DEV_ASSERT(wsa >= keys_sa && wsa < keys_sa + (unsigned)(PPP_ASSERT_SLOTS) * SLOT_B);
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(wsa), "r"(key) : "memory");
           wsa += SLOT_B;
         }
@@ -1242,7 +1252,9 @@ __global__ void __launch_bounds__(BD, MB) k_knnf(SearchParams P) {
       nb[u] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
       if (jb + u < m) {
         const unsigned key = keys[(jb + u) * BD];
-        nb[u] = __ldg(g.sorted + (rows[((key >> RB) & 7u) * BD] + (int)(key & (unsigned)(ROWCAP - 1))));
+        const int rj = (int)((key >> RB) & 7u), pos = rows[rj * BD] + (int)(key & (unsigned)(ROWCAP - 1));
+        PPP_DEV_ASSERT(rj <= 2 * R && pos >= 0 && pos < g.n_sorted);
+        nb[u] = __ldg(g.sorted + pos);
       }
     }
     if (io) {

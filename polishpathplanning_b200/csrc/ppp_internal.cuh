@@ -220,6 +220,23 @@ __device__ __forceinline__ void pdl_prologue() {
 #endif
 bool ppp_pdl_enabled();
 
+// Bounds-checked build (python -m polishpathplanning_b200.build --check -> libppp_gpu_check.so, loaded through
+// PPP_GPU_LIB): the index arithmetic of the kernels that read or write without clamping is asserted on the device and a
+// violation traps.  compute-sanitizer is not available on the measurement pool; tests/test_gpu_bounds.py runs a small
+// pass over every such kernel with this build instead.  In the normal build the macro expands to nothing.
+#ifdef PPP_CHECK_BOUNDS
+#define PPP_DEV_ASSERT(cond)                                                                                     \
+  do {                                                                                                           \
+    if (!(cond)) {                                                                                               \
+      printf("PPP_DEV_ASSERT failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, \
+             (int)threadIdx.x);                                                                                  \
+      __trap();                                                                                                  \
+    }                                                                                                            \
+  } while (0)
+#else
+#define PPP_DEV_ASSERT(cond) do { } while (0)
+#endif
+
 // `kernel` must be a plain identifier (bind template instantiations to a local `auto kern = ...`).
 #define PPP_LAUNCH(ctx, name, kernel, grid, block, smem, ...)                             \
   do {                                                                                    \

@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_chained(const int32_t* __
   if (threadIdx.x == 0) s_tile = (int)atomicAdd(state, 1ull);
   __syncthreads();
   const int tile = s_tile;
+  PPP_DEV_ASSERT(tile >= 0 && tile < tiles);
   volatile unsigned long long* words = state + 1;
   const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int32_t v[SCAN_ITEMS];

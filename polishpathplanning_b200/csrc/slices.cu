@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(256) k_band_fill(BandSet b, const float4* __re
     for_memberships(b, p.x, [&](int t) {
       int s = __ldg(b.slice + t);
       int pos = use_smem ? s_base[t] + atomicAdd(s_cnt + t, 1) : atomicAdd(cursor + s, 1);
+      PPP_DEV_ASSERT(pos >= 0 && offsets[s] + pos < offsets[s + 1]);
       idx_out[offsets[s] + pos] = (int32_t)i;
     });
   }
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(256) k_band_fill(BandSet b, const float4* __re
 // separated by __syncwarp only: 21 block-wide barriers for 2048 elements instead of 66.
 template <typename T>
 __device__ __forceinline__ void cta_sort_ce(T* a, int i, int l, int n) {
+  PPP_DEV_ASSERT(i >= 0 && i < l);
   if (l < n) { T x = a[i], y = a[l]; if (y < x) { a[i] = y; a[l] = x; } }
 }
 // Steps j0, j0 / 2, .., 1 of a merge over a[0 .. 2 * half) (n valid elements in front); ends with a block barrier.
@@ -638,7 +640,11 @@ __device__ void slice_order_single(const int64_t* __restrict__ band_off, const i
   // keep only the node keys (left members that found a pair); their order does not matter yet
   for (int i = threadIdx.x; i < B; i += blockDim.x) {
     u64 key = keys_g[o + i];
-    if (key != PPP_KEY_INF) k[atomicAdd(s_valid_p, 1)] = key;
+    if (key != PPP_KEY_INF) {
+      const int at = atomicAdd(s_valid_p, 1);
+      PPP_DEV_ASSERT(at >= 0 && at < B && (k != s_keys64 || at < smem_cap));
+      k[at] = key;
+    }
   }
   __syncthreads();
   const int nv = *s_valid_p;
@@ -668,6 +674,7 @@ __device__ void slice_order_single(const int64_t* __restrict__ band_off, const i
         if (id < lo_idx) { lo_idx = id; lo_slot = sl; }
         if (id > hi_idx) { hi_idx = id; hi_slot = sl; }
       }
+      PPP_DEV_ASSERT(r >= 0 && r < B && lo_slot >= 0 && lo_slot < B && hi_slot >= 0 && hi_slot < B);
       ty[o + r] = (double)ys[o + lo_slot];
       tz[o + r] = (double)zs[o + hi_slot];
     }
@@ -744,7 +751,10 @@ k_slice_order_cl(const int64_t* __restrict__ band_off, const int32_t* __restrict
     continue;                            // (the others wait for it at the next slice's first cluster barrier)
   }
   const int csh = 31 - __clz(chunk);
-  auto elem = [&](int g) -> u64* { return cl.map_shared_rank(s_arr, g >> csh) + (g & (chunk - 1)); };
+  auto elem = [&](int g) -> u64* {
+    PPP_DEV_ASSERT(g >= 0 && (g >> csh) < C && chunk <= chunk_cap);
+    return cl.map_shared_rank(s_arr, g >> csh) + (g & (chunk - 1));
+  };
   // the node keys (left members that found a pair) -> their place in the distributed array; order inside is arbitrary
   for (int i = b0 + threadIdx.x; i < b1; i += nt) {
     const u64 key = keys_g[o + i];
@@ -816,6 +826,7 @@ k_slice_order_cl(const int64_t* __restrict__ band_off, const int32_t* __restrict
         if (id < lo_idx) { lo_idx = id; lo_slot = sl; }
         if (id > hi_idx) { hi_idx = id; hi_slot = sl; }
       }
+      PPP_DEV_ASSERT(rnk >= 0 && rnk < B && lo_slot >= 0 && lo_slot < B && hi_slot >= 0 && hi_slot < B);
       ty[o + rnk] = (double)ys[o + lo_slot];
       tz[o + rnk] = (double)zs[o + hi_slot];
     }
