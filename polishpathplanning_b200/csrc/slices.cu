@@ -74,9 +74,12 @@ __device__ __forceinline__ void for_memberships(const BandSet& b, float x, F&& f
 }
 
 __global__ void __launch_bounds__(256) k_band_count(BandSet b, const float4* __restrict__ xyz4, int64_t n, int64_t chunk,
-                                                    int use_smem, int w_is_flag, int32_t* __restrict__ counts) {
+                                                    int use_smem, int w_is_flag, int32_t* __restrict__ counts,
+                                                    int S_all, int64_t* __restrict__ offsets_out) {
   pdl_prologue();
   extern __shared__ int32_t s_cnt[];
+  __shared__ long long s_scan[256];
+  __shared__ bool s_last;
   if (use_smem) {
     for (int t = threadIdx.x; t < b.S; t += blockDim.x) s_cnt[t] = 0;
     __syncthreads();
@@ -97,6 +100,35 @@ __global__ void __launch_bounds__(256) k_band_count(BandSet b, const float4* __r
       if (c) atomicAdd(counts + __ldg(b.slice + t), c);
     }
   }
+  if (!offsets_out) return;
+  // The LAST block to finish turns the S_all counts into the band offsets (exclusive scan, int64, total at [S_all])
+  // and zeroes the counts -- they are the fill pass's cursors -- and the ticket (counts[S_all]): no scan launch and no
+  // memset between the two passes of the band builder (each costs the chain ~10-20 us when the GPU is busy).
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd((unsigned*)(counts + S_all), 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int per = (S_all + (int)blockDim.x - 1) / (int)blockDim.x;
+  const int t0 = min((int)threadIdx.x * per, S_all), t1 = min(t0 + per, S_all);
+  long long sum = 0;
+  for (int t = t0; t < t1; t++) sum += ((const volatile int32_t*)counts)[t];
+  s_scan[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < (int)blockDim.x; o <<= 1) {     // inclusive scan of the per-thread sums (Hillis-Steele)
+    const long long v = (int)threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_scan[threadIdx.x] += v;
+    __syncthreads();
+  }
+  long long run = s_scan[threadIdx.x] - sum;
+  for (int t = t0; t < t1; t++) {
+    offsets_out[t] = run;
+    run += ((const volatile int32_t*)counts)[t];
+    counts[t] = 0;
+  }
+  if (threadIdx.x == blockDim.x - 1) { offsets_out[S_all] = s_scan[blockDim.x - 1]; counts[S_all] = 0; }
 }
 
 __global__ void __launch_bounds__(256) k_band_fill(BandSet b, const float4* __restrict__ xyz4, int64_t n, int64_t chunk,
@@ -867,18 +899,49 @@ struct NodeDest {
   int64_t* ext_off; int64_t ext_off_cap;
 };
 
-__global__ void __launch_bounds__(256) k_compact_nodes_auto(const int64_t* __restrict__ band_off, const int64_t* __restrict__ node_off,
+// n_nodes != nullptr: the node offsets are not known yet -- every block sums the node counts of the slices before its
+// own (and all of them) itself and stores its entry of node_off: for the few hundred to few thousand slices of a
+// sweep that is cheaper than one more launch in a chain whose every launch waits for a free SM slot.
+__global__ void __launch_bounds__(256) k_compact_nodes_auto(const int64_t* __restrict__ band_off, int64_t* __restrict__ node_off,
+                                                           const int32_t* __restrict__ n_nodes,
                                                            int S, const float* __restrict__ planes, const double* __restrict__ ty,
                                                            const double* __restrict__ tz, NodeDest D, int64_t* __restrict__ summary,
                                                            unsigned* __restrict__ host_out, unsigned* __restrict__ host_flag, unsigned seq) {
   pdl_prologue();
   __shared__ bool s_last;
+  __shared__ long long s_sum[2][8];
   const int s = blockIdx.x;
-  const int64_t total = node_off[S];
+  int64_t total, d;
+  int n;
+  if (n_nodes) {
+    long long before = 0, all = 0;
+    for (int t = threadIdx.x; t < S; t += blockDim.x) {
+      const long long v = n_nodes[t];
+      all += v;
+      if (t < s) before += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      before += __shfl_xor_sync(0xffffffffu, before, o);
+      all += __shfl_xor_sync(0xffffffffu, all, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_sum[0][threadIdx.x >> 5] = before; s_sum[1][threadIdx.x >> 5] = all; }
+    __syncthreads();
+    before = 0; all = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) { before += s_sum[0][w]; all += s_sum[1][w]; }
+    d = before; total = all; n = n_nodes[s];
+    if (threadIdx.x == 0) {
+      node_off[s] = d;
+      if (s == S - 1) node_off[S] = total;
+    }
+  } else {
+    total = node_off[S];
+    d = node_off[s];
+    n = (int)(node_off[s + 1] - d);
+  }
   const bool ext = D.ey && total <= D.ecap;
   double* y = ext ? D.ey : D.oy; double* x = ext ? D.ex : D.ox; double* z = ext ? D.ez : D.oz;
-  const int64_t so = band_off[s], d = node_off[s];
-  const int n = (int)(node_off[s + 1] - d);
+  const int64_t so = band_off[s];
   const double px = (double)planes[s];
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     y[d + i] = ty[so + i];
@@ -986,9 +1049,9 @@ static int bands_prepare(ppp_cloud* c, const float* plane_x_host, int S, float h
   }
   PPP_TRY(dev_alloc(ctx, &bp->fdev, 5 * (size_t)std::max(S, 1)));
   PPP_TRY(dev_alloc(ctx, &bp->pdev, (size_t)std::max(S, 1)));
-  PPP_TRY(dev_alloc(ctx, &bp->counts, (size_t)std::max(S, 1)));
+  PPP_TRY(dev_alloc(ctx, &bp->counts, (size_t)S + 1));     // [S]: the count kernel's ticket
   PPP_TRY(dev_alloc(ctx, &bp->offsets, (size_t)S + 1));
-  PPP_CUDA(cudaMemsetAsync(bp->counts, 0, (size_t)std::max(S, 1) * sizeof(int32_t), ctx->stream));
+  PPP_CUDA(cudaMemsetAsync(bp->counts, 0, ((size_t)S + 1) * sizeof(int32_t), ctx->stream));
   if (S > 0) {
     // pageable sources: the runtime stages them before returning, so the vectors may go out of scope
     PPP_CUDA(cudaMemcpyAsync(bp->fdev, stage.data(), stage.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -1011,12 +1074,13 @@ static int bands_prepare(ppp_cloud* c, const float* plane_x_host, int S, float h
   bp->blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((bp->n_src + 1023) / 1024, (int64_t)ctx->sm_count * 8));
   bp->chunk = (bp->n_src + bp->blocks - 1) / bp->blocks;
   if (bp->n_src > 0 && Sv > 0) {
+    // the kernel's last block also scans the counts into the offsets and zeroes them for the fill pass
     PPP_LAUNCH(ctx, "band_count", k_band_count, bp->blocks, 256, bp->use_smem ? (size_t)Sv * 4 : 0, bp->b, bp->src,
-               bp->n_src, bp->chunk, bp->use_smem, bp->w_is_flag, bp->counts);
+               bp->n_src, bp->chunk, bp->use_smem, bp->w_is_flag, bp->counts, S, (int64_t*)bp->offsets);
     PPP_CHECK_LAUNCH();
+    return PPP_OK;
   }
-  PPP_TRY(scan_exclusive_i32_to_i64(ctx, bp->counts, bp->offsets, S));
-  PPP_CUDA(cudaMemsetAsync(bp->counts, 0, (size_t)std::max(S, 1) * sizeof(int32_t), ctx->stream));
+  PPP_TRY(scan_exclusive_i32_to_i64(ctx, bp->counts, bp->offsets, S));   // no points or no valid plane: all zero
   return PPP_OK;
 }
 
@@ -1337,7 +1401,8 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
       PPP_TRY(dev_alloc_keep(ctx, &c->c_node_off, (size_t)S + 1));
       c->c_S_cap = S + 1;
     }
-    PPP_TRY(scan_exclusive_i32_to_i64(ctx, n_nodes, c->c_node_off, S));
+    const bool inline_scan = S <= 4096;   // the compaction kernel sums the node counts itself
+    if (!inline_scan) PPP_TRY(scan_exclusive_i32_to_i64(ctx, n_nodes, c->c_node_off, S));
     if (c->c_cap < Mb || !c->c_y) {   // cloud-owned result buffers that hold any possible total
       dev_free(ctx, c->c_y); dev_free(ctx, c->c_x); dev_free(ctx, c->c_z);
       c->c_y = c->c_x = c->c_z = nullptr; c->c_cap = 0;
@@ -1347,7 +1412,7 @@ int slice_contours_sect_async(ppp_cloud* c, const GridStore& gs, const float* pl
     NodeDest D{c->ext_y, c->ext_x, c->ext_z, c->ext_y ? c->ext_cap : 0, c->c_y, c->c_x, c->c_z, c->ext_off, c->ext_off_cap};
     const unsigned seq = ++ctx->fetch_seq ? ctx->fetch_seq : ++ctx->fetch_seq;
     PPP_LAUNCH(ctx, "compact_nodes", k_compact_nodes_auto, (unsigned)S, 256, 0, (const int64_t*)bp.offsets,
-               (const int64_t*)c->c_node_off, S, planes_dev, (const double*)ty, (const double*)tz, D, summary,
+               c->c_node_off, inline_scan ? (const int32_t*)n_nodes : (const int32_t*)nullptr, S, planes_dev, (const double*)ty, (const double*)tz, D, summary,
                (unsigned*)ctx->fetch_host, (unsigned*)fetch_flag(ctx), seq);
     PPP_CHECK_LAUNCH();
     int64_t h[4] = {0, 0, 0, 0};
