@@ -1916,7 +1916,7 @@ static int launch_search(ppp_cloud* c, SearchParams& P) {
     block = 32;
     smem = (size_t)std::max(P.cap, 1) * 8 * block;
   }
-  if (smem > 48 * 1024)
+  if (smem > 40 * 1024)
     PPP_CUDA(cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (P.nq > 0) {
     unsigned blocks = (unsigned)((P.nq + block - 1) / block);
@@ -1933,7 +1933,7 @@ static int launch_knn_fast_k(ppp_cloud* c, SearchParams& P) {
   auto kern = k_knn_fast<K, PB, RADIUS>;
   const int block = 128;
   size_t smem = (size_t)((K > 16 || RADIUS) ? (K > PB ? K : PB) : PB) * 8 * block;
-  if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem > 40 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   unsigned blocks = (unsigned)((P.nq + block - 1) / block);
   PPP_LAUNCH(ctx, RADIUS ? "radius_normals" : (P.normals ? "knn_normals" : "knn"), kern, blocks, block, smem, P);
   PPP_CHECK_LAUNCH();
@@ -2023,7 +2023,9 @@ static int launch_knn_fast(ppp_cloud* c, SearchParams& P) {
     // hand-over queries: one warp each, persistent warps (their number is only known on the device)
     P.use_redo = 1;
     size_t smem = (size_t)WARPQ_WARPS * 32 * P.cap * 8;
-    if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(k_knn_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (opt in from 40 KB of dynamic shared memory on: the kernels carry static arrays too -- k = 48 asks for exactly
+    // 48 KB here and was refused by the launch without it)
+    if (smem > 40 * 1024) PPP_CUDA(cudaFuncSetAttribute(k_knn_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned blocks = (unsigned)std::min<int64_t>((P.nq + WARPQ_WARPS - 1) / WARPQ_WARPS, (int64_t)ctx->sm_count * 8);
     PPP_LAUNCH(ctx, "knn_redo", k_knn_warp, blocks, WARPQ_WARPS * 32, smem, P);
     PPP_CHECK_LAUNCH();

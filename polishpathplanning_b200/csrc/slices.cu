@@ -1115,7 +1115,7 @@ int bands_launch(ppp_cloud* c, const float* plane_x_host, int S, float half_widt
       int64_t maxB = 0;
       for (int s = 0; s < S; s++) maxB = std::max(maxB, off_h[s + 1] - off_h[s]);
       int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(maxB, 1), 49152);  // <= 192 KB of int32
-      if (smem_cap * 4 > 48 * 1024)
+      if (smem_cap * 4 > 40 * 1024)
         PPP_CUDA(cudaFuncSetAttribute(k_band_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 4));
       PPP_LAUNCH(ctx, "band_sort", k_band_sort, (unsigned)S, 1024, (size_t)smem_cap * 4, (const int64_t*)offsets, idx,
                  smem_cap);
@@ -1161,7 +1161,7 @@ static int launch_slice_order(ppp_ctx* ctx, int S, int64_t band_est, bool expect
   const int64_t cap1 = C == 1 ? (int64_t)smem_cap : (int64_t)chunk_cap * C;
   const bool big = expect_big || band_est > cap1;   // a second launch takes the bands beyond cap1
   if (C == 1) {
-    if ((size_t)smem_cap * 8 > 48 * 1024)
+    if ((size_t)smem_cap * 8 > 40 * 1024)
       PPP_CUDA(cudaFuncSetAttribute(k_slice_order, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap * 8));
     // short bands: 256 threads sort them with a quarter of the barrier traffic, and more slices share an SM
     const int so_threads = smem_cap <= 4608 ? 256 : SO_THREADS;
@@ -1174,15 +1174,15 @@ static int launch_slice_order(ppp_ctx* ctx, int S, int64_t band_est, bool expect
     const unsigned grid = (unsigned)S * (unsigned)C;
     if (C == 2) {
       auto kern = k_slice_order_cl<2>;
-      if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 40 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       PPP_LAUNCH(ctx, "slice_order", kern, grid, SO_THREADS, smem, band_off, band_idx, sorted_if_pos, keys, ys, zs, scratch, chunk_cap, S, -1, max_B, ty, tz, n_nodes);
     } else if (C == 4) {
       auto kern = k_slice_order_cl<4>;
-      if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 40 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       PPP_LAUNCH(ctx, "slice_order", kern, grid, SO_THREADS, smem, band_off, band_idx, sorted_if_pos, keys, ys, zs, scratch, chunk_cap, S, -1, max_B, ty, tz, n_nodes);
     } else {
       auto kern = k_slice_order_cl<8>;
-      if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 40 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       PPP_LAUNCH(ctx, "slice_order", kern, grid, SO_THREADS, smem, band_off, band_idx, sorted_if_pos, keys, ys, zs, scratch, chunk_cap, S, -1, max_B, ty, tz, n_nodes);
     }
     PPP_CHECK_LAUNCH();
@@ -1292,7 +1292,7 @@ int contours_launch(ppp_cloud* c, const GridStore& gs, const float* planes_dev, 
       int smem_cap = (int)std::min<int64_t>(std::max<int64_t>(maxB, 2), 22000);  // 9 bytes per member, <= 198 KB
       size_t smem = 9 * (size_t)((smem_cap + 1) & ~1) + 16;
       auto kern = member_bits ? k_contour<true> : k_contour<false>;
-      if (smem > 48 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 40 * 1024) PPP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       PPP_LAUNCH(ctx, "contour_gen2", kern, (unsigned)S, 1024, smem, P, smem_cap);
       PPP_CHECK_LAUNCH();
     }

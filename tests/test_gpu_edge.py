@@ -643,3 +643,26 @@ def test_slice_order_thread_block_clusters(ctx, cluster, monkeypatch):
             o = oc.slice_contours(planes, "B", half_width=hw)
             assert all(np.array_equal(a, b) for a, b in zip(g, o)), (cluster, hw)
     gc.close()
+
+
+@pytest.mark.parametrize("k", [8, 16, 24, 32, 48, 64])
+def test_fixed_point_key_kernels_on_exact_ties_and_duplicates(ctx, k):
+    """The self-query search kernels order candidates by a 22/23-bit fixed-point d2 and hand every query whose
+    first k+1 candidates are not strictly separated by it to the exact kernel.  A lattice (every distance is tied
+    many times over), exact duplicates and a jittered copy (near-ties far below the fixed-point resolution) must
+    come out in the oracle's (d2, index) order, bit for bit -- lists and distances."""
+    g = np.arange(70, dtype=np.float32)
+    xx, yy = np.meshgrid(g, g, indexing="ij")
+    lattice = np.stack([xx.ravel(), yy.ravel(), np.zeros(xx.size, np.float32)], axis=1)          # 4900 points, spacing 1
+    rng = np.random.default_rng(17)
+    jitter = lattice[:1500] + np.float32(100.0) + rng.normal(0.0, 1e-4, (1500, 3)).astype(np.float32)
+    pts = np.concatenate([lattice, lattice[200:260], jitter], axis=0).astype(np.float32)          # + 60 exact duplicates
+    pts = pts[rng.permutation(pts.shape[0])]
+    c = synth.to_pointxyzrgb(pts) if hasattr(synth, "to_pointxyzrgb") else pts
+    gc = api.Cloud(ctx, c)
+    oc = po.OracleCloud(c)
+    gi, gd = gc.knn(k)
+    oi, od = oc.knn(k)
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(gi, oi)
+    gc.close()
